@@ -1,0 +1,219 @@
+/*
+ * b200vae.h -- C ABI of libb200vae.so, the sm_100a engine underneath
+ * rectorch_b200.{nets,models,samplers,evaluation,metrics}.
+ *
+ * The reference (makgyver/rectorch) is pure Python and has NO FFI of its own
+ * (SURVEY.md section 8b): the drop-in boundary is its Python class surface, which
+ * rectorch_b200 mirrors.  This header is the layer directly beneath that
+ * surface; every entry point names the reference code it replaces (file:line
+ * under /root/reference/rectorch) so a maintainer can see what a ctypes stub in
+ * rectorch itself would bind (INTEGRATION.md shows that stub).
+ *
+ * Conventions
+ *   - plain C types only; all `*_dev` / unqualified data pointers are DEVICE pointers
+ *     unless the name ends in `_host`.
+ *   - the caller owns every buffer it passes in (torch CUDA tensors in practice);
+ *     the library owns only the opaque context (workspaces, TMA descriptors).
+ *   - every call returns 0 on success or a negative B200VAE_E* code;
+ *     b200vae_last_error() returns a thread-local message.  There is no CPU
+ *     fallback anywhere: without a Blackwell GPU the calls fail.
+ *   - calls are asynchronous on the `stream` argument (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream) and are not thread-safe per context.
+ */
+#ifndef B200VAE_H
+#define B200VAE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200VAE_MAX_LAYERS 8
+
+#define B200VAE_OK            0
+#define B200VAE_EINVAL       -1   /* bad argument / unsupported shape            */
+#define B200VAE_ECUDA        -2   /* CUDA runtime / driver error                 */
+#define B200VAE_ESTATE       -3   /* call sequence error (params/CSR not bound)  */
+#define B200VAE_ECAPACITY    -4   /* batch or nnz exceeds the context capacity   */
+
+typedef struct b200vae_ctx b200vae_ctx;
+
+/* Network description == constructor arguments of
+ * MultiVAE_net(dec_dims, enc_dims, dropout) / MultiDAE_net(...)  (nets.py:208, 390).
+ * enc_dims[0] == dec_dims[n_dec] == n_items.  For is_vae the LAST encoder layer
+ * has 2*enc_dims[n_enc] outputs (nets.py:264). */
+typedef struct {
+    int32_t device;                          /* CUDA ordinal                                  */
+    int32_t is_vae;                          /* 1 = MultiVAE_net, 0 = MultiDAE_net            */
+    int32_t n_enc;                           /* number of encoder Linear layers               */
+    int32_t n_dec;                           /* number of decoder Linear layers               */
+    int32_t enc_dims[B200VAE_MAX_LAYERS + 1];
+    int32_t dec_dims[B200VAE_MAX_LAYERS + 1];
+    int32_t max_batch;                       /* rows per call, capacity                       */
+    int64_t max_batch_nnz;                   /* non-zeros per batch, capacity (input+target)  */
+    int32_t use_tensor_cores;                /* 1 = tcgen05 path for the item-sized GEMMs when
+                                                shapes allow (default), 0 = fp32 SIMT kernels */
+} b200vae_config;
+
+const char* b200vae_last_error(void);
+int  b200vae_version(void);
+
+int  b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg);
+int  b200vae_ctx_destroy(b200vae_ctx* ctx);
+
+/* Parameter / gradient / Adam-state arenas: four fp32 arrays of n_elems floats with
+ * the same internal layout.  Layer l (encoder layers first, then decoder) has its
+ * weight at w_off[l] and bias at b_off[l].  Weight layout is nn.Linear's (out,in)
+ * row-major EXCEPT encoder layer 0, which is stored item-major (in,out) = (n_items,H1)
+ * so that a user's history is a gather of contiguous rows; the Python side exposes it
+ * as a transposed nn.Parameter view (state_dict / checkpoints keep reference shapes,
+ * models.py:485-488).  Replaces: nn.Linear storage + torch.optim.Adam state. */
+int  b200vae_bind_params(b200vae_ctx* ctx, float* w, float* g, float* m, float* v,
+                         int64_t n_elems, const int64_t* w_off, const int64_t* b_off);
+
+/* Refresh the copies the engine derives from the weight arena (the tf32-rounded image of
+ * the decoder output weight that the tensor cores read).  b200vae_adam_step keeps them in
+ * step; call this after anything else wrote the arena (init_weights, load_state_dict,
+ * nets.py:235-247 / models.py:513). */
+int  b200vae_sync_weights(b200vae_ctx* ctx, void* stream);
+
+/* Device-side capacity-overflow flag (a batch had more non-zeros than max_batch_nnz).
+ * Synchronises the device; returns B200VAE_ECAPACITY once and clears the flag. */
+int  b200vae_check_error_flag(b200vae_ctx* ctx);
+
+/* AE_net.decode(z) (nets.py:227-233, 413-417): decoder layers on a caller-provided latent
+ * batch z [B x latent] -> scores [B x n_items]. */
+int  b200vae_decode(b200vae_ctx* ctx, const float* z, int32_t B, float* scores, void* stream);
+
+/* Bind a device-resident CSR user x item matrix (slot 0 = training/input matrix,
+ * slot 1 = target / held-out matrix).  values may be NULL (all ones).  Replaces the
+ * scipy matrices held by DataSampler (samplers.py:77-81). */
+int  b200vae_bind_csr(b200vae_ctx* ctx, int slot, const int64_t* indptr, const int32_t* indices,
+                      const float* values, int64_t n_rows);
+
+/* Compress a dense fp32 [B x n_items] device batch into the context's internal batch
+ * CSR for `slot` (used when a caller hands dense tensors to train_batch/predict like
+ * the reference does, models.py:441, 818-822).  After this call `row_ids == NULL`
+ * in the step functions means "the internal batch".  */
+int  b200vae_dense_to_csr(b200vae_ctx* ctx, int slot, const float* dense, int32_t B, void* stream);
+
+/* K1: CSR -> dense batch expander (DataSampler.__iter__, samplers.py:99-105).
+ * out[B x n_items] fp32; row_ids are rows of the bound CSR in `slot`. */
+int  b200vae_expand_batch(b200vae_ctx* ctx, int slot, const int32_t* row_ids, int32_t B,
+                          float* out, void* stream);
+
+/* One training step minus the optimizer: forward, loss, backward into the gradient
+ * arena (MultiVAE.train_batch models.py:817-832 / AETrainer.train_batch 441-445).
+ *   row_ids      rows of CSR slot 0 (and slot 1 when use_target) or NULL = internal batch
+ *   B_global     divisor of the batch mean (== B unless the batch is sharded over ranks)
+ *   beta         annealed KL weight (models.py:824-827); ignored for DAE
+ *   lam          MultiDAE norm-regulariser weight (models.py:702-706); 0 for VAE
+ *   dropout_p    nn.Dropout p (train mode)
+ *   seed/step    Philox key / counter for dropout + eps draws (production RNG)
+ *   keep_tape    optional uint8 per non-zero of the batch (1 = kept): parity mode, replaces Philox
+ *   eps_tape     optional [B x latent] N(0,1) draws: parity mode
+ *   loss_out     device float[4]: {loss, nll(BCE term), kld, reg}
+ */
+int  b200vae_forward_backward(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int32_t B_global,
+                              int use_target, float beta, float lam, float dropout_p,
+                              uint64_t seed, uint64_t step, int64_t row_offset,
+                              const uint8_t* keep_tape, const float* eps_tape,
+                              float* loss_out, void* stream);
+
+/* K8: fused Adam over the whole arena (torch.optim.Adam.step as configured at
+ * models.py:657-659 / 768-770), with the MultiDAE extras folded into the gradient read:
+ * g += lam * w/||w||_2 (per tensor) + weight_decay * w.  `step` is the 1-based count. */
+int  b200vae_adam_step(b200vae_ctx* ctx, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, float lam, int64_t step, void* stream);
+
+/* forward_backward + adam_step in one call (single-GPU fast path). */
+int  b200vae_train_step(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int use_target,
+                        float beta, float lam, float dropout_p, uint64_t seed, int64_t step,
+                        const uint8_t* keep_tape, const float* eps_tape,
+                        float lr, float beta1, float beta2, float eps, float weight_decay,
+                        float* loss_out, void* stream);
+
+/* End-to-end variant with HOST inputs (pinned or pageable): copies the batch CSR
+ * (indptr[B+1] int64 rebased to 0, indices int32, values fp32 or NULL) host->device,
+ * runs train_step, copies loss back to loss_host[4] and synchronises the stream. */
+int  b200vae_train_step_host(b200vae_ctx* ctx, const int64_t* indptr_host, const int32_t* indices_host,
+                             const float* values_host, int32_t B, float beta, float lam,
+                             float dropout_p, uint64_t seed, int64_t step, float lr,
+                             float weight_decay, float* loss_host, void* stream);
+
+/* K9: eval-mode forward (VAE.predict models.py:619-625 / AETrainer.predict 467-473).
+ * scores[B x n_items]; mu/logvar [B x latent] may be NULL.  remove_train sets the
+ * scores of the input's non-zeros to -inf.  `train_mode` != 0 runs the stochastic
+ * train-mode forward instead (net.forward()/encode() in training mode, nets.py:394-411). */
+int  b200vae_predict(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int remove_train,
+                     int train_mode, float dropout_p, uint64_t seed, uint64_t step,
+                     float* scores, float* mu, float* logvar, void* stream);
+
+/* K10: per-row top-K by radix select + ranking metrics against the held-out CSR
+ * (Metrics.recall_at_k/ndcg_at_k/hit_at_k/mrr_at_k, metrics.py:136-285).
+ *   scores   [B x n_items] device fp32
+ *   gt_row_ids rows of CSR slot 1, or NULL = internal batch of slot 1
+ *   kinds[i] 0=recall 1=ndcg 2=hit 3=mrr ; ks[i] = k ; out[n_metrics x B] fp32
+ *   topk_idx optional [B x kmax] int32 (sorted by score desc, ties by item id asc). */
+int  b200vae_topk_metrics(b200vae_ctx* ctx, const float* scores, const int32_t* gt_row_ids, int32_t B,
+                          const int32_t* kinds, const int32_t* ks, int32_t n_metrics,
+                          float* out, int32_t* topk_idx, void* stream);
+
+/* ---- context-free helpers (dense-tensor API surface of the reference) ------------------ */
+
+/* Same kernel as b200vae_topk_metrics on caller-provided device arrays: scores [B x n_items],
+ * ground truth as a batch-local CSR (indptr[B+1] starting at 0).  kinds/ks are DEVICE arrays;
+ * kmax = max_i min(ks[i], n_items).  Backs Metrics.compute(pred_scores, ground_truth, ...)
+ * (metrics.py:31-85). */
+int  b200vae_topk_metrics_csr(const float* scores, int32_t B, int32_t n_items, const int64_t* gt_indptr,
+                              const int32_t* gt_indices, const float* gt_values, const int32_t* kinds_dev,
+                              const int32_t* ks_dev, int32_t n_metrics, int32_t kmax, float* out,
+                              int32_t* topk_idx, void* stream);
+
+/* K1 without a context: out[B x n_items] = rows `row_ids` (NULL = 0..B-1) of a device CSR
+ * (DataSampler.__iter__, samplers.py:99-105). */
+int  b200vae_expand_rows_raw(const int64_t* indptr, const int32_t* indices, const float* values,
+                             const int32_t* row_ids, int32_t B, int32_t n_items, float* out, void* stream);
+
+/* dense [B x n_items] -> CSR in two phases: indices == NULL counts and scans into indptr
+ * (indptr[B] = nnz), a second call with buffers of >= cap entries fills them. */
+int  b200vae_dense_to_csr_raw(const float* dense, int32_t B, int32_t n_items, int64_t* lens_tmp,
+                              int64_t* indptr, int32_t* indices, float* values, int64_t cap, void* stream);
+
+/* out_rows[r] = -sum_j log_softmax(logits[r,:])_j * target[r,j]   (models.py:701, 813) */
+int  b200vae_multinomial_nll_rows(const float* logits, const float* target, int32_t B, int32_t n_items,
+                                  float* out_rows, void* stream);
+/* out_rows[r] = -0.5 * sum_l (1 + logvar - mu^2 - exp(logvar))      (models.py:814) */
+int  b200vae_kl_rows(const float* mu, const float* logvar, int32_t B, int32_t L, float* out_rows, void* stream);
+
+/* ---- per-kernel entry points (unit parity tests, ncu captures) ---------------------- */
+
+/* C[M x N] = A[M x K] * B^T  with tcgen05 TF32 (fp32 accumulate in TMEM).
+ * a_mn_major = 0: A is [M x K] row-major (K contiguous); 1: A is given as [K x M] (M contiguous)
+ * b_mn_major = 0: B is [N x K] row-major (K contiguous); 1: B is given as [K x N] (N contiguous)
+ * Leading dimensions in elements; must be multiples of 4; pointers 16-byte aligned. */
+int  b200vae_gemm_tf32(b200vae_ctx* ctx, const float* A, int64_t lda, int a_mn_major,
+                       const float* B, int64_t ldb, int b_mn_major,
+                       float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, void* stream);
+
+/* K4 standalone: lse[r] = log sum_j exp(h[r,:].W[j,:] + b[j]) for r < B without
+ * materialising the [B x n_items] logits (F.log_softmax over the decoder output,
+ * models.py:813 / nets.py:417).  h [B x H] row-major, W [n_items x H] row-major. */
+int  b200vae_dec_fwd_lse(b200vae_ctx* ctx, const float* h, const float* W, const float* bias,
+                         int32_t B, int32_t n_items, int32_t H, float* lse, void* stream);
+
+/* Introspection for bench.py: kernels launched by this context since the last reset. */
+int64_t b200vae_launch_count(b200vae_ctx* ctx, int reset);
+
+/* Time (ms) of the most recent execution of an instrumented kernel group, measured
+ * with CUDA events on the launching stream; which: 0 = decoder fwd (K4), 1 = Adam (K8),
+ * 2 = decoder bwd recompute (K5), 3 = dW_d GEMM, 4 = dh GEMM.  Enable with
+ * b200vae_set_timing(ctx, 1); values are valid after the stream is synchronised. */
+int  b200vae_set_timing(b200vae_ctx* ctx, int enable);
+float b200vae_kernel_ms(b200vae_ctx* ctx, int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VAE_H */

@@ -1,0 +1,193 @@
+// common.cuh -- shared declarations of the b200vae engine (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/b200vae.h"
+
+namespace b200 {
+
+void set_error(const char* fmt, ...);
+
+#define B200_CUDA_OK(expr)                                                            \
+    do {                                                                              \
+        cudaError_t _e = (expr);                                                      \
+        if (_e != cudaSuccess) {                                                      \
+            b200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,             \
+                            cudaGetErrorString(_e));                                  \
+            return B200VAE_ECUDA;                                                     \
+        }                                                                             \
+    } while (0)
+
+#define B200_CHECK(rc_expr)                                                           \
+    do {                                                                              \
+        int _rc = (rc_expr);                                                          \
+        if (_rc != 0) return _rc;                                                     \
+    } while (0)
+
+#define B200_REQUIRE(cond, code, ...)                                                 \
+    do {                                                                              \
+        if (!(cond)) {                                                                \
+            b200::set_error(__VA_ARGS__);                                             \
+            return (code);                                                            \
+        }                                                                             \
+    } while (0)
+
+static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
+
+// A batch of rows of a CSR matrix.  Row r of the batch is CSR row
+// (row_ids ? row_ids[r] : r); its non-zeros live at [indptr[gr], indptr[gr+1]).
+// `bp` [B+1] is the compact (batch-local) exclusive scan of the row lengths, so
+// per-non-zero batch arrays (scaled values, dropout keeps) are indexed bp[r]+k.
+struct BatchView {
+    const int64_t* indptr;
+    const int32_t* indices;
+    const float*   values;    // nullable -> 1.0f
+    const int32_t* row_ids;   // nullable -> identity
+    const int64_t* bp;        // [B+1]
+    int32_t        B;
+};
+
+struct Layer {
+    int in, out;              // nn.Linear(in, out)
+    int64_t w_off, b_off;     // offsets into the arenas
+    bool tanh_act;            // activation applied after this layer in the forward pass
+};
+
+// Epilogue description for the SIMT GEMM (simt_gemm.cu).
+enum { EPI_STORE = 0, EPI_LSE = 1, EPI_PROB = 2 };
+struct GemmEpi {
+    const float* bias = nullptr;      // per column n
+    int   act = 0;                    // 1 = tanh
+    const float* mulY = nullptr;      // out *= (1 - Y[m,n]^2)
+    int64_t ldy = 0;
+    float alpha = 1.f;
+    const float* addend = nullptr;    // out += addend_scale * addend[m,n]
+    int64_t ld_addend = 0;
+    float addend_scale = 0.f;
+    float* part_max = nullptr;        // EPI_LSE: [n_tiles x M]
+    float* part_sum = nullptr;
+    const float* lse = nullptr;       // EPI_PROB
+    const float* rowscale = nullptr;  // EPI_PROB: P = exp(logit - lse[m]) * rowscale[m]
+};
+
+struct Ctx;   // engine.cu
+
+// ---- kernel launchers (each returns a B200VAE_* code) -----------------------------------
+// sparse.cu
+int launch_batch_scan(Ctx* c, const int64_t* indptr, const int32_t* row_ids, int B, int64_t cap,
+                      int64_t* bp, cudaStream_t s);
+int launch_batch_prep(Ctx* c, const BatchView& in, float p, uint64_t seed, uint64_t step,
+                      int64_t row_offset, const uint8_t* keep_tape, bool train, float* xt,
+                      cudaStream_t s);
+int launch_row_sums(Ctx* c, const BatchView& v, float* out, cudaStream_t s);
+int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const float* Wt, int H,
+                       const float* bias, int act, float* out, cudaStream_t s);
+int launch_spmm_scatter(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
+                        int H, float* dWt, cudaStream_t s);
+int launch_bias_scatter(Ctx* c, const BatchView& v, float scale, float* db, cudaStream_t s);
+int launch_dense_count(Ctx* c, const float* dense, int B, int I, int64_t* lens, cudaStream_t s);
+int launch_dense_fill(Ctx* c, const float* dense, int B, int I, const int64_t* indptr,
+                      int32_t* indices, float* values, cudaStream_t s);
+int launch_scan_i64(Ctx* c, const int64_t* lens, int n, int64_t cap, int64_t* out, cudaStream_t s);
+int launch_expand(Ctx* c, const BatchView& v, int I, float* out, cudaStream_t s);
+int launch_mask_seen(Ctx* c, const BatchView& v, int I, float* scores, cudaStream_t s);
+int launch_row_loss(Ctx* c, const BatchView& tgt, const float* h, const float* gvec, int H,
+                    const float* bias, const float* lse, const float* T, float* loss_row,
+                    cudaStream_t s);
+
+// simt_gemm.cu
+int launch_simt_gemm(Ctx* c, int mode, const float* A, int64_t a_rs, int64_t a_cs, const float* B,
+                     int64_t b_rs, int64_t b_cs, float* C, int64_t ldc, int M, int N, int K,
+                     const GemmEpi& e, cudaStream_t s);
+int launch_colsum(Ctx* c, const float* X, int64_t ldx, int M, int N, float* out, cudaStream_t s);
+int launch_lse_merge(Ctx* c, const float* pmax, const float* psum, int n_tiles, int M, float* lse,
+                     cudaStream_t s);
+
+// elementwise.cu
+int launch_reparam_kl(Ctx* c, const float* enc_out, int B, int L, bool train, const float* eps_tape,
+                      uint64_t seed, uint64_t step, int64_t row_offset, const int32_t* row_ids,
+                      float* z, float* eps_out, float* kl_row, cudaStream_t s);
+int launch_dz_to_denc(Ctx* c, const float* dz, const float* enc_out, const float* eps, int B, int L,
+                      float beta_over_B, bool train, float* denc, cudaStream_t s);
+int launch_loss_final(Ctx* c, const float* loss_row, const float* kl_row, int B, float inv_Bg,
+                      float beta, float lam, const float* norms, int n_tensors, float* loss_out,
+                      cudaStream_t s);
+int launch_tensor_norms(Ctx* c, const float* w, const int64_t* offs, const int64_t* lens,
+                        int n_tensors, float* partial, float* norms, cudaStream_t s);
+int launch_adam(Ctx* c, float* w, const float* g, float* m, float* v, int64_t n, float lr_over_bc1,
+                float beta1, float beta2, float bc2_sqrt, float eps, float wd, float lam,
+                const float* norm_ptr, float* shadow, int64_t sh_lo, int64_t sh_hi, cudaStream_t s);
+int launch_round_tf32(Ctx* c, const float* x, float* y, int64_t n, cudaStream_t s);
+int launch_tanh_grad(Ctx* c, float* d, const float* y, int64_t n, cudaStream_t s);
+int launch_axpy(Ctx* c, float* y, const float* x, float a, int64_t n, cudaStream_t s);
+
+// topk.cu
+int launch_topk_metrics(Ctx* c, const float* scores, int I, const BatchView& gt, const int32_t* kinds,
+                        const int32_t* ks, int n_metrics, int kmax, float* out, int32_t* topk_idx,
+                        cudaStream_t s);
+
+// tc_gemm.cu  (tcgen05 / TMEM / TMA)
+enum { TC_EPI_STORE = 0, TC_EPI_LSE = 1, TC_EPI_PROB = 2 };
+struct TcEpi {
+    const float* bias = nullptr;       // per column
+    float* part_max = nullptr;         // TC_EPI_LSE partials [n_tiles_n x M]
+    float* part_sum = nullptr;
+    const float* lse = nullptr;        // TC_EPI_PROB
+    const float* rowscale = nullptr;
+    float* bias_grad = nullptr;        // TC_EPI_STORE: column `bias_col` of the product goes here
+    int bias_col = -1;
+    int split_k = 1;                   // TC_EPI_STORE: partial products C[s] at C + s*split_stride
+    int64_t split_stride = 0;
+};
+bool tc_supported(int M, int N, int K, int64_t lda, int64_t ldb);
+int launch_tc_gemm(Ctx* c, int mode, const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb,
+                   int b_mn, float* C, int64_t ldc, int M, int N, int K, const TcEpi& e,
+                   cudaStream_t s);
+int tc_lse_tiles(int N);
+int launch_splitk_reduce(Ctx* c, const float* parts, int n_split, int64_t split_stride, float* out,
+                         int64_t ld_out, int M, int N, int64_t ld_part, const float* addend,
+                         int64_t ld_add, float addend_scale, const float* mulY, int64_t ldy,
+                         cudaStream_t s);
+
+// ---- device helpers ----------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Philox4x32-10 (Salmon et al. 2011): counter (c0..c3), key (k0,k1).
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += W0;
+        k.y += W1;
+    }
+    return c;
+}
+// round-to-nearest fp32 -> tf32 (the tensor core itself truncates the low 13 mantissa bits,
+// which would bias every product towards zero; operands are pre-rounded instead)
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float u32_to_unit(uint32_t x) {   // (0,1]
+    return (float)(x >> 8) * (1.0f / 16777216.0f) + (0.5f / 16777216.0f);
+}
+#endif
+
+}  // namespace b200

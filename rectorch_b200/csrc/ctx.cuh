@@ -1,0 +1,84 @@
+// ctx.cuh -- the opaque engine context (workspaces + bound buffers).
+#pragma once
+#include "common.cuh"
+#include <vector>
+
+namespace b200 {
+
+struct CsrSlot {
+    const int64_t* indptr = nullptr;
+    const int32_t* indices = nullptr;
+    const float*   values = nullptr;
+    int64_t n_rows = 0;
+    // internal batch CSR (dense_to_csr / host staging); used when row_ids == NULL
+    int64_t* int_indptr = nullptr;   // [max_batch+1]
+    int32_t* int_indices = nullptr;  // [max_batch_nnz]
+    float*   int_values = nullptr;   // [max_batch_nnz]
+    bool     int_has_values = false;
+    int64_t* bp = nullptr;           // [max_batch+1] compact scan for the current batch
+};
+
+struct Ctx {
+    b200vae_config cfg;
+    int num_sms = 0;
+    int64_t launches = 0;
+    int n_items = 0, latent = 0;
+    std::vector<Layer> enc, dec;      // forward order
+    int n_tensors = 0;                // 2 * (n_enc + n_dec)
+    int max_width = 0;                // widest hidden activation
+
+    // arenas
+    float *w = nullptr, *g = nullptr, *m = nullptr, *v = nullptr;
+    int64_t n_elems = 0;
+    bool params_bound = false;
+
+    CsrSlot slot[2];
+
+    // workspaces (device)
+    float* xt = nullptr;              // [max_batch_nnz] scaled+dropped input values
+    float* T = nullptr;               // [B] target row sums
+    float* loss_row = nullptr;        // [B]
+    float* kl_row = nullptr;          // [B]
+    float* lse = nullptr;             // [B]
+    std::vector<float*> act_enc;      // per encoder layer output [B x out]
+    std::vector<float*> act_dec;      // per decoder layer output, except the last
+    float* z = nullptr;               // [B x latent]
+    float* eps = nullptr;             // [B x latent]
+    float* gvec = nullptr;            // [B x H_last]   sum_j t_uj W_d[j,:]
+    float* P = nullptr;               // [B x n_items]  softmax * T/B  (or its transpose)
+    float* hT = nullptr;              // [(H_last+8) x Bpad] transposed last hidden + ones row (tf32-rounded)
+    float* h_r = nullptr;             // [B x H_last] tf32-rounded copy of the last hidden activation
+    float* wd_shadow = nullptr;       // [n_items x H_last] tf32-rounded copy of W_d, maintained by Adam
+    int32_t* d_specs = nullptr;       // [128] metric specs for topk
+    float* dbuf[2] = {nullptr, nullptr};  // [B x max_width] ping-pong activation gradients
+    float* part_max = nullptr;        // [n_tiles x B]
+    float* part_sum = nullptr;
+    int    n_lse_tiles = 0;
+    float* splitk = nullptr;          // split-K partial products for dh
+    int64_t splitk_elems = 0;
+    float* norms = nullptr;           // [n_tensors]
+    float* norm_partial = nullptr;    // [n_tensors x 64]
+    int64_t* d_toff = nullptr;        // [n_tensors] tensor offsets (device copy)
+    int64_t* d_tlen = nullptr;
+    std::vector<int64_t> toff, tlen;  // host copies, parameters() order
+    float* loss_dev = nullptr;        // [4] scratch for train_step_host
+    int*   d_err = nullptr;           // device error flag (capacity overflow)
+    int64_t* lens_tmp = nullptr;      // [max_batch+1]
+
+    // timing instrumentation
+    bool timing = false;
+    cudaEvent_t ev[5][2];
+    bool ev_valid[5] = {false, false, false, false, false};
+
+    bool use_tc = true;
+    bool tc_dec = false;              // decoder-last shapes are tcgen05-eligible
+};
+
+inline void tick(Ctx* c, int which, int edge, cudaStream_t s) {
+    if (c->timing) {
+        cudaEventRecord(c->ev[which][edge], s);
+        if (edge == 1) c->ev_valid[which] = true;
+    }
+}
+
+}  // namespace b200

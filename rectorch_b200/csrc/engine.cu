@@ -1,0 +1,781 @@
+// engine.cu -- context management, step orchestration and the exported C ABI.
+//
+// Forward / backward structure follows the reference (file:line under
+// /root/reference/rectorch): nets.py:219-233 (MultiDAE_net), 394-417 (MultiVAE_net),
+// models.py:813-815 / 701-706 (losses), 441-446 / 817-835 (train_batch).  What differs is
+// the decomposition of the item-sized ends so that no [B x n_items] input or logits
+// tensor is ever materialised in the forward pass:
+//
+//   x~ . W1^T                  -> gather-sum of item-major W1 rows          (spmm_gather)
+//   sum_j log_softmax(l)_j t_j -> T*lse - h.(sum_j t_j W_d[j,:]) - sum_j t_j b_j
+//   dlogits = softmax*T/B - t/B: dense part through the GEMMs, sparse part by scatters
+#include <stdarg.h>
+#include <algorithm>
+#include <cmath>
+#include <new>
+#include "ctx.cuh"
+
+namespace b200 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+template <typename T>
+static int dmalloc(T** p, int64_t n) {
+    *p = nullptr;
+    if (n <= 0) n = 1;
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), (size_t)n * sizeof(T)));
+    return 0;
+}
+
+static void free_ctx(Ctx* c) {
+    auto F = [](void* p) { if (p) cudaFree(p); };
+    for (int s = 0; s < 2; ++s) {
+        F(c->slot[s].int_indptr); F(c->slot[s].int_indices); F(c->slot[s].int_values); F(c->slot[s].bp);
+    }
+    F(c->xt); F(c->T); F(c->loss_row); F(c->kl_row); F(c->lse);
+    for (float* p : c->act_enc) F(p);
+    for (float* p : c->act_dec) F(p);
+    F(c->z); F(c->eps); F(c->gvec); F(c->P); F(c->hT); F(c->dbuf[0]); F(c->dbuf[1]);
+    F(c->part_max); F(c->part_sum); F(c->splitk); F(c->norms); F(c->norm_partial);
+    F(c->d_toff); F(c->d_tlen); F(c->loss_dev); F(c->d_err); F(c->lens_tmp);
+    F(c->h_r); F(c->wd_shadow); F(c->d_specs);
+    for (int i = 0; i < 5; ++i)
+        for (int j = 0; j < 2; ++j) cudaEventDestroy(c->ev[i][j]);
+    delete c;
+}
+
+static int make_view(Ctx* c, int slot, const int32_t* row_ids, int B, BatchView* v, cudaStream_t s) {
+    CsrSlot& S = c->slot[slot];
+    v->B = B;
+    v->row_ids = row_ids;
+    if (row_ids) {
+        B200_REQUIRE(S.indptr != nullptr, B200VAE_ESTATE, "CSR slot %d is not bound", slot);
+        v->indptr = S.indptr;
+        v->indices = S.indices;
+        v->values = S.values;
+        v->bp = S.bp;
+        B200_CHECK(launch_batch_scan(c, S.indptr, row_ids, B, c->cfg.max_batch_nnz, S.bp, s));
+    } else {
+        v->indptr = S.int_indptr;
+        v->indices = S.int_indices;
+        v->values = S.int_has_values ? S.int_values : nullptr;
+        v->bp = S.int_indptr;   // the internal batch CSR is already compact
+    }
+    return 0;
+}
+
+// C = act(A * W^T + b) for an nn.Linear weight W [out x in] (row-major)
+static int linear_fwd(Ctx* c, const float* A, int B, const Layer& L, float* out, cudaStream_t s) {
+    GemmEpi e;
+    e.bias = c->w + L.b_off;
+    e.act = L.tanh_act ? 1 : 0;
+    return launch_simt_gemm(c, EPI_STORE, A, L.in, 1, c->w + L.w_off, 1, L.in, out, L.out, B, L.out, L.in, e, s);
+}
+
+// gradients of an nn.Linear (not encoder layer 0): dW = dY^T inp, db = colsum(dY),
+// dinp = (dY W) * tanh'(prev_out) if prev_out != NULL
+static int linear_bwd(Ctx* c, const float* dY, const float* inp, int B, const Layer& L, float* dinp,
+                      const float* prev_out, cudaStream_t s) {
+    GemmEpi e;
+    B200_CHECK(launch_simt_gemm(c, EPI_STORE, dY, 1, L.out, inp, L.in, 1, c->g + L.w_off, L.in, L.out, L.in, B, e, s));
+    B200_CHECK(launch_colsum(c, dY, L.out, B, L.out, c->g + L.b_off, s));
+    if (dinp) {
+        GemmEpi e2;
+        e2.mulY = prev_out;
+        e2.ldy = L.in;
+        B200_CHECK(launch_simt_gemm(c, EPI_STORE, dY, L.out, 1, c->w + L.w_off, L.in, 1, dinp, L.in, B, L.in, L.out, e2, s));
+    }
+    return 0;
+}
+
+struct FwdState {
+    BatchView in, tgt;
+    const float* h_last;      // input of the last decoder layer [B x H]
+    const float* h_last_tanh; // same pointer if that activation came out of a tanh, else NULL
+    int H;
+};
+
+// encoder + reparameterisation + hidden decoder layers.  Leaves z and h_last in the ctx.
+static int forward_hidden(Ctx* c, FwdState* st, int B, bool train, float p, uint64_t seed, uint64_t step,
+                          int64_t row_offset, const uint8_t* keep_tape, const float* eps_tape,
+                          cudaStream_t s) {
+    B200_CHECK(launch_batch_prep(c, st->in, p, seed, step, row_offset, keep_tape, train, c->xt, s));
+    const Layer& e0 = c->enc[0];
+    B200_CHECK(launch_spmm_gather(c, st->in, c->xt, c->w + e0.w_off, e0.out, c->w + e0.b_off,
+                                  e0.tanh_act ? 1 : 0, c->act_enc[0], s));
+    for (size_t i = 1; i < c->enc.size(); ++i)
+        B200_CHECK(linear_fwd(c, c->act_enc[i - 1], B, c->enc[i], c->act_enc[i], s));
+    const float* z;
+    const float* z_tanh = nullptr;
+    if (c->cfg.is_vae) {
+        B200_CHECK(launch_reparam_kl(c, c->act_enc.back(), B, c->latent, train, eps_tape, seed, step,
+                                     row_offset, st->in.row_ids, c->z, c->eps, c->kl_row, s));
+        z = c->z;
+    } else {
+        z = c->act_enc.back();
+        z_tanh = z;
+    }
+    const float* h = z;
+    const float* h_tanh = z_tanh;
+    for (size_t i = 0; i + 1 < c->dec.size(); ++i) {
+        B200_CHECK(linear_fwd(c, h, B, c->dec[i], c->act_dec[i], s));
+        h = c->act_dec[i];
+        h_tanh = h;
+    }
+    st->h_last = h;
+    st->h_last_tanh = h_tanh;
+    st->H = c->dec.back().in;
+    return 0;
+}
+
+// row-scale helper: rs[r] = T[r] * a
+__global__ void k_scale_rows(const float* __restrict__ T, float a, int B, float* __restrict__ rs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) rs[i] = T[i] * a;
+}
+
+// h [B x H] -> hT [(H+8) x Bp]: rows 0..H-1 = h^T, row H = 1 (bias-gradient column), rest 0.
+__global__ void k_transpose_ones(const float* __restrict__ h, int B, int H, int Bp, float* __restrict__ hT) {
+    __shared__ float tile[32][33];
+    int b0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+    int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        int b = b0 + i, hh = h0 + tx;
+        tile[i][tx] = (b < B && hh < H) ? tf32_rn(h[(int64_t)b * H + hh]) : ((hh == H && b < B) ? 1.f : 0.f);
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        int hh = h0 + i, b = b0 + tx;
+        if (hh < H + 8 && b < Bp) hT[(int64_t)hh * Bp + b] = tile[tx][i];
+    }
+}
+
+static int dec_lse(Ctx* c, const float* h, int B, int H, float* lse, cudaStream_t s) {
+    const Layer& L = c->dec.back();
+    const float* W = c->w + L.w_off;
+    const float* b = c->w + L.b_off;
+    int I = c->n_items;
+    if (c->tc_dec) {
+        // tensor-core operands: tf32-rounded copies (h_r made here, W_d shadow kept by Adam)
+        B200_CHECK(launch_round_tf32(c, h, c->h_r, (int64_t)B * H, s));
+        TcEpi e;
+        e.bias = b;
+        e.part_max = c->part_max;
+        e.part_sum = c->part_sum;
+        B200_CHECK(launch_tc_gemm(c, TC_EPI_LSE, c->h_r, H, 0, c->wd_shadow, H, 0, nullptr, 0, B, I, H, e, s));
+        B200_CHECK(launch_lse_merge(c, c->part_max, c->part_sum, tc_lse_tiles(I), B, lse, s));
+    } else {
+        GemmEpi e;
+        e.bias = b;
+        e.part_max = c->part_max;
+        e.part_sum = c->part_sum;
+        B200_CHECK(launch_simt_gemm(c, EPI_LSE, h, H, 1, W, 1, H, nullptr, 0, B, I, H, e, s));
+        B200_CHECK(launch_lse_merge(c, c->part_max, c->part_sum, (int)cdiv(I, 64), B, lse, s));
+    }
+    return 0;
+}
+
+static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int use_target, float beta,
+                            float lam, float p, uint64_t seed, uint64_t step, int64_t row_offset,
+                            const uint8_t* keep_tape, const float* eps_tape, float* loss_out,
+                            cudaStream_t s) {
+    B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
+    B200_REQUIRE(B >= 1 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
+    B200_REQUIRE(Bg >= B, B200VAE_EINVAL, "B_global (%d) < B (%d)", Bg, B);
+    const int I = c->n_items;
+    const float inv_Bg = 1.0f / (float)Bg;
+    FwdState st;
+    B200_CHECK(make_view(c, 0, row_ids, B, &st.in, s));
+    if (use_target) {
+        B200_CHECK(make_view(c, 1, row_ids, B, &st.tgt, s));
+    } else {
+        st.tgt = st.in;
+    }
+    // ---------------- forward ----------------
+    B200_CHECK(launch_row_sums(c, st.tgt, c->T, s));
+    B200_CHECK(forward_hidden(c, &st, B, true, p, seed, step, row_offset, keep_tape, eps_tape, s));
+    const Layer& DL = c->dec.back();
+    const int H = st.H;
+    const float* Wd = c->w + DL.w_off;
+    tick(c, 0, 0, s);
+    B200_CHECK(dec_lse(c, st.h_last, B, H, c->lse, s));
+    tick(c, 0, 1, s);
+    B200_CHECK(launch_spmm_gather(c, st.tgt, nullptr, Wd, H, nullptr, 0, c->gvec, s));
+    B200_CHECK(launch_row_loss(c, st.tgt, st.h_last, c->gvec, H, c->w + DL.b_off, c->lse, c->T, c->loss_row, s));
+    const bool dae_reg = (!c->cfg.is_vae) && lam != 0.f;
+    if (dae_reg)
+        B200_CHECK(launch_tensor_norms(c, c->w, c->d_toff, c->d_tlen, c->n_tensors, c->norm_partial, c->norms, s));
+    B200_CHECK(launch_loss_final(c, c->loss_row, c->cfg.is_vae ? c->kl_row : nullptr, B, inv_Bg,
+                                 c->cfg.is_vae ? beta : 0.f, dae_reg ? lam : 0.f,
+                                 dae_reg ? c->norms : nullptr, c->n_tensors, loss_out, s));
+
+    // ---------------- backward: decoder output layer ----------------
+    float* rowscale = c->loss_row;   // loss_row is consumed; reuse as T/Bg
+    k_scale_rows<<<(int)cdiv(B, 256), 256, 0, s>>>(c->T, inv_Bg, B, rowscale);
+    c->launches++;
+    float* dWd = c->g + DL.w_off;
+    float* dbd = c->g + DL.b_off;
+    float* d0 = c->dbuf[0];
+    float* d1 = c->dbuf[1];
+    if (c->tc_dec) {
+        // P^T [I x Bp] (item-major, users contiguous) from the recompute kernel
+        const int Bp = (int)round_up(B, 4);
+        TcEpi e;
+        e.bias = c->w + DL.b_off;
+        e.lse = c->lse;
+        e.rowscale = rowscale;
+        tick(c, 2, 0, s);
+        B200_CHECK(launch_tc_gemm(c, TC_EPI_PROB, c->h_r, H, 0, c->wd_shadow, H, 0, c->P, Bp, B, I, H, e, s));
+        tick(c, 2, 1, s);
+        // dW_d | db_d = P^T [I x B] * [h | 1]  : A = P^T (K-major), B = hT [(H+8) x Bp] (K-major)
+        dim3 tg((unsigned)cdiv(Bp, 32), (unsigned)cdiv(H + 8, 32));
+        k_transpose_ones<<<tg, dim3(32, 8), 0, s>>>(st.h_last, B, H, Bp, c->hT);
+        c->launches++;
+        TcEpi e2;
+        e2.bias_grad = dbd;
+        e2.bias_col = H;
+        tick(c, 3, 0, s);
+        B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->P, Bp, 0, c->hT, Bp, 0, dWd, H, I, H + 8, B, e2, s));
+        tick(c, 3, 1, s);
+        // dh = P W_d : A = P^T given as [K=I x M=Bp] (MN-major), B = W_d [K=I x N=H] (MN-major)
+        TcEpi e3;
+        int split = std::max(1, std::min(64, c->num_sms / (int)(cdiv(B, 128) * cdiv(H, 256))));
+        e3.split_k = split;
+        e3.split_stride = (int64_t)B * H;
+        B200_REQUIRE((int64_t)split * B * H <= c->splitk_elems, B200VAE_ECAPACITY, "split-K workspace too small");
+        tick(c, 4, 0, s);
+        B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->P, Bp, 1, c->wd_shadow, H, 1, c->splitk, H, B, H, I, e3, s));
+        B200_CHECK(launch_splitk_reduce(c, c->splitk, split, e3.split_stride, d0, H, B, H, H, c->gvec, H,
+                                        -inv_Bg, st.h_last_tanh, H, s));
+        tick(c, 4, 1, s);
+    } else {
+        GemmEpi e;
+        e.bias = c->w + DL.b_off;
+        e.lse = c->lse;
+        e.rowscale = rowscale;
+        tick(c, 2, 0, s);
+        B200_CHECK(launch_simt_gemm(c, EPI_PROB, st.h_last, H, 1, Wd, 1, H, c->P, I, B, I, H, e, s));
+        tick(c, 2, 1, s);
+        GemmEpi e2;
+        tick(c, 3, 0, s);
+        B200_CHECK(launch_simt_gemm(c, EPI_STORE, c->P, 1, I, st.h_last, H, 1, dWd, H, I, H, B, e2, s));
+        B200_CHECK(launch_colsum(c, c->P, I, B, I, dbd, s));
+        tick(c, 3, 1, s);
+        GemmEpi e3;
+        e3.addend = c->gvec;
+        e3.ld_addend = H;
+        e3.addend_scale = -inv_Bg;
+        e3.mulY = st.h_last_tanh;
+        e3.ldy = H;
+        tick(c, 4, 0, s);
+        B200_CHECK(launch_simt_gemm(c, EPI_STORE, c->P, I, 1, Wd, H, 1, d0, H, B, H, I, e3, s));
+        tick(c, 4, 1, s);
+    }
+    // sparse part of dlogits = -t/Bg
+    B200_CHECK(launch_spmm_scatter(c, st.tgt, nullptr, -inv_Bg, st.h_last, H, dWd, s));
+    B200_CHECK(launch_bias_scatter(c, st.tgt, -inv_Bg, dbd, s));
+
+    // ---------------- backward: hidden decoder layers ----------------
+    // invariant: `cur` holds d(loss)/d(pre-activation of the layer below the one being processed)
+    float* cur = d0;
+    float* nxt = d1;
+    const float* z_tanh = c->cfg.is_vae ? nullptr : c->act_enc.back();
+    const float* z = c->cfg.is_vae ? c->z : c->act_enc.back();
+    for (int i = (int)c->dec.size() - 2; i >= 0; --i) {
+        const float* inp = (i == 0) ? z : c->act_dec[i - 1];
+        const float* prev_tanh = (i == 0) ? z_tanh : c->act_dec[i - 1];
+        B200_CHECK(linear_bwd(c, cur, inp, B, c->dec[i], nxt, prev_tanh, s));
+        std::swap(cur, nxt);
+    }
+    if (c->cfg.is_vae) {
+        B200_CHECK(launch_dz_to_denc(c, cur, c->act_enc.back(), c->eps, B, c->latent, beta * inv_Bg, true, nxt, s));
+        std::swap(cur, nxt);
+    }
+    // ---------------- backward: encoder ----------------
+    for (int i = (int)c->enc.size() - 1; i >= 1; --i) {
+        const float* inp = c->act_enc[i - 1];
+        const float* prev_tanh = c->enc[i - 1].tanh_act ? c->act_enc[i - 1] : nullptr;
+        B200_CHECK(linear_bwd(c, cur, inp, B, c->enc[i], nxt, prev_tanh, s));
+        std::swap(cur, nxt);
+    }
+    const Layer& e0 = c->enc[0];
+    B200_CUDA_OK(cudaMemsetAsync(c->g + e0.w_off, 0, (size_t)I * e0.out * sizeof(float), s));
+    B200_CHECK(launch_spmm_scatter(c, st.in, c->xt, 1.0f, cur, e0.out, c->g + e0.w_off, s));
+    B200_CHECK(launch_colsum(c, cur, e0.out, B, e0.out, c->g + e0.b_off, s));
+    return 0;
+}
+
+static int adam_step(Ctx* c, float lr, float beta1, float beta2, float eps, float wd, float lam,
+                     int64_t step, cudaStream_t s) {
+    B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
+    B200_REQUIRE(step >= 1, B200VAE_EINVAL, "adam step must be >= 1");
+    double bc1 = 1.0 - std::pow((double)beta1, (double)step);
+    double bc2 = 1.0 - std::pow((double)beta2, (double)step);
+    float step_size = (float)((double)lr / bc1);
+    float bc2_sqrt = (float)std::sqrt(bc2);
+    tick(c, 1, 0, s);
+    const Layer& DL = c->dec.back();
+    float* shadow = c->tc_dec ? c->wd_shadow : nullptr;
+    const int64_t sh_lo = DL.w_off, sh_hi = DL.w_off + (int64_t)DL.in * DL.out;
+    if (wd == 0.f && lam == 0.f) {
+        B200_CHECK(launch_adam(c, c->w, c->g, c->m, c->v, c->n_elems, step_size, beta1, beta2, bc2_sqrt, eps, 0.f, 0.f, nullptr,
+                               shadow, sh_lo, sh_hi, s));
+    } else {
+        if (lam != 0.f)
+            B200_CHECK(launch_tensor_norms(c, c->w, c->d_toff, c->d_tlen, c->n_tensors, c->norm_partial, c->norms, s));
+        for (int t = 0; t < c->n_tensors; ++t) {
+            int64_t o = c->toff[t];
+            const bool is_wd = (o == DL.w_off);
+            B200_CHECK(launch_adam(c, c->w + o, c->g + o, c->m + o, c->v + o, c->tlen[t], step_size, beta1,
+                                   beta2, bc2_sqrt, eps, wd, lam, lam != 0.f ? c->norms + t : nullptr,
+                                   is_wd ? shadow : nullptr, 0, is_wd ? c->tlen[t] : 0, s));
+        }
+    }
+    tick(c, 1, 1, s);
+    return 0;
+}
+
+static int predict(Ctx* c, const int32_t* row_ids, int B, int remove_train, int train_mode, float p,
+                   uint64_t seed, uint64_t step, float* scores, float* mu, float* logvar, cudaStream_t s) {
+    B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
+    B200_REQUIRE(B >= 1 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
+    FwdState st;
+    B200_CHECK(make_view(c, 0, row_ids, B, &st.in, s));
+    st.tgt = st.in;
+    B200_CHECK(forward_hidden(c, &st, B, train_mode != 0, p, seed, step, 0, nullptr, nullptr, s));
+    const int L = c->latent, I = c->n_items;
+    if (c->cfg.is_vae) {
+        const float* eo = c->act_enc.back();
+        if (mu) B200_CUDA_OK(cudaMemcpy2DAsync(mu, L * sizeof(float), eo, 2 * L * sizeof(float), L * sizeof(float), B, cudaMemcpyDeviceToDevice, s));
+        if (logvar) B200_CUDA_OK(cudaMemcpy2DAsync(logvar, L * sizeof(float), eo + L, 2 * L * sizeof(float), L * sizeof(float), B, cudaMemcpyDeviceToDevice, s));
+    } else if (mu) {   // DAE: `mu` receives the encoder output (AE_net.encode)
+        B200_CUDA_OK(cudaMemcpyAsync(mu, c->act_enc.back(), (size_t)B * L * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    if (!scores) return 0;
+    const Layer& DL = c->dec.back();
+    if (c->tc_dec) {
+        TcEpi e;
+        e.bias = c->w + DL.b_off;
+        B200_CHECK(launch_round_tf32(c, st.h_last, c->h_r, (int64_t)B * st.H, s));
+        B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->h_r, st.H, 0, c->wd_shadow, st.H, 0, scores, I, B, I, st.H, e, s));
+    } else {
+        B200_CHECK(linear_fwd(c, st.h_last, B, DL, scores, s));
+    }
+    if (remove_train) B200_CHECK(launch_mask_seen(c, st.in, I, scores, s));
+    return 0;
+}
+
+}  // namespace b200
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+using namespace b200;
+
+extern "C" {
+
+const char* b200vae_last_error(void) { return g_err; }
+int b200vae_version(void) { return 100; }
+
+int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
+    B200_REQUIRE(out && cfg, B200VAE_EINVAL, "null argument");
+    *out = nullptr;
+    B200_REQUIRE(cfg->n_enc >= 1 && cfg->n_enc <= B200VAE_MAX_LAYERS && cfg->n_dec >= 1 && cfg->n_dec <= B200VAE_MAX_LAYERS,
+                 B200VAE_EINVAL, "layer counts out of range");
+    B200_REQUIRE(cfg->max_batch >= 1 && cfg->max_batch_nnz >= 1, B200VAE_EINVAL, "capacities must be positive");
+    int ndev = 0;
+    B200_CUDA_OK(cudaGetDeviceCount(&ndev));
+    B200_REQUIRE(cfg->device >= 0 && cfg->device < ndev, B200VAE_EINVAL, "no such CUDA device %d", cfg->device);
+    B200_CUDA_OK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    B200_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+    B200_REQUIRE(prop.major == 10, B200VAE_ECUDA,
+                 "b200vae is built for sm_100a (Blackwell) only; device %d is sm_%d%d", cfg->device, prop.major, prop.minor);
+    Ctx* c = new (std::nothrow) Ctx();
+    B200_REQUIRE(c, B200VAE_ECUDA, "out of host memory");
+    c->cfg = *cfg;
+    c->num_sms = prop.multiProcessorCount;
+    c->n_items = cfg->enc_dims[0];
+    c->latent = cfg->dec_dims[0];
+    c->use_tc = cfg->use_tensor_cores != 0;
+    for (int i = 0; i < 5; ++i)
+        for (int j = 0; j < 2; ++j) cudaEventCreate(&c->ev[i][j]);
+    if (cfg->dec_dims[cfg->n_dec] != c->n_items || cfg->enc_dims[cfg->n_enc] != c->latent) {
+        set_error("enc_dims/dec_dims are inconsistent (n_items %d vs %d, latent %d vs %d)", c->n_items,
+                  cfg->dec_dims[cfg->n_dec], cfg->enc_dims[cfg->n_enc], c->latent);
+        free_ctx(c);
+        return B200VAE_EINVAL;
+    }
+    for (int i = 0; i < cfg->n_enc; ++i) {
+        Layer L;
+        L.in = cfg->enc_dims[i];
+        L.out = cfg->enc_dims[i + 1];
+        L.tanh_act = true;
+        if (cfg->is_vae && i == cfg->n_enc - 1) { L.out *= 2; L.tanh_act = false; }
+        L.w_off = L.b_off = -1;
+        c->enc.push_back(L);
+    }
+    for (int i = 0; i < cfg->n_dec; ++i) {
+        Layer L;
+        L.in = cfg->dec_dims[i];
+        L.out = cfg->dec_dims[i + 1];
+        L.tanh_act = (i != cfg->n_dec - 1);
+        L.w_off = L.b_off = -1;
+        c->dec.push_back(L);
+    }
+    c->n_tensors = 2 * (cfg->n_enc + cfg->n_dec);
+    c->max_width = 1;
+    for (auto& L : c->enc) c->max_width = std::max(c->max_width, L.out);
+    for (size_t i = 0; i + 1 < c->dec.size(); ++i) c->max_width = std::max(c->max_width, c->dec[i].out);
+    c->max_width = std::max(c->max_width, c->latent);
+
+    const int64_t Bm = cfg->max_batch, I = c->n_items, nnz = cfg->max_batch_nnz;
+    const int H = c->dec.back().in;
+    const int64_t Bp = round_up(Bm, 4);
+    c->tc_dec = c->use_tc && tc_supported((int)Bm, (int)I, H, H, H) && (I >= 1024);
+    int rc = 0;
+#define A_(expr) do { if (!rc) rc = (expr); } while (0)
+    for (int s = 0; s < 2; ++s) {
+        A_(dmalloc(&c->slot[s].int_indptr, Bm + 1));
+        A_(dmalloc(&c->slot[s].int_indices, nnz));
+        A_(dmalloc(&c->slot[s].int_values, nnz));
+        A_(dmalloc(&c->slot[s].bp, Bm + 1));
+    }
+    A_(dmalloc(&c->xt, nnz));
+    A_(dmalloc(&c->T, Bm)); A_(dmalloc(&c->loss_row, Bm)); A_(dmalloc(&c->kl_row, Bm)); A_(dmalloc(&c->lse, Bm));
+    for (auto& L : c->enc) { float* p = nullptr; A_(dmalloc(&p, Bm * L.out)); c->act_enc.push_back(p); }
+    for (size_t i = 0; i + 1 < c->dec.size(); ++i) { float* p = nullptr; A_(dmalloc(&p, Bm * c->dec[i].out)); c->act_dec.push_back(p); }
+    A_(dmalloc(&c->z, Bm * c->latent)); A_(dmalloc(&c->eps, Bm * c->latent));
+    A_(dmalloc(&c->gvec, Bm * H));
+    A_(dmalloc(&c->P, Bp * I));
+    A_(dmalloc(&c->hT, (int64_t)(H + 8) * Bp));
+    A_(dmalloc(&c->h_r, Bm * H));
+    A_(dmalloc(&c->wd_shadow, c->tc_dec ? I * H : 1));
+    A_(dmalloc(&c->d_specs, 128));
+    A_(dmalloc(&c->dbuf[0], Bm * c->max_width)); A_(dmalloc(&c->dbuf[1], Bm * c->max_width));
+    c->n_lse_tiles = (int)std::max<int64_t>(cdiv(I, 64), 1);
+    A_(dmalloc(&c->part_max, (int64_t)c->n_lse_tiles * Bm)); A_(dmalloc(&c->part_sum, (int64_t)c->n_lse_tiles * Bm));
+    c->splitk_elems = c->tc_dec ? (int64_t)64 * Bm * H : 1;
+    A_(dmalloc(&c->splitk, c->splitk_elems));
+    A_(dmalloc(&c->norms, c->n_tensors)); A_(dmalloc(&c->norm_partial, (int64_t)c->n_tensors * 64));
+    A_(dmalloc(&c->d_toff, c->n_tensors)); A_(dmalloc(&c->d_tlen, c->n_tensors));
+    A_(dmalloc(&c->loss_dev, 4)); A_(dmalloc(&c->d_err, 1)); A_(dmalloc(&c->lens_tmp, Bm + 1));
+#undef A_
+    if (!rc && cudaMemset(c->d_err, 0, sizeof(int)) != cudaSuccess) rc = B200VAE_ECUDA;
+    if (rc) { free_ctx(c); return rc; }
+    *out = reinterpret_cast<b200vae_ctx*>(c);
+    return 0;
+}
+
+int b200vae_ctx_destroy(b200vae_ctx* ctx) {
+    if (!ctx) return 0;
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    cudaSetDevice(c->cfg.device);
+    cudaDeviceSynchronize();
+    free_ctx(c);
+    return 0;
+}
+
+int b200vae_bind_params(b200vae_ctx* ctx, float* w, float* g, float* m, float* v, int64_t n_elems,
+                        const int64_t* w_off, const int64_t* b_off) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    B200_REQUIRE(c && w && g && m && v && w_off && b_off, B200VAE_EINVAL, "null argument");
+    c->w = w; c->g = g; c->m = m; c->v = v; c->n_elems = n_elems;
+    c->toff.clear(); c->tlen.clear();
+    size_t nl = c->enc.size() + c->dec.size();
+    for (size_t l = 0; l < nl; ++l) {
+        Layer& L = (l < c->enc.size()) ? c->enc[l] : c->dec[l - c->enc.size()];
+        L.w_off = w_off[l];
+        L.b_off = b_off[l];
+        int64_t wl = (int64_t)L.in * L.out;
+        B200_REQUIRE(L.w_off >= 0 && L.w_off + wl <= n_elems && L.b_off >= 0 && L.b_off + L.out <= n_elems,
+                     B200VAE_EINVAL, "layer %zu offsets fall outside the arena", l);
+        B200_REQUIRE(L.w_off % 4 == 0 && L.b_off % 4 == 0, B200VAE_EINVAL, "layer %zu offsets must be multiples of 4 floats", l);
+        c->toff.push_back(L.w_off); c->tlen.push_back(wl);
+        c->toff.push_back(L.b_off); c->tlen.push_back(L.out);
+    }
+    B200_CUDA_OK(cudaMemcpy(c->d_toff, c->toff.data(), c->toff.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    B200_CUDA_OK(cudaMemcpy(c->d_tlen, c->tlen.data(), c->tlen.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    c->params_bound = true;
+    return b200vae_sync_weights(ctx, nullptr);
+}
+
+int b200vae_bind_csr(b200vae_ctx* ctx, int slot, const int64_t* indptr, const int32_t* indices,
+                     const float* values, int64_t n_rows) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    B200_REQUIRE(c && (slot == 0 || slot == 1), B200VAE_EINVAL, "bad slot");
+    B200_REQUIRE(indptr && (indices || n_rows == 0), B200VAE_EINVAL, "null CSR arrays");
+    c->slot[slot].indptr = indptr;
+    c->slot[slot].indices = indices;
+    c->slot[slot].values = values;
+    c->slot[slot].n_rows = n_rows;
+    return 0;
+}
+
+int b200vae_dense_to_csr(b200vae_ctx* ctx, int slot, const float* dense, int32_t B, void* stream) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    cudaStream_t s = (cudaStream_t)stream;
+    B200_REQUIRE(c && dense && (slot == 0 || slot == 1), B200VAE_EINVAL, "bad argument");
+    B200_REQUIRE(B >= 1 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
+    CsrSlot& S = c->slot[slot];
+    B200_CHECK(launch_dense_count(c, dense, B, c->n_items, c->lens_tmp, s));
+    B200_CHECK(launch_scan_i64(c, c->lens_tmp, B, c->cfg.max_batch_nnz, S.int_indptr, s));
+    B200_CHECK(launch_dense_fill(c, dense, B, c->n_items, S.int_indptr, S.int_indices, S.int_values, s));
+    S.int_has_values = true;
+    return 0;
+}
+
+int b200vae_expand_batch(b200vae_ctx* ctx, int slot, const int32_t* row_ids, int32_t B, float* out, void* stream) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    cudaStream_t s = (cudaStream_t)stream;
+    B200_REQUIRE(c && out && (slot == 0 || slot == 1), B200VAE_EINVAL, "bad argument");
+    B200_REQUIRE(B >= 0 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
+    if (B == 0) return 0;
+    BatchView v;
+    B200_CHECK(make_view(c, slot, row_ids, B, &v, s));
+    return launch_expand(c, v, c->n_items, out, s);
+}
+
+int b200vae_forward_backward(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int32_t B_global,
+                             int use_target, float beta, float lam, float dropout_p, uint64_t seed,
+                             uint64_t step, int64_t row_offset, const uint8_t* keep_tape,
+                             const float* eps_tape, float* loss_out, void* stream) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    B200_REQUIRE(c && loss_out, B200VAE_EINVAL, "null argument");
+    B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, B200VAE_EINVAL, "dropout_p must be in [0,1)");
+    return forward_backward(c, row_ids, B, B_global, use_target, beta, lam, dropout_p, seed, step, row_offset,
+                            keep_tape, eps_tape, loss_out, (cudaStream_t)stream);
+}
+
+int b200vae_sync_weights(b200vae_ctx* ctx, void* stream) {
+    // refresh every derived copy of the parameters (the tf32 image of W_d read by the tensor cores);
+    // call after the weight arena was modified by anything other than b200vae_adam_step
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    B200_REQUIRE(c && c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
+    if (!c->tc_dec) return 0;
+    const Layer& DL = c->dec.back();
+    return launch_round_tf32(c, c->w + DL.w_off, c->wd_shadow, (int64_t)DL.in * DL.out, (cudaStream_t)stream);
+}
+
+int b200vae_adam_step(b200vae_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay,
+                      float lam, int64_t step, void* stream) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    B200_REQUIRE(c, B200VAE_EINVAL, "null context");
+    return adam_step(c, lr, beta1, beta2, eps, weight_decay, lam, step, (cudaStream_t)stream);
+}
+
+int b200vae_train_step(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int use_target, float beta,
+                       float lam, float dropout_p, uint64_t seed, int64_t step, const uint8_t* keep_tape,
+                       const float* eps_tape, float lr, float beta1, float beta2, float eps, float weight_decay,
+                       float* loss_out, void* stream) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    B200_REQUIRE(c && loss_out, B200VAE_EINVAL, "null argument");
+    B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, B200VAE_EINVAL, "dropout_p must be in [0,1)");
+    B200_CHECK(forward_backward(c, row_ids, B, B, use_target, beta, lam, dropout_p, seed, (uint64_t)step, 0,
+                                keep_tape, eps_tape, loss_out, (cudaStream_t)stream));
+    return adam_step(c, lr, beta1, beta2, eps, weight_decay, lam, step, (cudaStream_t)stream);
+}
+
+// ---- context-free helpers used by rectorch_b200.metrics / models.loss_function ---------------
+static Ctx* null_ctx() {
+    static Ctx nc;
+    static bool init = false;
+    if (!init) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) nc.num_sms = prop.multiProcessorCount;
+        nc.cfg.max_batch_nnz = INT64_MAX;
+        cudaMalloc(reinterpret_cast<void**>(&nc.d_err), sizeof(int));
+        cudaMemset(nc.d_err, 0, sizeof(int));
+        init = true;
+    }
+    return &nc;
+}
+
+int b200vae_topk_metrics_csr(const float* scores, int32_t B, int32_t n_items, const int64_t* gt_indptr,
+                             const int32_t* gt_indices, const float* gt_values, const int32_t* kinds_dev,
+                             const int32_t* ks_dev, int32_t n_metrics, int32_t kmax, float* out,
+                             int32_t* topk_idx, void* stream) {
+    B200_REQUIRE(scores && gt_indptr && kinds_dev && ks_dev && out && B >= 1, B200VAE_EINVAL, "bad argument");
+    BatchView gt;
+    gt.indptr = gt_indptr; gt.indices = gt_indices; gt.values = gt_values; gt.row_ids = nullptr; gt.bp = gt_indptr; gt.B = B;
+    return launch_topk_metrics(null_ctx(), scores, n_items, gt, kinds_dev, ks_dev, n_metrics, kmax, out, topk_idx,
+                               (cudaStream_t)stream);
+}
+
+int b200vae_expand_rows_raw(const int64_t* indptr, const int32_t* indices, const float* values,
+                            const int32_t* row_ids, int32_t B, int32_t n_items, float* out, void* stream) {
+    B200_REQUIRE(indptr && out && B >= 0, B200VAE_EINVAL, "bad argument");
+    if (B == 0) return 0;
+    BatchView v;
+    v.indptr = indptr; v.indices = indices; v.values = values; v.row_ids = row_ids; v.bp = nullptr; v.B = B;
+    return launch_expand(null_ctx(), v, n_items, out, (cudaStream_t)stream);
+}
+
+int b200vae_dense_to_csr_raw(const float* dense, int32_t B, int32_t n_items, int64_t* lens_tmp, int64_t* indptr,
+                             int32_t* indices, float* values, int64_t cap, void* stream) {
+    // two-phase: indices == NULL -> only count + scan (indptr[B] = nnz); else fill
+    cudaStream_t s = (cudaStream_t)stream;
+    Ctx* c = null_ctx();
+    B200_REQUIRE(dense && indptr && lens_tmp && B >= 1, B200VAE_EINVAL, "bad argument");
+    if (!indices) {
+        B200_CHECK(launch_dense_count(c, dense, B, n_items, lens_tmp, s));
+        return launch_scan_i64(c, lens_tmp, B, INT64_MAX, indptr, s);
+    }
+    // dense_fill reads the capacity from the context
+    c->cfg.max_batch_nnz = cap;
+    int rc = launch_dense_fill(c, dense, B, n_items, indptr, indices, values, s);
+    c->cfg.max_batch_nnz = INT64_MAX;
+    return rc;
+}
+
+
+
+int b200vae_train_step_host(b200vae_ctx* ctx, const int64_t* indptr_host, const int32_t* indices_host,
+                            const float* values_host, int32_t B, float beta, float lam, float dropout_p,
+                            uint64_t seed, int64_t step, float lr, float weight_decay, float* loss_host,
+                            void* stream) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    cudaStream_t s = (cudaStream_t)stream;
+    B200_REQUIRE(c && indptr_host && indices_host && loss_host, B200VAE_EINVAL, "null argument");
+    B200_REQUIRE(B >= 1 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
+    int64_t nnz = indptr_host[B];
+    B200_REQUIRE(indptr_host[0] == 0 && nnz >= 0 && nnz <= c->cfg.max_batch_nnz, B200VAE_ECAPACITY,
+                 "batch nnz %lld exceeds capacity %lld", (long long)nnz, (long long)c->cfg.max_batch_nnz);
+    CsrSlot& S = c->slot[0];
+    B200_CUDA_OK(cudaMemcpyAsync(S.int_indptr, indptr_host, (size_t)(B + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    B200_CUDA_OK(cudaMemcpyAsync(S.int_indices, indices_host, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (values_host)
+        B200_CUDA_OK(cudaMemcpyAsync(S.int_values, values_host, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, s));
+    S.int_has_values = values_host != nullptr;
+    B200_CHECK(forward_backward(c, nullptr, B, B, 0, beta, lam, dropout_p, seed, (uint64_t)step, 0, nullptr, nullptr, c->loss_dev, s));
+    B200_CHECK(adam_step(c, lr, 0.9f, 0.999f, 1e-8f, weight_decay, lam, step, s));
+    B200_CUDA_OK(cudaMemcpyAsync(loss_host, c->loss_dev, 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    B200_CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int b200vae_predict(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int remove_train, int train_mode,
+                    float dropout_p, uint64_t seed, uint64_t step, float* scores, float* mu, float* logvar,
+                    void* stream) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    B200_REQUIRE(c, B200VAE_EINVAL, "null context");
+    return predict(c, row_ids, B, remove_train, train_mode, dropout_p, seed, step, scores, mu, logvar, (cudaStream_t)stream);
+}
+
+int b200vae_decode(b200vae_ctx* ctx, const float* z, int32_t B, float* scores, void* stream) {
+    // AE_net.decode(z) (nets.py:227-233, 413-417): decoder layers on a caller-provided latent batch
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    cudaStream_t s = (cudaStream_t)stream;
+    B200_REQUIRE(c && z && scores, B200VAE_EINVAL, "null argument");
+    B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
+    B200_REQUIRE(B >= 1 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
+    const float* h = z;
+    for (size_t i = 0; i + 1 < c->dec.size(); ++i) {
+        B200_CHECK(linear_fwd(c, h, B, c->dec[i], c->act_dec[i], s));
+        h = c->act_dec[i];
+    }
+    const Layer& DL = c->dec.back();
+    if (c->tc_dec) {
+        TcEpi e;
+        e.bias = c->w + DL.b_off;
+        B200_CHECK(launch_round_tf32(c, h, c->h_r, (int64_t)B * DL.in, s));
+        return launch_tc_gemm(c, TC_EPI_STORE, c->h_r, DL.in, 0, c->wd_shadow, DL.in, 0, scores, c->n_items, B, c->n_items, DL.in, e, s);
+    }
+    return linear_fwd(c, h, B, DL, scores, s);
+}
+
+int b200vae_topk_metrics(b200vae_ctx* ctx, const float* scores, const int32_t* gt_row_ids, int32_t B,
+                         const int32_t* kinds, const int32_t* ks, int32_t n_metrics, float* out,
+                         int32_t* topk_idx, void* stream) {
+    // kinds / ks are HOST arrays (a handful of ints); they are staged through the context
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    cudaStream_t s = (cudaStream_t)stream;
+    B200_REQUIRE(c && scores && kinds && ks && out && n_metrics >= 1 && n_metrics <= 64, B200VAE_EINVAL, "bad argument");
+    B200_REQUIRE(B >= 1 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
+    int kmax = 1;
+    for (int i = 0; i < n_metrics; ++i) {
+        B200_REQUIRE(kinds[i] >= 0 && kinds[i] <= 3 && ks[i] >= 1, B200VAE_EINVAL, "bad metric spec %d", i);
+        kmax = std::max(kmax, std::min(ks[i], c->n_items));
+    }
+    int32_t h_specs[128] = {0};
+    for (int i = 0; i < n_metrics; ++i) { h_specs[i] = kinds[i]; h_specs[64 + i] = ks[i]; }
+    // pageable source: the copy is staged before cudaMemcpyAsync returns, so the stack buffer is safe
+    B200_CUDA_OK(cudaMemcpyAsync(c->d_specs, h_specs, sizeof(h_specs), cudaMemcpyHostToDevice, s));
+    BatchView gt;
+    B200_CHECK(make_view(c, 1, gt_row_ids, B, &gt, s));
+    return launch_topk_metrics(c, scores, c->n_items, gt, c->d_specs, c->d_specs + 64, n_metrics, kmax, out, topk_idx, s);
+}
+
+int b200vae_gemm_tf32(b200vae_ctx* ctx, const float* A, int64_t lda, int a_mn_major, const float* B, int64_t ldb,
+                      int b_mn_major, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, void* stream) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    B200_REQUIRE(c && A && B && C, B200VAE_EINVAL, "null argument");
+    TcEpi e;
+    return launch_tc_gemm(c, TC_EPI_STORE, A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, e, (cudaStream_t)stream);
+}
+
+int b200vae_dec_fwd_lse(b200vae_ctx* ctx, const float* h, const float* W, const float* bias, int32_t B,
+                        int32_t n_items, int32_t H, float* lse, void* stream) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    cudaStream_t s = (cudaStream_t)stream;
+    B200_REQUIRE(c && h && W && lse, B200VAE_EINVAL, "null argument");
+    B200_REQUIRE(B <= c->cfg.max_batch && n_items <= c->n_items, B200VAE_ECAPACITY, "exceeds context capacity");
+    B200_REQUIRE(tc_supported(B, n_items, H, H, H), B200VAE_EINVAL, "shape not supported by the tcgen05 path (H %% 4 != 0?)");
+    TcEpi e;
+    e.bias = bias;
+    e.part_max = c->part_max;
+    e.part_sum = c->part_sum;
+    tick(c, 0, 0, s);
+    B200_CHECK(launch_tc_gemm(c, TC_EPI_LSE, h, H, 0, W, H, 0, nullptr, 0, B, n_items, H, e, s));
+    B200_CHECK(launch_lse_merge(c, c->part_max, c->part_sum, tc_lse_tiles(n_items), B, lse, s));
+    tick(c, 0, 1, s);
+    return 0;
+}
+
+int64_t b200vae_launch_count(b200vae_ctx* ctx, int reset) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return -1;
+    int64_t n = c->launches;
+    if (reset) c->launches = 0;
+    return n;
+}
+
+int b200vae_set_timing(b200vae_ctx* ctx, int enable) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return B200VAE_EINVAL;
+    c->timing = enable != 0;
+    return 0;
+}
+
+float b200vae_kernel_ms(b200vae_ctx* ctx, int which) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || which < 0 || which >= 5 || !c->ev_valid[which]) return -1.f;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, c->ev[which][0], c->ev[which][1]) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+int b200vae_check_error_flag(b200vae_ctx* ctx) {
+    // device-side capacity overflow flag (set by the scan kernels); synchronises the device
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c) return B200VAE_EINVAL;
+    int flag = 0;
+    B200_CUDA_OK(cudaMemcpy(&flag, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(c->d_err, 0, sizeof(int));
+        set_error("a batch exceeded max_batch_nnz (%lld): results of that step are invalid", (long long)c->cfg.max_batch_nnz);
+        return B200VAE_ECAPACITY;
+    }
+    return 0;
+}
+
+}  // extern "C"

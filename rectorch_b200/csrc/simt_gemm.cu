@@ -1,0 +1,188 @@
+// simt_gemm.cu -- fp32 CUDA-core GEMM with fused epilogues for the SMALL dense layers
+// (hidden x hidden / hidden x latent Linear layers, nets.py:398-404, 413-416, and their
+// backward), which are <2% of the step's FLOPs and need exact fp32 for loss parity.
+// The item-sized contractions go through tc_gemm.cu (tcgen05) when shapes allow; this
+// kernel also serves them for shapes TMA cannot address (rows not 16 B aligned, e.g.
+// the 2-item nets of the reference's unit tests).
+//
+//   C[m,n] = epi( alpha * sum_k A(m,k) * B(k,n) )
+//   A(m,k) = A[m*a_rs + k*a_cs],  B(k,n) = B[k*b_rs + n*b_cs]   (any strides -> any transposes)
+#include "ctx.cuh"
+
+namespace b200 {
+
+constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_simt_gemm(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float* __restrict__ B,
+            int64_t b_rs, int64_t b_cs, float* __restrict__ C, int64_t ldc, int M, int N, int K,
+            GemmEpi e) {
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    const bool a_kfast = (a_cs == 1);
+    const bool b_nfast = (b_cs == 1);
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int i = tid; i < BM * BK; i += 256) {
+            int mm, kk;
+            if (a_kfast) { kk = i % BK; mm = i / BK; } else { mm = i % BM; kk = i / BM; }
+            int gm = m0 + mm, gk = k0 + kk;
+            As[kk][mm] = (gm < M && gk < K) ? A[(int64_t)gm * a_rs + (int64_t)gk * a_cs] : 0.f;
+        }
+#pragma unroll
+        for (int i = tid; i < BN * BK; i += 256) {
+            int nn, kk;
+            if (b_nfast) { nn = i % BN; kk = i / BN; } else { kk = i % BK; nn = i / BK; }
+            int gn = n0 + nn, gk = k0 + kk;
+            Bs[kk][nn] = (gn < N && gk < K) ? B[(int64_t)gk * b_rs + (int64_t)gn * b_cs] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    if (MODE == EPI_STORE) {
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            int gm = m0 + ty * TM + i;
+            if (gm >= M) continue;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                int gn = n0 + tx * TN + j;
+                if (gn >= N) continue;
+                float y = e.alpha * acc[i][j];
+                if (e.bias) y += e.bias[gn];
+                if (e.addend) y += e.addend_scale * e.addend[(int64_t)gm * e.ld_addend + gn];
+                if (e.act) y = tanhf(y);
+                if (e.mulY) {
+                    float t = e.mulY[(int64_t)gm * e.ldy + gn];
+                    y *= (1.f - t * t);
+                }
+                C[(int64_t)gm * ldc + gn] = y;
+            }
+        }
+    } else if (MODE == EPI_LSE) {
+        // per (row, 64-column tile): running max and sum of exp(logit - max)
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            int gm = m0 + ty * TM + i;
+            float mx = -INFINITY;
+            float v[TN];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                int gn = n0 + tx * TN + j;
+                v[j] = (gn < N) ? acc[i][j] + (e.bias ? e.bias[gn] : 0.f) : -INFINITY;
+                mx = fmaxf(mx, v[j]);
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            float sacc = 0.f;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) sacc += (v[j] == -INFINITY) ? 0.f : expf(v[j] - mx);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+            if (tx == 0 && gm < M) {
+                e.part_max[(int64_t)blockIdx.x * M + gm] = mx;
+                e.part_sum[(int64_t)blockIdx.x * M + gm] = sacc;
+            }
+        }
+    } else {   // EPI_PROB: P = exp(logit - lse[m]) * rowscale[m]
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+            int gm = m0 + ty * TM + i;
+            if (gm >= M) continue;
+            float l = e.lse[gm], rs = e.rowscale[gm];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                int gn = n0 + tx * TN + j;
+                if (gn >= N) continue;
+                float y = acc[i][j] + (e.bias ? e.bias[gn] : 0.f);
+                C[(int64_t)gm * ldc + gn] = expf(y - l) * rs;
+            }
+        }
+    }
+}
+
+int launch_simt_gemm(Ctx* c, int mode, const float* A, int64_t a_rs, int64_t a_cs, const float* B,
+                     int64_t b_rs, int64_t b_cs, float* C, int64_t ldc, int M, int N, int K,
+                     const GemmEpi& e, cudaStream_t s) {
+    if (M == 0 || N == 0) return 0;
+    dim3 grid((unsigned)cdiv(N, BN), (unsigned)cdiv(M, BM));
+    B200_REQUIRE(grid.y <= 65535, B200VAE_EINVAL, "simt_gemm: M too large (%d)", M);
+    switch (mode) {
+        case EPI_STORE: k_simt_gemm<EPI_STORE><<<grid, 256, 0, s>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e); break;
+        case EPI_LSE:   k_simt_gemm<EPI_LSE><<<grid, 256, 0, s>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e); break;
+        default:        k_simt_gemm<EPI_PROB><<<grid, 256, 0, s>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e); break;
+    }
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// out[n] = sum_m X[m*ldx + n]   -- fixed summation order (deterministic)
+__global__ void k_colsum(const float* __restrict__ X, int64_t ldx, int M, int N, float* __restrict__ out) {
+    int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float acc = 0.f;
+    for (int m = 0; m < M; ++m) acc += X[(int64_t)m * ldx + n];
+    out[n] = acc;
+}
+
+int launch_colsum(Ctx* c, const float* X, int64_t ldx, int M, int N, float* out, cudaStream_t s) {
+    if (N == 0) return 0;
+    k_colsum<<<(int)cdiv(N, 128), 128, 0, s>>>(X, ldx, M, N, out);
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// lse[r] = M + log(sum_t psum[t,r] * exp(pmax[t,r] - M)),  M = max_t pmax[t,r]; one warp per row
+__global__ void k_lse_merge(const float* __restrict__ pmax, const float* __restrict__ psum, int n_tiles,
+                            int M, float* __restrict__ lse) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= M) return;
+    float mx = -INFINITY;
+    for (int t = lane; t < n_tiles; t += 32) mx = fmaxf(mx, pmax[(int64_t)t * M + warp]);
+    mx = warp_max(mx);
+    float sacc = 0.f;
+    for (int t = lane; t < n_tiles; t += 32) {
+        float pm = pmax[(int64_t)t * M + warp];
+        if (pm != -INFINITY) sacc += psum[(int64_t)t * M + warp] * expf(pm - mx);
+    }
+    sacc = warp_sum(sacc);
+    if (lane == 0) lse[warp] = mx + logf(sacc);
+}
+
+int launch_lse_merge(Ctx* c, const float* pmax, const float* psum, int n_tiles, int M, float* lse,
+                     cudaStream_t s) {
+    if (M == 0) return 0;
+    int threads = 256;
+    k_lse_merge<<<(int)cdiv((int64_t)M * 32, threads), threads, 0, s>>>(pmax, psum, n_tiles, M, lse);
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200

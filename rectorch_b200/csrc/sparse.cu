@@ -1,0 +1,443 @@
+// sparse.cu -- CSR batch handling and the sparse ends of the network.
+//
+//  K1  expand / dense_to_csr   : DataSampler.__iter__ (samplers.py:99-105) and its inverse
+//  K2  spmm_gather             : F.normalize + nn.Dropout + first encoder nn.Linear
+//                                (nets.py:395-401) as a gather-sum of item-major weight rows;
+//                                also  g_u = sum_j t_uj W_d[j,:]  for the multinomial NLL
+//  K7  spmm_scatter            : the transposed operation for the weight gradients
+//
+// All kernels are HBM/L2-bound row gathers: one CTA per user row, threads across the
+// hidden dimension so every warp reads 128 B-contiguous pieces of a weight row.
+#include "ctx.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------
+// scans
+// ------------------------------------------------------------------------------------------
+__global__ void k_batch_scan(const int64_t* __restrict__ indptr, const int32_t* __restrict__ row_ids,
+                             int B, int64_t cap, int64_t* __restrict__ bp, int* err) {
+    // single CTA, 1024 threads; chunked Hillis-Steele scan over the row lengths
+    __shared__ int64_t sh[1024];
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < B; base += 1024) {
+        int r = base + threadIdx.x;
+        int64_t len = 0;
+        if (r < B) {
+            int64_t gr = row_ids ? (int64_t)row_ids[r] : (int64_t)r;
+            len = indptr[gr + 1] - indptr[gr];
+        }
+        sh[threadIdx.x] = len;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            int64_t t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (r < B) bp[r] = carry + sh[threadIdx.x] - len;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        bp[B] = carry;
+        if (carry > cap) *err = 1;
+    }
+}
+
+int launch_batch_scan(Ctx* c, const int64_t* indptr, const int32_t* row_ids, int B, int64_t cap,
+                      int64_t* bp, cudaStream_t s) {
+    k_batch_scan<<<1, 1024, 0, s>>>(indptr, row_ids, B, cap, bp, c->d_err);
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void k_scan_i64(const int64_t* __restrict__ lens, int n, int64_t cap,
+                           int64_t* __restrict__ out, int* err) {
+    __shared__ int64_t sh[1024];
+    __shared__ int64_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        int r = base + threadIdx.x;
+        int64_t len = (r < n) ? lens[r] : 0;
+        sh[threadIdx.x] = len;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            int64_t t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (r < n) out[r] = carry + sh[threadIdx.x] - len;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out[n] = carry;
+        if (carry > cap) *err = 1;
+    }
+}
+
+int launch_scan_i64(Ctx* c, const int64_t* lens, int n, int64_t cap, int64_t* out, cudaStream_t s) {
+    k_scan_i64<<<1, 1024, 0, s>>>(lens, n, cap, out, c->d_err);
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// batch_prep: per row  s = 1/max(||x||,1e-12);  xt = x*s*keep/(1-p)   (nets.py:395-397)
+// one warp per row
+// ------------------------------------------------------------------------------------------
+__global__ void k_batch_prep(BatchView v, float p, uint64_t seed, uint64_t step, int64_t row_offset,
+                             const uint8_t* __restrict__ keep_tape, int train, int64_t cap,
+                             float* __restrict__ xt) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= v.B) return;
+    int64_t gr = v.row_ids ? (int64_t)v.row_ids[warp] : (int64_t)warp;
+    int64_t a = v.indptr[gr], b = v.indptr[gr + 1];
+    int64_t o = v.bp[warp];
+    if (o + (b - a) > cap) return;   // capacity overflow flagged by the scan
+    float ss = 0.f;
+    for (int64_t k = a + lane; k < b; k += 32) {
+        float x = v.values ? v.values[k] : 1.f;
+        ss += x * x;
+    }
+    ss = warp_sum(ss);
+    float denom = fmaxf(sqrtf(ss), 1e-12f);
+    bool drop = train && p > 0.f;
+    float inv_keep = 1.0f / (1.0f - p);
+    for (int64_t k = a + lane; k < b; k += 32) {
+        float x = v.values ? v.values[k] : 1.f;
+        float xn = x / denom;
+        if (drop) {
+            bool keep;
+            if (keep_tape) {
+                keep = keep_tape[o + (k - a)] != 0;
+            } else {
+                uint64_t grow = (uint64_t)(gr + row_offset);
+                uint4 ctr = make_uint4((uint32_t)grow, (uint32_t)(grow >> 32), (uint32_t)v.indices[k],
+                                       (uint32_t)step);
+                uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ 0x0D0Du);
+                uint4 r = philox4x32(ctr, key);
+                keep = u32_to_unit(r.x) > p;
+            }
+            xn = keep ? xn * inv_keep : 0.f;
+        }
+        xt[o + (k - a)] = xn;
+    }
+}
+
+int launch_batch_prep(Ctx* c, const BatchView& in, float p, uint64_t seed, uint64_t step,
+                      int64_t row_offset, const uint8_t* keep_tape, bool train, float* xt,
+                      cudaStream_t s) {
+    if (in.B == 0) return 0;
+    int threads = 256;
+    int blocks = (int)cdiv((int64_t)in.B * 32, threads);
+    k_batch_prep<<<blocks, threads, 0, s>>>(in, p, seed, step, row_offset, keep_tape, train ? 1 : 0,
+                                            c->cfg.max_batch_nnz, xt);
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void k_row_sums(BatchView v, float* __restrict__ out) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= v.B) return;
+    int64_t gr = v.row_ids ? (int64_t)v.row_ids[warp] : (int64_t)warp;
+    int64_t a = v.indptr[gr], b = v.indptr[gr + 1];
+    float sacc = 0.f;
+    for (int64_t k = a + lane; k < b; k += 32) sacc += v.values ? v.values[k] : 1.f;
+    sacc = warp_sum(sacc);
+    if (lane == 0) out[warp] = sacc;
+}
+
+int launch_row_sums(Ctx* c, const BatchView& v, float* out, cudaStream_t s) {
+    if (v.B == 0) return 0;
+    int threads = 256;
+    k_row_sums<<<(int)cdiv((int64_t)v.B * 32, threads), threads, 0, s>>>(v, out);
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 spmm_gather: out[r,:] = act(bias + sum_k vals[bp[r]+k] * Wt[col_k,:])
+// one CTA per row; VEC=4 -> float4 lanes across H (H % 4 == 0, 16 B aligned rows)
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_spmm_gather(BatchView v, const float* __restrict__ vals, const float* __restrict__ Wt, int H,
+              const float* __restrict__ bias, int act, float* __restrict__ out) {
+    int r = blockIdx.x;
+    int64_t gr = v.row_ids ? (int64_t)v.row_ids[r] : (int64_t)r;
+    int64_t a = v.indptr[gr];
+    int n = (int)(v.indptr[gr + 1] - a);
+    int64_t o = v.bp[r];
+    const int32_t* cols = v.indices + a;
+    const float* xv = vals ? vals + o : nullptr;
+    const float* raw = v.values ? v.values + a : nullptr;
+    for (int h0 = threadIdx.x * VEC; h0 < H; h0 += blockDim.x * VEC) {
+        float acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        int k = 0;
+        for (; k + 4 <= n; k += 4) {   // 4 independent row loads in flight
+            float w[4][VEC];
+            float x[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float* row = Wt + (int64_t)cols[k + u] * H + h0;
+                x[u] = xv ? xv[k + u] : (raw ? raw[k + u] : 1.f);
+                if (VEC == 4) {
+                    float4 t = __ldg(reinterpret_cast<const float4*>(row));
+                    w[u][0] = t.x; w[u][1 % VEC] = t.y; w[u][2 % VEC] = t.z; w[u][3 % VEC] = t.w;
+                } else {
+                    w[u][0] = __ldg(row);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] = fmaf(x[u], w[u][i], acc[i]);
+        }
+        for (; k < n; ++k) {
+            const float* row = Wt + (int64_t)cols[k] * H + h0;
+            float x = xv ? xv[k] : (raw ? raw[k] : 1.f);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] = fmaf(x, __ldg(row + i), acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float y = acc[i] + (bias ? bias[h0 + i] : 0.f);
+            if (act) y = tanhf(y);
+            out[(int64_t)r * H + h0 + i] = y;
+        }
+    }
+}
+
+int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const float* Wt, int H,
+                       const float* bias, int act, float* out, cudaStream_t s) {
+    if (v.B == 0) return 0;
+    bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(Wt) & 15) == 0);
+    if (vec) {
+        int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));
+        k_spmm_gather<4><<<v.B, threads, 0, s>>>(v, vals, Wt, H, bias, act, out);
+    } else {
+        int threads = (int)std::min<int64_t>(256, round_up(H, 32));
+        k_spmm_gather<1><<<v.B, threads, 0, s>>>(v, vals, Wt, H, bias, act, out);
+    }
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K7 spmm_scatter: dWt[col_k,:] += scale * vals[k] * dY[r,:]      (fp32 reductions in L2)
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_spmm_scatter(BatchView v, const float* __restrict__ vals, float scale, const float* __restrict__ dY,
+               int H, float* __restrict__ dWt) {
+    int r = blockIdx.x;
+    int64_t gr = v.row_ids ? (int64_t)v.row_ids[r] : (int64_t)r;
+    int64_t a = v.indptr[gr];
+    int n = (int)(v.indptr[gr + 1] - a);
+    int64_t o = v.bp[r];
+    const int32_t* cols = v.indices + a;
+    const float* xv = vals ? vals + o : nullptr;
+    const float* raw = v.values ? v.values + a : nullptr;
+    for (int h0 = threadIdx.x * VEC; h0 < H; h0 += blockDim.x * VEC) {
+        float d[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) d[i] = dY[(int64_t)r * H + h0 + i] * scale;
+        for (int k = 0; k < n; ++k) {
+            float x = xv ? xv[k] : (raw ? raw[k] : 1.f);
+            if (x == 0.f) continue;   // dropped entries contribute nothing
+            float* row = dWt + (int64_t)cols[k] * H + h0;
+            if (VEC == 4) {
+                atomicAdd(reinterpret_cast<float4*>(row),
+                          make_float4(x * d[0], x * d[1 % VEC], x * d[2 % VEC], x * d[3 % VEC]));
+            } else {
+                atomicAdd(row, x * d[0]);
+            }
+        }
+    }
+}
+
+int launch_spmm_scatter(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
+                        int H, float* dWt, cudaStream_t s) {
+    if (v.B == 0) return 0;
+    bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(dWt) & 15) == 0);
+    if (vec) {
+        int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));
+        k_spmm_scatter<4><<<v.B, threads, 0, s>>>(v, vals, scale, dY, H, dWt);
+    } else {
+        int threads = (int)std::min<int64_t>(256, round_up(H, 32));
+        k_spmm_scatter<1><<<v.B, threads, 0, s>>>(v, vals, scale, dY, H, dWt);
+    }
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// db[col_k] += scale * value_k     (sparse part of the decoder bias gradient)
+__global__ void k_bias_scatter(BatchView v, float scale, float* __restrict__ db) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= v.B) return;
+    int64_t gr = v.row_ids ? (int64_t)v.row_ids[warp] : (int64_t)warp;
+    int64_t a = v.indptr[gr], b = v.indptr[gr + 1];
+    for (int64_t k = a + lane; k < b; k += 32) {
+        float x = v.values ? v.values[k] : 1.f;
+        atomicAdd(db + v.indices[k], scale * x);
+    }
+}
+
+int launch_bias_scatter(Ctx* c, const BatchView& v, float scale, float* db, cudaStream_t s) {
+    if (v.B == 0) return 0;
+    int threads = 256;
+    k_bias_scatter<<<(int)cdiv((int64_t)v.B * 32, threads), threads, 0, s>>>(v, scale, db);
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// dense <-> CSR
+// ------------------------------------------------------------------------------------------
+__global__ void k_dense_count(const float* __restrict__ dense, int B, int I, int64_t* __restrict__ lens) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const float* row = dense + (int64_t)warp * I;
+    int cnt = 0;
+    for (int j = lane; j < I; j += 32) cnt += (row[j] != 0.f);
+    cnt = (int)warp_sum((float)cnt);   // exact for counts < 2^24
+    if (lane == 0) lens[warp] = cnt;
+}
+
+int launch_dense_count(Ctx* c, const float* dense, int B, int I, int64_t* lens, cudaStream_t s) {
+    int threads = 256;
+    k_dense_count<<<(int)cdiv((int64_t)B * 32, threads), threads, 0, s>>>(dense, B, I, lens);
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void k_dense_fill(const float* __restrict__ dense, int B, int I,
+                             const int64_t* __restrict__ indptr, int64_t cap,
+                             int32_t* __restrict__ indices, float* __restrict__ values) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const float* row = dense + (int64_t)warp * I;
+    int64_t o = indptr[warp];
+    if (indptr[warp + 1] > cap) return;
+    for (int j0 = 0; j0 < I; j0 += 32) {
+        int j = j0 + lane;
+        float x = (j < I) ? row[j] : 0.f;
+        unsigned m = __ballot_sync(0xffffffffu, x != 0.f);
+        if (x != 0.f) {
+            int pos = __popc(m & ((1u << lane) - 1u));
+            indices[o + pos] = j;
+            values[o + pos] = x;
+        }
+        o += __popc(m);
+    }
+}
+
+int launch_dense_fill(Ctx* c, const float* dense, int B, int I, const int64_t* indptr,
+                      int32_t* indices, float* values, cudaStream_t s) {
+    int threads = 256;
+    k_dense_fill<<<(int)cdiv((int64_t)B * 32, threads), threads, 0, s>>>(
+        dense, B, I, indptr, c->cfg.max_batch_nnz, indices, values);
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void k_expand(BatchView v, int I, float* __restrict__ out) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= v.B) return;
+    int64_t gr = v.row_ids ? (int64_t)v.row_ids[warp] : (int64_t)warp;
+    int64_t a = v.indptr[gr], b = v.indptr[gr + 1];
+    for (int64_t k = a + lane; k < b; k += 32)
+        out[(int64_t)warp * I + v.indices[k]] = v.values ? v.values[k] : 1.f;
+}
+
+int launch_expand(Ctx* c, const BatchView& v, int I, float* out, cudaStream_t s) {
+    if (v.B == 0) return 0;
+    B200_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)v.B * I * sizeof(float), s));
+    int threads = 256;
+    k_expand<<<(int)cdiv((int64_t)v.B * 32, threads), threads, 0, s>>>(v, I, out);
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+__global__ void k_mask_seen(BatchView v, int I, float* __restrict__ scores) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= v.B) return;
+    int64_t gr = v.row_ids ? (int64_t)v.row_ids[warp] : (int64_t)warp;
+    int64_t a = v.indptr[gr], b = v.indptr[gr + 1];
+    for (int64_t k = a + lane; k < b; k += 32) {
+        float x = v.values ? v.values[k] : 1.f;
+        if (x != 0.f) scores[(int64_t)warp * I + v.indices[k]] = -INFINITY;
+    }
+}
+
+int launch_mask_seen(Ctx* c, const BatchView& v, int I, float* scores, cudaStream_t s) {
+    if (v.B == 0) return 0;
+    int threads = 256;
+    k_mask_seen<<<(int)cdiv((int64_t)v.B * 32, threads), threads, 0, s>>>(v, I, scores);
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// row_loss: loss_r = T_r * lse_r - h_r . g_r - sum_k t_k * b[col_k]       (models.py:813)
+// one warp per row
+// ------------------------------------------------------------------------------------------
+__global__ void k_row_loss(BatchView tgt, const float* __restrict__ h, const float* __restrict__ gvec,
+                           int H, const float* __restrict__ bias, const float* __restrict__ lse,
+                           const float* __restrict__ T, float* __restrict__ loss_row) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= tgt.B) return;
+    float dot = 0.f;
+    for (int i = lane; i < H; i += 32) dot = fmaf(h[(int64_t)warp * H + i], gvec[(int64_t)warp * H + i], dot);
+    int64_t gr = tgt.row_ids ? (int64_t)tgt.row_ids[warp] : (int64_t)warp;
+    int64_t a = tgt.indptr[gr], b = tgt.indptr[gr + 1];
+    float tb = 0.f;
+    for (int64_t k = a + lane; k < b; k += 32)
+        tb = fmaf(tgt.values ? tgt.values[k] : 1.f, bias[tgt.indices[k]], tb);
+    dot = warp_sum(dot);
+    tb = warp_sum(tb);
+    if (lane == 0) loss_row[warp] = T[warp] * lse[warp] - dot - tb;
+}
+
+int launch_row_loss(Ctx* c, const BatchView& tgt, const float* h, const float* gvec, int H,
+                    const float* bias, const float* lse, const float* T, float* loss_row,
+                    cudaStream_t s) {
+    if (tgt.B == 0) return 0;
+    int threads = 256;
+    k_row_loss<<<(int)cdiv((int64_t)tgt.B * 32, threads), threads, 0, s>>>(tgt, h, gvec, H, bias, lse,
+                                                                            T, loss_row);
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200

@@ -1,0 +1,484 @@
+// tc_gemm.cu -- the item-sized contractions of the decoder output layer on the 5th-gen
+// tensor cores: tcgen05.mma (kind::tf32, fp32 accumulate in TMEM), operands staged in shared
+// memory by TMA (128 B swizzle), warp-specialised persistent CTAs, one CTA per SM.
+//
+//   D[M x N] = A[M x K] * B[N x K]^T
+//
+//   TC_EPI_LSE   K4  logits = h W_d^T + b never leave the SM: each epilogue thread owns one user
+//                    row (one TMEM lane) and folds its 256-item tile into an online (max, sum exp);
+//                    output = per-(item tile, user) partials, merged by k_lse_merge.
+//                    (F.log_softmax over nets.py:417's output, models.py:813)
+//   TC_EPI_PROB  K5  same mainloop, epilogue recomputes softmax from the saved lse and stores
+//                    P^T[item, user] = exp(logit - lse_u) * T_u/B  (coalesced: a warp's 32 lanes
+//                    are 32 consecutive users)                      (dlogits of loss.backward())
+//   TC_EPI_STORE     plain product (+ bias), optional split-K partials and a "bias column":
+//                    dW_d|db_d = P^T [h | 1]  and  dh = P W_d.
+//
+// Operand "majorness": K-major = the contraction index is contiguous in memory (TMA box
+// 32 floats of K x rows), MN-major = the M/N index is contiguous (box 32 floats of M/N x 32
+// K-rows, one box per 32-wide chunk).  Both map onto SWIZZLE_128B shared-memory descriptors;
+// the instruction descriptor's a_major/b_major bits select the interpretation.
+//
+// Pipelines (all mbarrier based, no __syncthreads in the steady state):
+//   warp 0   TMA producer      : empty[s] -> issue loads -> full[s] (complete_tx)
+//   warp 1   MMA issuer        : full[s] -> 4 x tcgen05.mma (K=8 each) -> commit -> empty[s];
+//                                after the last K block: commit -> tmem_full[a]
+//   warps 2-5 epilogue         : tmem_full[a] -> tcgen05.ld 32 columns at a time -> math ->
+//                                global stores -> tmem_empty[a]
+// TMEM: 512 columns = 2 accumulator stages x 256 columns, so the epilogue of tile i overlaps
+// the MMAs of tile i+1.
+#include <cuda.h>
+#include <algorithm>
+#include "ctx.cuh"
+
+namespace b200 {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                       // floats per K block = 128 B = one swizzle row
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+constexpr int TC_B_BYTES = 256 * TC_BK * 4;     // 32 KB (max N tile)
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_THREADS = 192;
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr unsigned long long SPIN_LIMIT = 1ull << 28;
+
+// ---------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    unsigned long long spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > SPIN_LIMIT) {   // a protocol bug must fail loudly, not hang the GPU
+            printf("b200vae tc_gemm: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// SM100 shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor layout:
+// start[0,14) LBO[16,30) SBO[32,46) version[46,48)=1 layout_type[61,64)=2)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
+    d |= 2ull << 61;
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------
+// kernel
+// ---------------------------------------------------------------------------------------
+struct TcArgs {
+    float* C;
+    int64_t ldc;
+    int M, N, K;
+    int BN;                 // N tile (multiple of 16, <= 256)
+    int tiles_m, tiles_n;
+    int kb_total;           // K blocks overall
+    int kb_per_split;
+    int split_k;
+    int64_t split_stride;
+    int n_store;            // STORE: columns < n_store go to C
+    int bias_col;           // STORE: this column goes to bias_grad[m] (or -1)
+    const float* bias;
+    float* part_max;
+    float* part_sum;
+    const float* lse;
+    const float* rowscale;
+    float* bias_grad;
+    int vec_ok;             // C rows are 16 B aligned
+};
+
+template <int MODE, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4);
+    uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + TC_STAGES * TC_STAGE_BYTES + 8 * (2 * TC_STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM allocation: all 512 columns (1 CTA / SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    const int total_tiles = a.tiles_m * a.tiles_n * a.split_k;
+    const uint32_t b_bytes = (uint32_t)a.BN * TC_BK * 4u;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int m_idx = t % a.tiles_m;
+                const int n_idx = (t / a.tiles_m) % a.tiles_n;
+                const int sp = t / (a.tiles_m * a.tiles_n);
+                const int kb0 = sp * a.kb_per_split;
+                const int kb1 = min(a.kb_total, kb0 + a.kb_per_split);
+                const int m0 = m_idx * TC_BM, n0 = n_idx * a.BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+                    const uint32_t sb = sa + TC_A_BYTES;
+                    mbar_expect_tx(full_bar(stage), TC_A_BYTES + b_bytes);
+                    const int k0 = kb * TC_BK;
+                    if (!A_MN) {
+                        tma_load_2d(sa, &tmA, full_bar(stage), k0, m0);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < TC_BM / 32; ++c) tma_load_2d(sa + c * 4096, &tmA, full_bar(stage), m0 + 32 * c, k0);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sb, &tmB, full_bar(stage), k0, n0);
+                    } else {
+                        for (int c = 0; c < a.BN / 32; ++c) tma_load_2d(sb + c * 4096, &tmB, full_bar(stage), n0 + 32 * c, k0);
+                    }
+                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer =================================
+        // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1,
+        // a/b_format TF32 [7,10)/[10,13)=2, a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                               ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int sp = t / (a.tiles_m * a.tiles_n);
+            const int kb0 = sp * a.kb_per_split;
+            const int kb1 = min(a.kb_total, kb0 + a.kb_per_split);
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+            tcgen05_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                tcgen05_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+                    const uint32_t sb = sa + TC_A_BYTES;
+#pragma unroll
+                    for (int j = 0; j < TC_BK / 8; ++j) {
+                        const uint64_t ad = A_MN ? make_sdesc(sa + j * 1024, 4096, 1024) : make_sdesc(sa + j * 32, 0, 1024);
+                        const uint64_t bd = B_MN ? make_sdesc(sb + j * 1024, 4096, 1024) : make_sdesc(sb + j * 32, 0, 1024);
+                        tcgen05_mma_tf32(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+                    }
+                    tcgen05_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
+                    if (kb == kb1 - 1) tcgen05_commit(tfull_bar(acc)); // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
+            }
+            if (kb1 <= kb0 && lane == 0) mbar_arrive(tfull_bar(acc));   // empty K range (never with sane splits)
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    } else {
+        // =============================== epilogue ===================================
+        const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const int row_in_tile = q * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const float LOG2E = 1.4426950408889634f;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int m_idx = t % a.tiles_m;
+            const int n_idx = (t / a.tiles_m) % a.tiles_n;
+            const int sp = t / (a.tiles_m * a.tiles_n);
+            const int m = m_idx * TC_BM + row_in_tile;
+            const int n0 = n_idx * a.BN;
+            const int n_valid = min(a.BN, a.N - n0);
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tcgen05_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+            float run_max = -INFINITY, run_sum = 0.f;
+            float lse_m = 0.f, rs_m = 0.f;
+            if (MODE == TC_EPI_PROB && m < a.M) { lse_m = a.lse[m]; rs_m = a.rowscale[m]; }
+            for (int c0 = 0; c0 < n_valid; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
+                const int nc = min(32, n_valid - c0);
+                if (MODE == TC_EPI_LSE) {
+                    float cmax = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (i < nc) {
+                            v[i] += a.bias ? __ldg(a.bias + n0 + c0 + i) : 0.f;
+                            cmax = fmaxf(cmax, v[i]);
+                        }
+                    }
+                    const float new_max = fmaxf(run_max, cmax);
+                    const float off = new_max * LOG2E;
+                    float csum = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (i < nc) csum += exp2f(fmaf(v[i], LOG2E, -off));
+                    run_sum = run_sum * exp2f((run_max - new_max) * LOG2E) + csum;
+                    run_max = new_max;
+                } else if (MODE == TC_EPI_PROB) {
+                    // P^T[(n0+c0+i) * ldc + m]: for fixed i the warp writes 32 consecutive floats
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (i < nc && m < a.M) {
+                            const float x = v[i] + (a.bias ? __ldg(a.bias + n0 + c0 + i) : 0.f);
+                            const float pr = exp2f((x - lse_m) * LOG2E) * rs_m;
+                            a.C[(int64_t)(n0 + c0 + i) * a.ldc + m] = tf32_rn(pr);
+                        }
+                    }
+                } else {
+                    if (m < a.M) {
+                        float* crow = a.C + (int64_t)sp * a.split_stride + (int64_t)m * a.ldc;
+                        const int col0 = n0 + c0;
+                        if (a.vec_ok && col0 + 32 <= a.n_store && (!a.bias || ((uintptr_t)a.bias & 15) == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + col0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                                *reinterpret_cast<float4*>(crow + col0 + i) =
+                                    make_float4(v[i] + b4.x, v[i + 1] + b4.y, v[i + 2] + b4.z, v[i + 3] + b4.w);
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const int col = col0 + i;
+                                if (i < nc) {
+                                    if (col < a.n_store) crow[col] = v[i] + (a.bias ? __ldg(a.bias + col) : 0.f);
+                                    else if (col == a.bias_col) a.bias_grad[m] = v[i];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if (MODE == TC_EPI_LSE && m < a.M) {
+                a.part_max[(int64_t)n_idx * a.M + m] = run_max;
+                a.part_sum[(int64_t)n_idx * a.M + m] = run_sum;
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    // teardown
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, row pitch ld floats
+static int make_tmap(CUtensorMap* tm, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                     int box_outer) {
+    EncodeTiledFn enc = get_encode();
+    B200_REQUIRE(enc, B200VAE_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4ull};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B200_REQUIRE(r == CUDA_SUCCESS, B200VAE_ECUDA,
+                 "cuTensorMapEncodeTiled failed (%d): base %p inner %lld outer %lld ld %lld box %dx%d", (int)r, base,
+                 (long long)inner, (long long)outer, (long long)ld, box_inner, box_outer);
+    return 0;
+}
+
+bool tc_supported(int M, int N, int K, int64_t lda, int64_t ldb) {
+    return M >= 1 && N >= 16 && K >= 8 && (lda % 4 == 0) && (ldb % 4 == 0);
+}
+
+static int pick_bn(int N, bool b_mn) {
+    if (N >= 256) return 256;
+    return (int)round_up(N, b_mn ? 32 : 16);
+}
+int tc_lse_tiles(int N) { return (int)cdiv(N, pick_bn(N, false)); }
+
+template <int MODE, bool A_MN, bool B_MN>
+static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args, int grid, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        B200_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<MODE, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        attr_set = true;
+    }
+    k_tc_gemm<MODE, A_MN, B_MN><<<grid, TC_THREADS, TC_SMEM, s>>>(tmA, tmB, args);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_tc_gemm(Ctx* c, int mode, const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn,
+                   float* C, int64_t ldc, int M, int N, int K, const TcEpi& e, cudaStream_t s) {
+    B200_REQUIRE(tc_supported(M, N, K, lda, ldb), B200VAE_EINVAL, "tc_gemm: unsupported shape M=%d N=%d K=%d lda=%lld ldb=%lld",
+                 M, N, K, (long long)lda, (long long)ldb);
+    B200_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, B200VAE_EINVAL, "tc_gemm: operands must be 16-byte aligned");
+    TcArgs a;
+    a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
+    a.BN = pick_bn(N, b_mn != 0);
+    a.tiles_m = (int)cdiv(M, TC_BM);
+    a.tiles_n = (int)cdiv(N, a.BN);
+    a.kb_total = (int)cdiv(K, TC_BK);
+    a.split_k = std::max(1, std::min(e.split_k, a.kb_total));
+    a.kb_per_split = (int)cdiv(a.kb_total, a.split_k);
+    a.split_k = (int)cdiv(a.kb_total, a.kb_per_split);     // no empty splits
+    a.split_stride = e.split_stride;
+    a.bias = e.bias; a.part_max = e.part_max; a.part_sum = e.part_sum; a.lse = e.lse; a.rowscale = e.rowscale;
+    a.bias_grad = e.bias_grad;
+    a.bias_col = e.bias_col;
+    a.n_store = (e.bias_col >= 0) ? e.bias_col : N;
+    a.vec_ok = (C && ((uintptr_t)C & 15) == 0 && (ldc % 4 == 0) && (e.split_stride % 4 == 0)) ? 1 : 0;
+    if (mode == TC_EPI_STORE && e.split_k > 1 && a.split_k != e.split_k) {
+        // the caller sized its reduction for e.split_k partials: zero the ones we will not write
+        B200_CUDA_OK(cudaMemsetAsync(C + (int64_t)a.split_k * e.split_stride, 0,
+                                     (size_t)(e.split_k - a.split_k) * e.split_stride * sizeof(float), s));
+    }
+    CUtensorMap tmA, tmB;
+    if (!a_mn) B200_CHECK(make_tmap(&tmA, A, K, M, lda, TC_BK, TC_BM));
+    else       B200_CHECK(make_tmap(&tmA, A, M, K, lda, 32, TC_BK));
+    if (!b_mn) B200_CHECK(make_tmap(&tmB, B, K, N, ldb, TC_BK, a.BN));
+    else       B200_CHECK(make_tmap(&tmB, B, N, K, ldb, 32, TC_BK));
+    const int total = a.tiles_m * a.tiles_n * a.split_k;
+    const int grid = std::min(total, c->num_sms);
+    int rc;
+#define INST(MODE_, AM, BM_) rc = launch_inst<MODE_, AM, BM_>(tmA, tmB, a, grid, s)
+    if (mode == TC_EPI_LSE) { B200_REQUIRE(!a_mn && !b_mn, B200VAE_EINVAL, "LSE epilogue expects K-major operands"); INST(TC_EPI_LSE, false, false); }
+    else if (mode == TC_EPI_PROB) { B200_REQUIRE(!a_mn && !b_mn, B200VAE_EINVAL, "PROB epilogue expects K-major operands"); INST(TC_EPI_PROB, false, false); }
+    else if (!a_mn && !b_mn) INST(TC_EPI_STORE, false, false);
+    else if (a_mn && !b_mn) INST(TC_EPI_STORE, true, false);
+    else if (!a_mn && b_mn) INST(TC_EPI_STORE, false, true);
+    else INST(TC_EPI_STORE, true, true);
+#undef INST
+    c->launches++;
+    return rc;
+}
+
+// out[m,n] = (sum_s parts[s][m,n] + addend_scale*addend[m,n]) * (1 - Y[m,n]^2)
+__global__ void k_splitk_reduce(const float* __restrict__ parts, int n_split, int64_t split_stride, float* __restrict__ out,
+                                int64_t ld_out, int M, int N, int64_t ld_part, const float* __restrict__ addend, int64_t ld_add,
+                                float addend_scale, const float* __restrict__ mulY, int64_t ldy) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)M * N) return;
+    int m = (int)(i / N), n = (int)(i % N);
+    float acc = 0.f;
+    for (int s = 0; s < n_split; ++s) acc += parts[(int64_t)s * split_stride + (int64_t)m * ld_part + n];
+    if (addend) acc += addend_scale * addend[(int64_t)m * ld_add + n];
+    if (mulY) {
+        float t = mulY[(int64_t)m * ldy + n];
+        acc *= (1.f - t * t);
+    }
+    out[(int64_t)m * ld_out + n] = acc;
+}
+
+int launch_splitk_reduce(Ctx* c, const float* parts, int n_split, int64_t split_stride, float* out, int64_t ld_out, int M,
+                         int N, int64_t ld_part, const float* addend, int64_t ld_add, float addend_scale, const float* mulY,
+                         int64_t ldy, cudaStream_t s) {
+    int64_t n = (int64_t)M * N;
+    if (n == 0) return 0;
+    k_splitk_reduce<<<(int)cdiv(n, 256), 256, 0, s>>>(parts, n_split, split_stride, out, ld_out, M, N, ld_part, addend, ld_add,
+                                                       addend_scale, mulY, ldy);
+    c->launches++;
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200

@@ -1,0 +1,419 @@
+"""Trainers with the reference's API (rectorch/models.py:70-161, 164-322, 325-516, 628-706,
+709-908) whose bodies are kernel launches.
+
+``MultiDAE(mdae_net, lam=0.2, learning_rate=1e-3)`` and
+``MultiVAE(mvae_net, beta=1., anneal_steps=0, learning_rate=1e-3)`` keep every public
+attribute the reference's tests look at (``network``, ``device``, ``learning_rate``,
+``optimizer`` -- a real ``torch.optim.Adam`` whose state tensors are views of the engine's
+exp_avg / exp_avg_sq arenas, so ``optimizer.state_dict()`` is what the reference would
+checkpoint -- ``lam`` / ``beta``, ``anneal_steps``, ``annealing``, ``gradient_updates``).
+
+One ``train_batch`` = one call into libb200vae.so: sparse input layer, small dense layers,
+fused decoder GEMM + log-softmax + loss, backward, fused Adam.  With ``torch.distributed``
+initialised (one process per GPU) users are sharded row-wise by the sampler, gradients are
+summed with ONE ``all_reduce`` of the flat gradient arena per step, and every rank applies
+the identical Adam update.
+"""
+import logging
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+from torch import optim
+
+from .engine import Engine, draw_seed, param_norm_sum
+from .evaluation import ValidFunc, evaluate
+from .samplers import DataSampler, RowBatch
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+__all__ = ['RecSysModel', 'TorchNNTrainer', 'AETrainer', 'MultiDAE', 'MultiVAE']
+
+logger = logging.getLogger(__name__)
+
+
+class RecSysModel():
+    """Abstract base class of every recommender (rectorch/models.py:70-161)."""
+
+    def train(self, train_data, **kwargs):
+        raise NotImplementedError()
+
+    def predict(self, x, *args, **kwargs):
+        raise NotImplementedError()
+
+    def save_model(self, filepath, *args, **kwargs):
+        raise NotImplementedError()
+
+    def load_model(self, filepath, *args, **kwargs):
+        raise NotImplementedError()
+
+
+class TorchNNTrainer(RecSysModel):
+    """Abstract trainer of a torch network (rectorch/models.py:164-322)."""
+
+    def __init__(self, net, learning_rate=1e-3):
+        self.network = net
+        self.learning_rate = learning_rate
+        self.optimizer = None
+        if next(self.network.parameters()).is_cuda:
+            self.device = torch.device("cuda")
+        else:
+            self.device = torch.device("cpu")
+
+    def loss_function(self, prediction, ground_truth, *args, **kwargs):
+        raise NotImplementedError()
+
+    def train(self, train_data, valid_data=None, valid_metric=None, valid_func=ValidFunc(evaluate),
+              num_epochs=100, verbose=1, **kwargs):
+        raise NotImplementedError()
+
+    def train_epoch(self, epoch, train_data, *args, **kwargs):
+        raise NotImplementedError()
+
+    def train_batch(self, epoch, tr_batch, te_batch, *args, **kwargs):
+        raise NotImplementedError()
+
+    def predict(self, x, *args, **kwargs):
+        raise NotImplementedError()
+
+    def __str__(self):
+        s = self.__class__.__name__ + "(\n"
+        for k, v in self.__dict__.items():
+            if k.startswith("_"):
+                continue
+            sv = "\n".join(["  " + line for line in str(str(v)).split("\n")])[2:]
+            s += "  %s = %s,\n" % (k, sv)
+        s = s[:-2] + "\n)"
+        return s
+
+    def __repr__(self):
+        return str(self)
+
+
+def _dist_world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+class AETrainer(TorchNNTrainer):
+    """Shared machinery of the two auto-encoder trainers (epoch loop, logging, predict,
+    checkpoints: rectorch/models.py:379-516)."""
+
+    _b200_trainer = True
+    _is_vae = False
+    _weight_decay = 0.0
+
+    def __init__(self, ae_net, learning_rate=1e-3):
+        super(AETrainer, self).__init__(ae_net, learning_rate)
+        if self.device.type != "cuda":
+            raise RuntimeError(
+                "rectorch_b200 trainers run on a Blackwell GPU only (the network is on %s). Build the "
+                "network and move it first: MultiVAE(MultiVAE_net(dims).cuda()). There is no CPU fallback."
+                % self.device)
+        self._engine = self.network.engine          # adopts the parameters into the flat arenas
+        self.device = self._engine.device
+        self._make_optimizer(learning_rate)
+        self._loss_hist = torch.zeros(4 * 4096, dtype=torch.float32, device=self.device)
+
+    # ---- optimizer <-> arena coupling --------------------------------------------------------------
+    def _make_optimizer(self, lr):
+        self.optimizer = optim.Adam(self.network.parameters(), lr=lr, weight_decay=self._weight_decay)
+        self._adopt_optimizer_state(fresh=True)
+
+    def _adopt_optimizer_state(self, fresh=False):
+        """Make ``optimizer.state[p]`` = {'step', 'exp_avg', 'exp_avg_sq'} with the moments being
+        VIEWS of the engine's m / v arenas (what torch.optim.Adam lazily creates on its first
+        step, torch/optim/adam.py::_init_group).  After ``optimizer.load_state_dict`` the loaded
+        moments are copied into the arenas first."""
+        eng = self._engine
+        views = eng.state_views()
+        step_val = 0.0
+        old = self.optimizer.state
+        with torch.no_grad():
+            for p, (mv, vv) in zip(eng.params, views):
+                st = old.get(p, {})
+                if not fresh and "exp_avg" in st:
+                    mv.copy_(st["exp_avg"])
+                    vv.copy_(st["exp_avg_sq"])
+                    step_val = float(st["step"])
+        self._step_tensor = torch.tensor(step_val, dtype=torch.float32)
+        for p, (mv, vv) in zip(eng.params, views):
+            self.optimizer.state[p] = {"step": self._step_tensor, "exp_avg": mv, "exp_avg_sq": vv}
+        eng.adam_steps = int(step_val)
+        if fresh:
+            eng.m.zero_()
+            eng.v.zero_()
+
+    def _hyper(self):
+        g = self.optimizer.param_groups[0]
+        return g["lr"], g["betas"], g["eps"], g["weight_decay"]
+
+    # ---- batch plumbing ----------------------------------------------------------------------------------
+    def _bind_sampler(self, sampler):
+        if getattr(self, "_bound_sampler", None) is not sampler:
+            tr, te = sampler.device_csr(self.device)
+            self._engine.bind_csr(0, tr)
+            if te is not None:
+                self._engine.bind_csr(1, te)
+            self._bound_sampler = sampler
+
+    def _step(self, tr_batch, te_batch, beta, lam, loss_slot):
+        """Launch one optimisation step; the 4 loss components land in ``loss_slot`` (device)."""
+        eng = self._engine
+        net = self.network
+        lr, betas, eps, wd = self._hyper()
+        p = float(net.dropout.p)
+        seed = draw_seed()
+        rank, world = _dist_world()
+        kw = dict(beta=beta, lam=lam, dropout_p=p, seed=seed)
+        if isinstance(tr_batch, RowBatch):
+            self._bind_sampler(tr_batch.sampler)
+            kw["rows"] = tr_batch.rows
+            kw["use_target"] = bool(self._is_vae and tr_batch.has_te and te_batch is not None)
+            row_offset = tr_batch.sampler.row_offset
+            B_local = int(tr_batch.rows.numel())
+        else:
+            kw["dense"] = Engine._as_dense(tr_batch, self.device)
+            if self._is_vae and te_batch is not None:
+                kw["dense_target"] = Engine._as_dense(te_batch, self.device)
+            row_offset = 0
+            B_local = int(kw["dense"].shape[0])
+        eng.loss_buf = loss_slot
+        if world == 1:
+            eng.train_step(lr=lr, betas=betas, eps=eps, weight_decay=wd, **kw)
+        else:
+            # row-sharded data parallelism: local gradients are already scaled by 1/B_global
+            eng.forward_backward(B_global=B_local * world, step=eng.adam_steps + 1, row_offset=row_offset, **kw)
+            dist.all_reduce(eng.g, op=dist.ReduceOp.SUM)
+            dist.all_reduce(loss_slot, op=dist.ReduceOp.SUM)
+            eng.adam(lr, betas, eps, wd, lam)
+        self._step_tensor += 1.0
+
+    def _loss_from(self, comps, beta, lam):
+        """Python float loss from the 4 device components (sum over ranks already applied)."""
+        c = comps.tolist()
+        _, world = _dist_world()
+        if world == 1:
+            return c[0]
+        return c[1] + beta * c[2] + lam * (c[3] / world)
+
+    # ---- reference API -----------------------------------------------------------------------------------
+    def train(self, train_data, valid_data=None, valid_metric=None, valid_func=ValidFunc(evaluate),
+              num_epochs=100, verbose=1):
+        try:
+            for epoch in range(1, num_epochs + 1):
+                self.train_epoch(epoch, train_data, verbose)
+                if valid_data is not None:
+                    assert valid_metric is not None, \
+                        "In case of validation 'valid_metric' must be provided"
+                    valid_res = valid_func(self, valid_data, valid_metric)
+                    mu_val = np.mean(valid_res)
+                    std_err_val = np.std(valid_res) / np.sqrt(len(valid_res))
+                    logger.info('| epoch %d | %s %.3f (%.4f) |', epoch, valid_metric, mu_val, std_err_val)
+        except KeyboardInterrupt:
+            logger.warning('Handled KeyboardInterrupt: exiting from training early')
+
+    def train_epoch(self, epoch, train_loader, verbose=1):
+        """rectorch/models.py:401-422.  With this package's DataSampler the loop never builds a
+        dense batch and reads the losses back once per log window instead of once per batch."""
+        self.network.train()
+        train_loss = 0
+        partial_loss = 0
+        epoch_start_time = time.time()
+        start_time = time.time()
+        n_batches = len(train_loader)
+        log_delay = max(10, n_batches // 10 ** verbose)
+        fast = isinstance(train_loader, DataSampler)
+        it = train_loader.iter_rows(self.device) if fast else train_loader
+        window = []       # (slot index, beta, lam) of steps whose loss is still on the device
+        cap = self._loss_hist.numel() // 4
+        for batch_idx, item in enumerate(it):
+            if fast:
+                slot = len(window) % cap
+                beta, lam = self._step_coeffs()
+                self._step(item, item if item.has_te else None, beta, lam, self._loss_hist[4 * slot:4 * slot + 4])
+                self._after_step()
+                window.append((slot, beta, lam))
+                flush = (batch_idx + 1) % log_delay == 0 or len(window) == cap
+                if flush:
+                    partial_loss += self._drain(window)
+            else:
+                data, gt = item
+                partial_loss += self.train_batch(data, gt)
+            if (batch_idx + 1) % log_delay == 0:
+                elapsed = time.time() - start_time
+                logger.info('| epoch %d | %d/%d batches | ms/batch %.2f | loss %.2f |',
+                            epoch, (batch_idx + 1), n_batches, elapsed * 1000 / log_delay,
+                            partial_loss / log_delay)
+                train_loss += partial_loss
+                partial_loss = 0.0
+                start_time = time.time()
+        if window:
+            partial_loss += self._drain(window)
+        if fast:
+            self._engine.check_overflow()
+        total_loss = (train_loss + partial_loss) / max(n_batches, 1)
+        time_diff = time.time() - epoch_start_time
+        logger.info("| epoch %d | loss %.4f | total time: %.2fs |", epoch, total_loss, time_diff)
+        self.last_epoch_loss = total_loss
+        return total_loss
+
+    def _drain(self, window):
+        hist = self._loss_hist[:4 * (max(s for s, _, _ in window) + 1)].view(-1, 4).cpu()
+        total = 0.0
+        for slot, beta, lam in window:
+            total += self._loss_from(hist[slot], beta, lam)
+        window.clear()
+        return total
+
+    def _step_coeffs(self):
+        return 0.0, 0.0
+
+    def _after_step(self):
+        pass
+
+    def train_batch(self, tr_batch, te_batch=None):
+        """One optimisation step; returns the loss as a python float (device -> host sync), like
+        rectorch/models.py:424-447 / 817-835."""
+        beta, lam = self._step_coeffs()
+        slot = self._loss_hist[:4]
+        self._step(tr_batch, te_batch, beta, lam, slot)
+        self._after_step()
+        return self._loss_from(slot, beta, lam)
+
+    def predict(self, x, remove_train=True):
+        """Eval-mode scores; ``remove_train`` sets the scores of x's non-zeros to -inf
+        (rectorch/models.py:449-473, 594-625).  ``x``: dense tensor (any device) or RowBatch."""
+        self.network.eval()
+        eng = self._engine
+        if isinstance(x, RowBatch):
+            self._bind_sampler(x.sampler)
+            scores, mu, logvar = eng.predict(rows=x.rows, remove_train=remove_train)
+        else:
+            scores, mu, logvar = eng.predict(dense=Engine._as_dense(x, self.device), remove_train=remove_train)
+        if self._is_vae:
+            return scores, mu, logvar
+        return (scores, )
+
+    def save_model(self, filepath, cur_epoch):
+        state = {'epoch': cur_epoch,
+                 'state_dict': self.network.state_dict(),
+                 'optimizer': self.optimizer.state_dict()}
+        self._save_checkpoint(filepath, state)
+
+    def _save_checkpoint(self, filepath, state):
+        logger.info("Saving model checkpoint to %s...", filepath)
+        torch.save(state, filepath)
+        logger.info("Model checkpoint saved!")
+
+    def load_model(self, filepath):
+        assert os.path.isfile(filepath), "The checkpoint file %s does not exist." % filepath
+        logger.info("Loading model checkpoint from %s...", filepath)
+        checkpoint = torch.load(filepath, map_location=self.device, weights_only=False)
+        self.network.load_state_dict(checkpoint['state_dict'])
+        self.optimizer.load_state_dict(checkpoint['optimizer'])
+        self._adopt_optimizer_state(fresh=False)
+        logger.info("Model checkpoint loaded!")
+        return checkpoint
+
+    # ---- dense-tensor loss API --------------------------------------------------------------------------------
+    def _nll_dense(self, recon_x, x):
+        dev = self.device
+        r = Engine._as_dense(recon_x, dev)
+        t = Engine._as_dense(x, dev)
+        assert r.shape == t.shape, "recon_x and x must have the same shape"
+        rows = torch.empty(r.shape[0], dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().b200vae_multinomial_nll_rows(ptr(r), ptr(t), r.shape[0], r.shape[1], ptr(rows),
+                                                          stream_ptr()))
+        return rows.mean()
+
+
+class MultiDAE(AETrainer):
+    """Denoising auto-encoder trainer (rectorch/models.py:628-706): multinomial NLL +
+    ``lam * sum_p ||p||_2`` (un-squared norm per parameter tensor, biases included), Adam with
+    coupled ``weight_decay=0.001`` (models.py:657-659).  ``train_batch`` ignores ``te_batch``
+    (AETrainer.train_batch, models.py:441-446)."""
+
+    _is_vae = False
+    _weight_decay = 0.001
+
+    def __init__(self, mdae_net, lam=0.2, learning_rate=1e-3):
+        super(MultiDAE, self).__init__(mdae_net, learning_rate)
+        self.lam = lam
+
+    def _step_coeffs(self):
+        return 0.0, float(self.lam)
+
+    def loss_function(self, recon_x, x):
+        bce = self._nll_dense(recon_x, x)
+        return bce + self.lam * param_norm_sum(self._engine)
+
+
+class MultiVAE(AETrainer):
+    """Variational auto-encoder trainer (rectorch/models.py:709-908): multinomial NLL +
+    ``beta_t * KL`` with linear annealing ``beta_t = min(beta, updates / anneal_steps)``
+    (models.py:824-827), Adam without weight decay, best-on-validation checkpointing in
+    :meth:`train` (models.py:879-892)."""
+
+    _is_vae = True
+    _weight_decay = 0.0
+
+    def __init__(self, mvae_net, beta=1., anneal_steps=0, learning_rate=1e-3):
+        super(MultiVAE, self).__init__(mvae_net, learning_rate=learning_rate)
+        self.anneal_steps = anneal_steps
+        self.annealing = anneal_steps > 0
+        self.gradient_updates = 0.
+        self.beta = beta
+
+    def _step_coeffs(self):
+        if self.annealing:
+            return min(self.beta, 1. * self.gradient_updates / self.anneal_steps), 0.0
+        return self.beta, 0.0
+
+    def _after_step(self):
+        self.gradient_updates += 1.
+
+    def loss_function(self, recon_x, x, mu, logvar, beta=1.0):
+        bce = self._nll_dense(recon_x, x)
+        dev = self.device
+        m = Engine._as_dense(mu, dev)
+        lv = Engine._as_dense(logvar, dev)
+        rows = torch.empty(m.shape[0], dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().b200vae_kl_rows(ptr(m), ptr(lv), m.shape[0], m.shape[1], ptr(rows), stream_ptr()))
+        return bce + beta * rows.mean()
+
+    def train(self, train_data, valid_data=None, valid_metric=None, valid_func=ValidFunc(evaluate),
+              num_epochs=200, best_path="chkpt_best.pth", verbose=1):
+        try:
+            best_perf = -1.
+            for epoch in range(1, num_epochs + 1):
+                self.train_epoch(epoch, train_data, verbose)
+                if valid_data:
+                    assert valid_metric is not None, \
+                        "In case of validation 'valid_metric' must be provided"
+                    valid_res = valid_func(self, valid_data, valid_metric)
+                    mu_val = np.mean(valid_res)
+                    std_err_val = np.std(valid_res) / np.sqrt(len(valid_res))
+                    logger.info('| epoch %d | %s %.3f (%.4f) |', epoch, valid_metric, mu_val, std_err_val)
+                    if best_perf < mu_val:
+                        self.save_model(best_path, epoch)
+                        best_perf = mu_val
+        except KeyboardInterrupt:
+            logger.warning('Handled KeyboardInterrupt: exiting from training early')
+
+    def save_model(self, filepath, cur_epoch):
+        state = {'epoch': cur_epoch,
+                 'state_dict': self.network.state_dict(),
+                 'optimizer': self.optimizer.state_dict(),
+                 'gradient_updates': self.gradient_updates}
+        self._save_checkpoint(filepath, state)
+
+    def load_model(self, filepath):
+        checkpoint = super().load_model(filepath)
+        self.gradient_updates = checkpoint['gradient_updates']
+        return checkpoint

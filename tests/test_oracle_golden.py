@@ -1,0 +1,99 @@
+"""CPU: the oracle restatement against the fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py) and against the reference's own known answers."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import multvae_oracle as O
+from tests._util import golden_matrices, load_golden, oracle_net, rel_err
+
+CASES = ["cfg1_dae", "small_vae", "vae_1layer", "small_dae"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_training_matches_reference(name):
+    g = load_golden(name)
+    tr, te = golden_matrices(g)
+    net = oracle_net(g)
+    st = O.AdamState(net, lr=1e-3, weight_decay=0.0 if g["vae"] else 1e-3)
+    sp_tr = tr.to_scipy()
+    sp_te = te.to_scipy() if (te is not None and g["vae"]) else None
+    losses = []
+    for it, (x, t) in enumerate(O.batches(sp_tr, sp_te, g["batch"])):
+        if it >= g["steps"]:
+            break
+        beta_t = O.beta_schedule(g["beta"], g["anneal"], it) if g["vae"] else 0.0
+        drop, eps = O.replay_rng_tape(g["seed_rng"] + it, x.shape[0], g["n_items"], g["dec_dims"][0], g["p"], g["vae"])
+        losses.append(O.train_step(net, st, x, t, beta=beta_t, lam=g["lam"], drop_scale=drop, eps=eps))
+    assert rel_err(losses, g["ref_losses"]).max() <= 2e-6
+    sd = net.state_dict()
+    for k, v in sd.items():
+        assert np.abs(v.numpy() - g["final/" + k]).max() <= 2e-6, k
+    # Adam moments too (parameters() order)
+    for i, k in enumerate(sd.keys()):
+        assert np.abs(st.m[i].numpy() - g["adam_m/" + k]).max() <= 1e-6, k
+        assert np.abs(st.v[i].numpy() - g["adam_v/" + k]).max() <= 1e-6, k
+
+
+@pytest.mark.parametrize("name", ["cfg1_dae", "small_vae", "small_dae"])
+def test_evaluation_matches_reference(name):
+    g = load_golden(name)
+    tr, te = golden_matrices(g)
+    net = oracle_net(g, "final")
+    mets = [k[len("metric/"):] for k in g if k.startswith("metric/")]
+    res = O.evaluate(net, tr.to_scipy(), te.to_scipy(), g["batch"], mets)
+    for m in mets:
+        ref = g["metric/" + m].astype(np.float64)
+        mine = np.asarray(res[m], dtype=np.float64)
+        assert np.array_equal(np.isnan(ref), np.isnan(mine)), m          # users without heldout -> NaN
+        assert abs(np.nanmean(ref) - np.nanmean(mine)) < 1e-6, m
+    x0 = torch.from_numpy(tr.rows(0, min(g["batch"], g["n_users"])).toarray())
+    pred = O.predict(net, x0, True)[0].numpy()
+    ref = g["pred0"]
+    assert np.array_equal(np.isinf(ref), np.isinf(pred))
+    fin = np.isfinite(ref)
+    assert np.abs(pred[fin] - ref[fin]).max() < 1e-5
+
+
+def test_metric_known_answers():
+    """rectorch/tests/test_metrics.py:18-61 and the fixture derived from the reference."""
+    scores = np.array([[4., 3., 2., 1.]])
+    gt = np.array([[1., 1., 0., 0.]])
+    gt2 = np.array([[0, 0, 1., 1.]])
+    assert O.ndcg_at_k(scores, gt, 2)[0] == 1.0
+    assert O.ndcg_at_k(scores, gt2, 2)[0] == 0.0
+    assert abs(O.ndcg_at_k(scores, gt2, 3)[0] - 0.3065735964) < 1e-5
+    s5 = np.array([[4., 3., 2., 1., 0.]])
+    g5 = np.array([[1., 1., 0., 0., 1.]])
+    g5b = np.array([[0, 0, 1., 1., 1.]])
+    assert O.recall_at_k(s5, g5, 2)[0] == 1.0 and O.recall_at_k(s5, g5b, 2)[0] == 0.0
+    assert abs(O.recall_at_k(s5, g5, 3)[0] - 0.6666666) < 1e-5
+    assert abs(O.recall_at_k(s5, g5b, 3)[0] - 0.3333333) < 1e-5
+    s2 = np.array([[4., 3., 2., 1.], [1., 2., 3., 4.]])
+    g2 = np.array([[0, 0, 1., 1.], [0, 0, 1., 1.]])
+    assert np.all(O.hit_at_k(s2, g2, 3) == np.array([1., 1.])) and np.all(O.hit_at_k(s2, g2, 2) == np.array([0., 1.]))
+    s3 = np.array([[4., 2., 3., 1.], [1., 2., 3., 4.]])
+    assert np.all(O.mrr_at_k(s3, g2, 3) == np.array([.5, 1.])) and np.all(O.mrr_at_k(s3, g2, 1) == np.array([0., 1.]))
+    z = np.load("tests/golden/metrics_small.npz") if False else None  # noqa: F841 (fixture checked below)
+
+
+def test_metric_fixture(golden_dir):
+    import os
+    z = np.load(os.path.join(golden_dir, "metrics_small.npz"))
+    for m in z.files:
+        if "@" not in m:
+            continue
+        mine = np.asarray(O.compute_metrics(z["scores"], z["gt"], [m])[m], dtype=np.float64)
+        assert np.allclose(mine, z[m]), m
+
+
+def test_loss_known_answer():
+    """loss(recon=[[1,1],[1,1]], x=[[1,1],[2,1]], mu=0, logvar=0) = mean(2ln2, 3ln2)."""
+    w = torch.zeros(2, 2)
+    net = O.Net([(torch.zeros(4, 2), torch.zeros(4))], [(w, torch.zeros(2))], True, 0.0)
+    c = {"logits": torch.ones(2, 2), "mu": torch.zeros(2, 2), "logvar": torch.zeros(2, 2)}
+    val = float(O.loss_value(net, c, torch.tensor([[1., 1.], [2., 1.]]), beta=1.0))
+    assert abs(val - 2.5 * math.log(2.0)) < 1e-6
+    assert abs(val - 1.7328680) < 1e-6
