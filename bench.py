@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- users/sec of MultiVAE training (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --steps K --warmup W    # reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[1], "cfg2"): MultiVAE [50000-600-200] =
+MultiVAE_net([200, 600, 50000]), synthetic 200K users x 50K items per GPU (Zipf/lognormal
+generator of rectorch_b200/synth.py), batch 500 per GPU, dropout 0.5, beta 0.2 with
+anneal_steps 20000, Adam lr 1e-3.  One "step" = one train_batch (forward, loss, backward, Adam;
+plus ONE all_reduce of the flat gradient arena when N > 1) on 500 users per GPU.  Weak scaling:
+per-GPU batch and per-GPU user shard are fixed, the global batch is 500*N.
+
+One JSON line on stdout (rank 0):
+  value        users/s with the CSR matrix resident in HBM (CUDA-event timed, max over ranks)
+  e2e          users/s through the C-ABI call with HOST (pinned) CSR batches: H2D of the batch,
+               the step, D2H of the loss, every step inside the timed region
+  roofline     dominant kernel of the step (by measured time) vs MEASURED_PEAKS.json
+  roofline_k4  the fused decoder-GEMM + log-softmax kernel (north-star kernel), HBM and tensor view
+  cpu_baseline the oracle port (torch-CPU restatement of the reference path) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CFG = {"name": "cfg2", "dec_dims": [200, 600, 50000], "n_users": 200_000, "n_items": 50_000, "batch": 500,
+       "dropout": 0.5, "beta": 0.2, "anneal_steps": 20000, "lr": 1e-3}
+METRIC = "users/sec (MultiVAE [50000-600-200], batch 500/GPU, synthetic 200K x 50K per GPU)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons = [], None, set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, budget_s, batch=None, n_rows=None):
+    """Times oracle.train_step (dense [B x I] tensors, explicit backward + Adam, torch CPU ops with all
+    host threads) including the sampler's CSR->dense expansion and the RNG draws, like the reference's
+    train_epoch loop (models.py:409-410, samplers.py:99-100)."""
+    from oracle import multvae_oracle as O
+    from rectorch_b200 import synth
+    from rectorch_b200.nets import MultiVAE_net
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = batch or CFG["batch"]
+    total = steps + warmup
+    n_rows = n_rows or B * total
+    csr = synth.make_matrix(min(n_rows, CFG["n_users"]), CFG["n_items"], seed=synth.DEFAULT_SEED)
+    sp = csr.to_scipy()
+    torch.manual_seed(0)
+    net = MultiVAE_net(list(CFG["dec_dims"]), None, CFG["dropout"])
+    onet = O.Net.from_state_dict({k: v.detach() for k, v in net.state_dict().items()}, True, CFG["dropout"])
+    ost = O.AdamState(onet, lr=CFG["lr"])
+    # calibrate the bounded sample: one untimed step at the full batch
+    t0 = time.perf_counter()
+    x = torch.from_numpy(np.asarray(sp[0:B].toarray(), dtype=np.float32))
+    drop, eps = O.replay_rng_tape(1, B, CFG["n_items"], CFG["dec_dims"][0], CFG["dropout"], True)
+    O.train_step(onet, ost, x, None, beta=0.0, drop_scale=drop, eps=eps)
+    per_step = time.perf_counter() - t0
+    if per_step * total > budget_s:
+        B = int(max(100, min(B, B * budget_s / (per_step * total))))
+    it_rows = sp.shape[0]
+    times = []
+    for it in range(total):
+        lo = (it * B) % max(it_rows - B, 1)
+        t0 = time.perf_counter()
+        x = torch.from_numpy(np.asarray(sp[lo:lo + B].toarray(), dtype=np.float32))
+        drop, eps = O.replay_rng_tape(100 + it, B, CFG["n_items"], CFG["dec_dims"][0], CFG["dropout"], True)
+        beta_t = O.beta_schedule(CFG["beta"], CFG["anneal_steps"], it)
+        O.train_step(onet, ost, x, None, beta=beta_t, drop_scale=drop, eps=eps)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    return {"value": B / (ms / 1e3), "ms_per_step": ms, "batch": B, "cores": cores,
+            "sample": "%d steps x %d users of the cfg2 workload (dense [B x 50000] fp32, sampler + RNG + fwd + "
+                      "bwd + Adam), torch %s CPU ops, %d threads" % (len(times), B, torch.__version__, cores)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup, budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "users/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg2: MultiVAE [50000-600-200], batch %d (bounded sample of the 200K x 50K matrix)" % r["batch"],
+                       "global_batch": r["batch"], "timing": "host wall clock; inputs (240 MB of weights) exceed L2"},
+            "cpu_baseline": {"value": r["value"], "unit": "users/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "users/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from rectorch_b200 import synth
+    from rectorch_b200.models import MultiVAE
+    from rectorch_b200.nets import MultiVAE_net
+    from rectorch_b200.samplers import DataSampler
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    B, K, W = CFG["batch"], args.steps, args.warmup
+    n_users = min(CFG["n_users"], max(B * (K + W), B * 8))
+    n_users = CFG["n_users"] if args.full_matrix else n_users
+    csr = synth.make_matrix(n_users, CFG["n_items"], seed=synth.DEFAULT_SEED + rank)
+    torch.manual_seed(0)
+    net = MultiVAE_net(list(CFG["dec_dims"]), None, CFG["dropout"]).cuda(dev)
+    model = MultiVAE(net, beta=CFG["beta"], anneal_steps=CFG["anneal_steps"], learning_rate=CFG["lr"])
+    eng = model._engine
+    sampler = DataSampler(csr, None, batch_size=B, shuffle=False, device=dev)
+    batches = list(sampler.iter_rows(dev))
+    model.network.train()
+    slots = model._loss_hist
+
+    def step(i):
+        rb = batches[i % len(batches)]
+        beta, lam = model._step_coeffs()
+        model._step(rb, None, beta, lam, slots[4 * (i % 1024):4 * (i % 1024) + 4])
+        model._after_step()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(W):
+        step(i)
+    barrier()
+    eng.launch_count(reset=True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(W, W + K):
+        step(i)
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if rank == 0 else None
+    launches = eng.launch_count()
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    eng.check_overflow()
+    last_loss = float(slots[4 * ((W + K - 1) % 1024)].item())
+    ms_step = ms_total / K
+    value = world * B / (ms_step / 1e3)
+
+    # ---- e2e: host (pinned) CSR batches through the C ABI, H2D + step + D2H loss every step ----
+    from rectorch_b200 import _lib
+    from rectorch_b200._lib import check
+    import ctypes
+    nb = min(len(batches), 64)
+    host = []
+    for b in range(nb):
+        sl = csr.rows(b * B, (b + 1) * B)
+        ip = torch.from_numpy(sl.indptr.copy()).pin_memory()
+        ix = torch.from_numpy(sl.indices.copy()).pin_memory()
+        host.append((ip, ix))
+    loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+    h2d = float(np.mean([ip.numel() * 8 + ix.numel() * 4 for ip, ix in host]))
+    e2e_steps = min(K, 200)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+
+    def host_step(i):
+        ip, ix = host[i % nb]
+        beta, _ = model._step_coeffs()
+        eng.adam_steps += 1
+        check(_lib.lib().b200vae_train_step_host(eng._ctx, ctypes.c_void_p(ip.data_ptr()), ctypes.c_void_p(ix.data_ptr()),
+                                                 None, B, float(beta), 0.0, CFG["dropout"], 12345 + i, eng.adam_steps,
+                                                 CFG["lr"], 0.0, ctypes.c_void_p(loss_host.data_ptr()),
+                                                 ctypes.c_void_p(stream)))
+        model._after_step()
+
+    e2e = None
+    if world == 1:
+        for i in range(3):
+            host_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            host_step(i)
+        barrier()
+        dt = time.perf_counter() - t0
+        e2e = {"value": B * e2e_steps / dt, "unit": "users/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 16,
+               "steps": e2e_steps, "api": "b200vae_train_step_host (pinned host CSR batch -> loss[4] on host, stream sync per step)"}
+        # the reference-shaped call: train_batch(dense host FloatTensor [B x I]) -- PCIe bound (100 MB/step)
+        xd = torch.from_numpy(csr.rows(0, B).toarray()).pin_memory()
+        model.train_batch(xd)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(10):
+            model.train_batch(xd)
+        barrier()
+        dtd = time.perf_counter() - t0
+        e2e["dense_api"] = {"value": B * 10 / dtd, "unit": "users/s", "h2d_bytes_per_step": int(xd.numel() * 4),
+                            "api": "MultiVAE.train_batch(pinned dense FloatTensor) as the reference's loop does"}
+    else:
+        # N > 1: the public trainer call per step with a host sync of the loss (train_batch)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            model.train_batch(batches[i % len(batches)])
+        barrier()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * e2e_steps / float(t.item()), "unit": "users/s", "h2d_bytes_per_step": 0,
+               "d2h_bytes_per_step": 16, "steps": e2e_steps,
+               "api": "MultiVAE.train_batch(RowBatch) + loss read back every step (CSR resident per rank)"}
+
+    # ---- per-kernel timing pass (CUDA events inside the library, on the launching stream) ----
+    eng.set_timing(True)
+    names = ["dec_fwd_lse(K4)", "adam(K8)", "dec_bwd_prob(K5)", "dWd_gemm", "dh_gemm"]
+    acc = np.zeros(5)
+    reps = 20
+    for i in range(reps):
+        step(W + K + i)
+        torch.cuda.synchronize(dev)
+        acc += np.array([eng.kernel_ms(j) for j in range(5)])
+    eng.set_timing(False)
+    kms = acc / reps
+    peaks = load_peaks()
+    P = eng.n_elems
+    I, H = CFG["n_items"], CFG["dec_dims"][1]
+    nnz_b = float(np.mean([ix.numel() for _, ix in host])) if host else 0.0
+    adam_bytes = 28.0 * P + 4.0 * I * H          # w,g,m,v read; w,m,v written; + tf32 shadow of W_d written
+    k4_bytes = 4.0 * I * H + 4.0 * I + 4.0 * B * H + 8.0 * B * (-(-I // 256))
+    k4_flops = 2.0 * B * I * H
+    dom = int(np.argmax(kms))
+    roof_dom = None
+    if dom == 1:
+        ach = adam_bytes / (kms[1] * 1e-3) / 1e9
+        roof_dom = {"kernel": names[1], "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms": float(kms[1]), "peak_src": peaks["src"]}
+    else:
+        flops = {0: k4_flops, 2: k4_flops, 3: 2.0 * B * I * (H + 8), 4: 2.0 * B * I * H}[dom]
+        ach = flops / (kms[dom] * 1e-3) / 1e12
+        pk = peaks["bf16_tflops_sustained"] / 2.0
+        roof_dom = {"kernel": names[dom], "bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s",
+                    "frac": ach / pk, "traffic": None, "ms": float(kms[dom]),
+                    "peak_src": peaks["src"] + " bf16 sustained / 2 (tf32)"}
+    k4_gbs = k4_bytes / (kms[0] * 1e-3) / 1e9 if kms[0] > 0 else None
+    k4_tf = k4_flops / (kms[0] * 1e-3) / 1e12 if kms[0] > 0 else None
+    roof_k4 = {"kernel": names[0], "ms": float(kms[0]), "hbm_gbs": k4_gbs, "hbm_frac": (k4_gbs or 0) / peaks["hbm_gbs"],
+               "tflops_tf32": k4_tf, "tensor_frac_of_bf16_half": (k4_tf or 0) / (peaks["bf16_tflops"] / 2.0),
+               "algorithmic_bytes": k4_bytes, "flops": k4_flops}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(6, 2, budget_s=25.0)
+        cpu = {"value": r["value"], "unit": "users/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "users/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (tf32 tensor-core operands, fp32 accumulate)", "data": "synthetic",
+                "config": {"workload": "cfg2: MultiVAE [50000-600-200], %d users x 50000 items per GPU, batch %d per GPU"
+                                       % (n_users, B), "global_batch": B * world, "parallelism": "dp%d row-sharded, 1 allreduce/step" % world,
+                           "l2": "no flush: per-step working set (4 x 242 MB arenas) exceeds the 126 MB L2"},
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+                "roofline": roof_dom, "roofline_k4": roof_k4,
+                "kernel_ms": {n: float(v) for n, v in zip(names, kms)},
+                "cpu_baseline": cpu, "last_loss": last_loss}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--full-matrix", action="store_true", help="generate all 200K users per GPU even for short runs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

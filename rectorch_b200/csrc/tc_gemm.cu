@@ -108,15 +108,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// SM100 shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor layout:
-// start[0,14) LBO[16,30) SBO[32,46) version[46,48)=1 layout_type[61,64)=2)
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// SM100 shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout:
+// start[0,14) LBO[16,30) SBO[32,46) version[46,48)=1 layout_type[61,64)).
+//   K-major  operands: layout_type 2 = SWIZZLE_128B (8 rows x 128 B atoms, 16 B swizzle granules),
+//                      SBO = 1024 (stride between 8-row groups), LBO unused.
+//   MN-major tf32 operands: the ONLY layout the tensor core accepts is layout_type 1 =
+//                      SWIZZLE_128B_BASE32B (4 K-rows x 128 B atoms, 32 B swizzle granules;
+//                      TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): SBO = 512 (stride between
+//                      4-K-row groups), LBO = stride between 32-float MN chunks.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
     uint64_t d = 0;
     d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= 1ull << 46;
-    d |= 2ull << 61;
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 
@@ -238,8 +244,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint32_t sb = sa + TC_A_BYTES;
 #pragma unroll
                     for (int j = 0; j < TC_BK / 8; ++j) {
-                        const uint64_t ad = A_MN ? make_sdesc(sa + j * 1024, 4096, 1024) : make_sdesc(sa + j * 32, 0, 1024);
-                        const uint64_t bd = B_MN ? make_sdesc(sb + j * 1024, 4096, 1024) : make_sdesc(sb + j * 32, 0, 1024);
+                        const uint64_t ad = A_MN ? make_sdesc(sa + j * 1024, 4096, 512, 1) : make_sdesc(sa + j * 32, 0, 1024, 2);
+                        const uint64_t bd = B_MN ? make_sdesc(sb + j * 1024, 4096, 512, 1) : make_sdesc(sb + j * 32, 0, 1024, 2);
                         tcgen05_mma_tf32(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
                     }
                     tcgen05_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
@@ -369,7 +375,7 @@ static EncodeTiledFn get_encode() {
 
 // 2-D fp32 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, row pitch ld floats
 static int make_tmap(CUtensorMap* tm, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
-                     int box_outer) {
+                     int box_outer, bool mn_major) {
     EncodeTiledFn enc = get_encode();
     B200_REQUIRE(enc, B200VAE_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
@@ -377,7 +383,9 @@ static int make_tmap(CUtensorMap* tm, const float* base, int64_t inner, int64_t 
     cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, B200VAE_ECUDA,
                  "cuTensorMapEncodeTiled failed (%d): base %p inner %lld outer %lld ld %lld box %dx%d", (int)r, base,
@@ -433,10 +441,10 @@ int launch_tc_gemm(Ctx* c, int mode, const float* A, int64_t lda, int a_mn, cons
                                      (size_t)(e.split_k - a.split_k) * e.split_stride * sizeof(float), s));
     }
     CUtensorMap tmA, tmB;
-    if (!a_mn) B200_CHECK(make_tmap(&tmA, A, K, M, lda, TC_BK, TC_BM));
-    else       B200_CHECK(make_tmap(&tmA, A, M, K, lda, 32, TC_BK));
-    if (!b_mn) B200_CHECK(make_tmap(&tmB, B, K, N, ldb, TC_BK, a.BN));
-    else       B200_CHECK(make_tmap(&tmB, B, N, K, ldb, 32, TC_BK));
+    if (!a_mn) B200_CHECK(make_tmap(&tmA, A, K, M, lda, TC_BK, TC_BM, false));
+    else       B200_CHECK(make_tmap(&tmA, A, M, K, lda, 32, TC_BK, true));
+    if (!b_mn) B200_CHECK(make_tmap(&tmB, B, K, N, ldb, TC_BK, a.BN, false));
+    else       B200_CHECK(make_tmap(&tmB, B, N, K, ldb, 32, TC_BK, true));
     const int total = a.tiles_m * a.tiles_n * a.split_k;
     const int grid = std::min(total, c->num_sms);
     int rc;

@@ -160,8 +160,9 @@ class AETrainer(TorchNNTrainer):
                 self._engine.bind_csr(1, te)
             self._bound_sampler = sampler
 
-    def _step(self, tr_batch, te_batch, beta, lam, loss_slot):
-        """Launch one optimisation step; the 4 loss components land in ``loss_slot`` (device)."""
+    def _step(self, tr_batch, te_batch, beta, lam, loss_slot, rng_tape=None):
+        """Launch one optimisation step; the 4 loss components land in ``loss_slot`` (device).
+        ``rng_tape = (keep_bytes_at_nonzeros, eps)`` replaces the Philox draws (parity tests)."""
         eng = self._engine
         net = self.network
         lr, betas, eps, wd = self._hyper()
@@ -169,6 +170,10 @@ class AETrainer(TorchNNTrainer):
         seed = draw_seed()
         rank, world = _dist_world()
         kw = dict(beta=beta, lam=lam, dropout_p=p, seed=seed)
+        if rng_tape is not None:
+            keep, eps_t = rng_tape
+            kw["keep_tape"] = None if keep is None else keep.to(self.device, dtype=torch.uint8).contiguous()
+            kw["eps_tape"] = None if eps_t is None else eps_t.to(self.device, dtype=torch.float32).contiguous()
         if isinstance(tr_batch, RowBatch):
             self._bind_sampler(tr_batch.sampler)
             kw["rows"] = tr_batch.rows
@@ -275,12 +280,12 @@ class AETrainer(TorchNNTrainer):
     def _after_step(self):
         pass
 
-    def train_batch(self, tr_batch, te_batch=None):
+    def train_batch(self, tr_batch, te_batch=None, _rng_tape=None):
         """One optimisation step; returns the loss as a python float (device -> host sync), like
         rectorch/models.py:424-447 / 817-835."""
         beta, lam = self._step_coeffs()
         slot = self._loss_hist[:4]
-        self._step(tr_batch, te_batch, beta, lam, slot)
+        self._step(tr_batch, te_batch, beta, lam, slot, _rng_tape)
         self._after_step()
         return self._loss_from(slot, beta, lam)
 

@@ -1,0 +1,245 @@
+"""GPU: end-to-end parity of the CUDA path (through the C ABI) against
+  (a) the golden fixtures produced by the unmodified reference, and
+  (b) the oracle on freshly seeded inputs, incl. a shape that takes the tcgen05 path.
+
+Tolerances (BASELINE.json north_star): loss within 1e-4 relative, recall@k / ndcg@k within 1e-3.
+The stochastic parts are replayed from the reference's generator through the RNG tape
+(dropout keep bits at the non-zeros + eps), see SURVEY.md section 8c.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import multvae_oracle as O
+from rectorch_b200 import synth
+from rectorch_b200.engine import Engine
+from rectorch_b200.evaluation import evaluate
+from rectorch_b200.models import MultiDAE, MultiVAE
+from rectorch_b200.nets import MultiDAE_net, MultiVAE_net
+from rectorch_b200.samplers import DataSampler
+from tests._util import golden_matrices, load_golden, oracle_net, rel_err, state_dict_from, tape_for
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-4
+METRIC_ATOL = 1e-3
+
+
+def _build(g, use_tc=True):
+    net = (MultiVAE_net if g["vae"] else MultiDAE_net)(list(g["dec_dims"]), None, g["p"])
+    net.load_state_dict(state_dict_from(g, "init"))
+    net.use_tensor_cores = use_tc
+    net = net.cuda()
+    if g["vae"]:
+        return MultiVAE(net, beta=g["beta"], anneal_steps=g["anneal"])
+    return MultiDAE(net, lam=g["lam"])
+
+
+def _run_steps(model, g, tr, te, steps, onet=None, ost=None):
+    """Tape-driven steps through Engine.train_step (one C call each).  Returns device losses and,
+    when an oracle net is given, the oracle's losses for the same steps."""
+    eng = model._engine
+    losses, olosses = [], []
+    latent = g["dec_dims"][0]
+    for it in range(steps):
+        lo, hi = it * g["batch"], min((it + 1) * g["batch"], g["n_users"])
+        if lo >= hi:
+            break
+        x = torch.from_numpy(tr.rows(lo, hi).toarray())
+        t = torch.from_numpy(te.rows(lo, hi).toarray()) if (te is not None and g["vae"]) else None
+        drop, keep, eps = tape_for(g["seed_rng"] + it, x, latent, g["p"], g["vae"])
+        beta_t = O.beta_schedule(g["beta"], g["anneal"], it) if g["vae"] else 0.0
+        assert abs((model._step_coeffs()[0] if g["vae"] else 0.0) - beta_t) < 1e-12
+        losses.append(model.train_batch(x.cuda(), None if t is None else t.cuda(), _rng_tape=(keep, eps)))
+        if onet is not None:
+            olosses.append(O.train_step(onet, ost, x, t, beta=beta_t, lam=g["lam"], drop_scale=drop, eps=eps))
+    eng.check_overflow()
+    return np.array(losses), np.array(olosses)
+
+
+@pytest.mark.parametrize("name", ["cfg1_dae", "small_vae", "vae_1layer", "small_dae"])
+def test_training_parity_with_reference_fixture(name):
+    """Per-step loss, final weights and Adam moments vs the unmodified reference's run."""
+    g = load_golden(name)
+    tr, te = golden_matrices(g)
+    model = _build(g)
+    losses, _ = _run_steps(model, g, tr, te, g["steps"])
+    assert len(losses) == g["steps"]
+    err = rel_err(losses, g["ref_losses"])
+    assert err.max() <= LOSS_RTOL, "per-step loss rel err %s" % err
+    sd = model.network.state_dict()
+    for k, v in sd.items():
+        d = np.abs(v.detach().cpu().numpy() - g["final/" + k]).max()
+        assert d <= 5e-5, "%s: max |dw| %g" % (k, d)
+    osd = model.optimizer.state_dict()["state"]
+    for i, k in enumerate(sd.keys()):
+        assert np.abs(osd[i]["exp_avg"].cpu().numpy() - g["adam_m/" + k]).max() <= 5e-5, k
+        assert float(osd[i]["step"]) == g["steps"]
+
+
+@pytest.mark.parametrize("name", ["cfg1_dae", "small_vae", "small_dae"])
+def test_predict_and_metrics_parity_with_reference_fixture(name):
+    """K9 + K10 on the reference's trained weights: scores, -inf mask, per-user metrics."""
+    g = load_golden(name)
+    tr, te = golden_matrices(g)
+    net = (MultiVAE_net if g["vae"] else MultiDAE_net)(list(g["dec_dims"]), None, g["p"])
+    net.load_state_dict(state_dict_from(g, "final"))
+    model = (MultiVAE if g["vae"] else MultiDAE)(net.cuda())
+    x0 = torch.from_numpy(tr.rows(0, min(g["batch"], g["n_users"])).toarray())
+    out = model.predict(x0, True)
+    assert len(out) == (3 if g["vae"] else 1)
+    pred = out[0].cpu().numpy()
+    ref = g["pred0"]
+    assert np.array_equal(np.isinf(ref), np.isinf(pred)) and np.all(pred[np.isinf(pred)] < 0)
+    fin = np.isfinite(ref)
+    assert np.abs(pred[fin] - ref[fin]).max() < 1e-4
+    mets = [k[len("metric/"):] for k in g if k.startswith("metric/")]
+    sampler = DataSampler(tr.to_scipy(), te.to_scipy(), batch_size=g["batch"], shuffle=False)
+    res = evaluate(model, sampler, mets)
+    for m in mets:
+        refm = g["metric/" + m].astype(np.float64)
+        mine = np.asarray(res[m], dtype=np.float64)
+        assert mine.shape == refm.shape
+        assert np.array_equal(np.isnan(refm), np.isnan(mine)), m
+        assert abs(np.nanmean(refm) - np.nanmean(mine)) <= METRIC_ATOL, m
+        # per-user agreement except where near-ties can swap neighbouring ranks
+        assert np.nanmean(np.abs(refm - mine) > 1e-6) < 0.02, m
+
+
+def _tc_case(vae, n_users=768, n_items=4096, hidden=96, latent=32, batch=256, p=0.5, seed=5):
+    csr = synth.make_matrix(n_users, n_items, seed=seed, mu=3.0, sigma=0.7, min_len=3, max_len=400)
+    tr, te = synth.split_heldout(csr, 0.2, seed=seed + 1)
+    dims = [latent, hidden, n_items] if vae else [hidden, n_items]
+    g = {"vae": vae, "dec_dims": dims, "n_users": n_users, "n_items": n_items, "batch": batch, "p": p,
+         "seed_rng": 900 + seed, "beta": 0.3, "anneal": 10, "lam": 0.2}
+    return g, tr, te
+
+
+@pytest.mark.parametrize("vae", [True, False])
+@pytest.mark.parametrize("use_tc", [True, False])
+def test_training_parity_with_oracle_item_sized(vae, use_tc):
+    """n_items = 4096: the decoder output layer runs on tcgen05 (use_tc) or the fp32 SIMT path.
+    Three optimisation steps with the RNG tape, oracle side by side."""
+    g, tr, te = _tc_case(vae)
+    torch.manual_seed(11)
+    net = (MultiVAE_net if vae else MultiDAE_net)(list(g["dec_dims"]), None, g["p"])
+    sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net.use_tensor_cores = use_tc
+    model = (MultiVAE(net.cuda(), beta=g["beta"], anneal_steps=g["anneal"]) if vae else MultiDAE(net.cuda(), lam=g["lam"]))
+    assert model._engine.use_tc == use_tc
+    onet = O.Net.from_state_dict(sd0, vae, g["p"])
+    ost = O.AdamState(onet, lr=1e-3, weight_decay=0.0 if vae else 1e-3)
+    losses, olosses = _run_steps(model, g, tr, te, 3, onet, ost)
+    err = rel_err(losses, olosses)
+    assert err.max() <= LOSS_RTOL, "loss rel err %s (device %s oracle %s)" % (err, losses, olosses)
+    osd = onet.state_dict()
+    for k, v in model.network.state_dict().items():
+        diff = (v.detach().cpu() - osd[k]).abs()
+        print("%-22s max|dw| %.3e  frac>2e-4 %.4f  frac>2e-5 %.4f" % (
+            k, diff.max().item(), (diff > 2e-4).float().mean().item(), (diff > 2e-5).float().mean().item()))
+    for k, v in model.network.state_dict().items():
+        d = (v.detach().cpu() - osd[k]).abs().max().item()
+        # Adam normalises the step to ~lr, so a sign flip of a ~0 gradient moves a weight by <= 2*lr per step
+        assert d <= 3 * 3 * 1e-3, "%s: max |dw| %g" % (k, d)
+        frac = ((v.detach().cpu() - osd[k]).abs() > 2e-4).float().mean().item()
+        assert frac < 0.02, "%s: %.3f of the weights differ by > 2e-4" % (k, frac)
+    # evaluation on the trained weights: device path vs oracle
+    sampler = DataSampler(tr.to_scipy(), te.to_scipy(), batch_size=g["batch"], shuffle=False)
+    mets = ["recall@20", "recall@50", "ndcg@100"]
+    res = evaluate(model, sampler, mets)
+    ores = O.evaluate(onet, tr.to_scipy(), te.to_scipy(), g["batch"], mets)
+    for m in mets:
+        assert abs(np.nanmean(res[m]) - np.nanmean(ores[m])) <= METRIC_ATOL, m
+
+
+def test_gradients_vs_oracle_tc_path():
+    """forward_backward only (no Adam): every gradient tensor of the tcgen05 path against the
+    oracle's hand-derived backward, relative to the tensor's own scale."""
+    g, tr, te = _tc_case(True)
+    torch.manual_seed(12)
+    net = MultiVAE_net(list(g["dec_dims"]), None, g["p"])
+    sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    model = MultiVAE(net.cuda(), beta=0.3)
+    eng = model._engine
+    x = torch.from_numpy(tr.rows(0, 256).toarray())
+    t = torch.from_numpy(te.rows(0, 256).toarray())
+    drop, keep, eps = tape_for(77, x, g["dec_dims"][0], g["p"], True)
+    buf = eng.forward_backward(dense=x.cuda(), dense_target=t.cuda(), beta=0.3, dropout_p=g["p"],
+                               keep_tape=keep.cuda(), eps_tape=eps.cuda())
+    loss = float(buf[0].item())
+    onet = O.Net.from_state_dict(sd0, True, g["p"])
+    c = O.forward(onet, x, True, drop, eps)
+    oloss = float(O.loss_value(onet, c, t, 0.3))
+    ograds = O.backward(onet, c, t, 0.3)
+    assert abs(loss - oloss) / abs(oloss) <= LOSS_RTOL
+    for i in range(len(eng.shapes)):
+        gw, gb = eng._views(eng.g, i)
+        for got, ref, nm in ((gw, ograds[2 * i], "w%d" % i), (gb, ograds[2 * i + 1], "b%d" % i)):
+            scale = ref.abs().max().item() + 1e-12
+            d = (got.detach().cpu() - ref).abs().max().item()
+            assert d <= 2e-3 * scale, "%s: max err %g vs scale %g" % (nm, d, scale)
+
+
+def test_full_size_properties_cfg2_shapes():
+    """BASELINE config #2 shapes (I = 50000, [600, 200], B = 500) -- too big for the CPU oracle in
+    the test budget, so size-independent properties:
+      * loss is finite and equals nll + beta*kld of the reported components
+      * lse-based NLL >= 0 and decreases over 30 steps on a fixed batch
+      * gradient arena: d(loss)/d(b_d) sums to ~0 (softmax*T/B - t/B summed over items and users)
+      * predict(): seen items are -inf, everything else finite; top-K metrics in range
+    """
+    n_items, B = 50000, 500
+    csr = synth.make_matrix(2000, n_items, seed=21)
+    tr, te = synth.split_heldout(csr, 0.2, seed=22)
+    torch.manual_seed(0)
+    net = MultiVAE_net([200, 600, n_items]).cuda()
+    model = MultiVAE(net, beta=0.2, anneal_steps=20000)
+    sampler = DataSampler(tr, te, batch_size=B, shuffle=False)
+    eng = model._engine
+    assert eng.use_tc
+    batches = list(sampler.iter_rows())
+    first = batches[0]
+    model._bind_sampler(sampler)
+    buf = eng.forward_backward(rows=first.rows, beta=0.2, dropout_p=0.5, seed=1, step=1)
+    c = buf.tolist()
+    assert np.isfinite(c).all() and abs(c[0] - (c[1] + 0.2 * c[2])) <= 1e-4 * abs(c[0]) and c[1] > 0
+    i_last = len(eng.shapes) - 1
+    _, gb = eng._views(eng.g, i_last)
+    gw, _ = eng._views(eng.g, i_last)
+    assert torch.isfinite(eng.g).all()
+    assert abs(gb.sum().item()) < 1e-3 * gb.abs().sum().item() + 1e-6
+    losses = [model.train_batch(first) for _ in range(30)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+    scores = model.predict(first, True)[0]
+    dense = sampler.device_csr()[0]
+    from rectorch_b200._expand import expand_rows
+    x = expand_rows(dense, first.rows)
+    assert torch.isinf(scores[x != 0]).all() and torch.isfinite(scores[x == 0]).all()
+    res = evaluate(model, sampler, ["recall@20", "ndcg@100"])
+    assert res["recall@20"].shape == (2000,)
+    ok = ~np.isnan(res["recall@20"])
+    assert np.all((res["recall@20"][ok] >= 0) & (res["recall@20"][ok] <= 1))
+    assert np.all((res["ndcg@100"][ok] >= 0) & (res["ndcg@100"][ok] <= 1 + 1e-6))
+
+
+def test_philox_rng_statistics_and_row_keying():
+    """Production RNG: dropout keeps ~ (1-p) of the non-zeros; results depend on the global row id,
+    not on the position in the batch (sharding invariance)."""
+    n_items = 2048
+    csr = synth.make_matrix(512, n_items, seed=4, mu=3.5, sigma=0.5, min_len=10, max_len=300)
+    torch.manual_seed(0)
+    net = MultiVAE_net([16, 64, n_items]).cuda()
+    eng = net.engine
+    net.train()
+    from rectorch_b200.engine import DeviceCSR
+    d = DeviceCSR(csr, "cuda")
+    eng.bind_csr(0, d)
+    rows_a = torch.arange(0, 128, dtype=torch.int32, device="cuda")
+    rows_b = torch.flip(rows_a, dims=[0])
+    _, mu_a, _ = eng.predict(rows=rows_a, remove_train=False, train_mode=True, dropout_p=0.5, seed=1234, want_scores=False)
+    _, mu_b, _ = eng.predict(rows=rows_b, remove_train=False, train_mode=True, dropout_p=0.5, seed=1234, want_scores=False)
+    assert torch.allclose(mu_a, torch.flip(mu_b, dims=[0]), atol=1e-6)
+    _, mu_c, _ = eng.predict(rows=rows_a, remove_train=False, train_mode=True, dropout_p=0.5, seed=99, want_scores=False)
+    assert not torch.allclose(mu_a, mu_c)
+    _, mu_e, _ = eng.predict(rows=rows_a, remove_train=False, train_mode=False, want_scores=False)
+    assert not torch.allclose(mu_a, mu_e)
