@@ -47,8 +47,11 @@ struct BatchView {
     const float*   values;    // nullable -> 1.0f
     const int32_t* row_ids;   // nullable -> identity
     const int64_t* bp;        // [B+1]
+    const int32_t* sp;        // [B+1] exclusive scan of the per-row segment counts (SPMM_SEG non-zeros each)
     int32_t        B;
 };
+
+constexpr int SPMM_SEG = 64;   // non-zeros per sparse gather/scatter work unit
 
 struct Layer {
     int in, out;              // nn.Linear(in, out)
@@ -78,7 +81,7 @@ struct Ctx;   // engine.cu
 // ---- kernel launchers (each returns a B200VAE_* code) -----------------------------------
 // sparse.cu
 int launch_batch_scan(Ctx* c, const int64_t* indptr, const int32_t* row_ids, int B, int64_t cap,
-                      int64_t* bp, cudaStream_t s);
+                      int64_t* bp, int32_t* sp, cudaStream_t s);
 int launch_batch_prep(Ctx* c, const BatchView& in, float p, uint64_t seed, uint64_t step,
                       int64_t row_offset, const uint8_t* keep_tape, bool train, float* xt,
                       cudaStream_t s);
@@ -141,6 +144,7 @@ struct TcEpi {
     int bias_col = -1;
     int split_k = 1;                   // TC_EPI_STORE: partial products C[s] at C + s*split_stride
     int64_t split_stride = 0;
+    int n_fastest = 0;                 // walk N tiles first (A tile shared through L2 by consecutive CTAs)
 };
 bool tc_supported(int M, int N, int K, int64_t lda, int64_t ldb);
 int launch_tc_gemm(Ctx* c, int mode, const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb,

@@ -16,6 +16,7 @@ struct CsrSlot {
     float*   int_values = nullptr;   // [max_batch_nnz]
     bool     int_has_values = false;
     int64_t* bp = nullptr;           // [max_batch+1] compact scan for the current batch
+    int32_t* sp = nullptr;           // [max_batch+1] segment pointer for the current batch
 };
 
 struct Ctx {
@@ -50,6 +51,8 @@ struct Ctx {
     float* h_r = nullptr;             // [B x H_last] tf32-rounded copy of the last hidden activation
     float* wd_shadow = nullptr;       // [n_items x H_last] tf32-rounded copy of W_d, maintained by Adam
     int32_t* d_specs = nullptr;       // [128] metric specs for topk
+    float* spmm_acc = nullptr;        // [B x max(width)] zeroed accumulator for multi-segment gathers
+    int*   spmm_ticket = nullptr;     // [B] zeroed per-row completion tickets
     float* dbuf[2] = {nullptr, nullptr};  // [B x max_width] ping-pong activation gradients
     float* part_max = nullptr;        // [n_tiles x B]
     float* part_sum = nullptr;

@@ -37,7 +37,7 @@ static int dmalloc(T** p, int64_t n) {
 static void free_ctx(Ctx* c) {
     auto F = [](void* p) { if (p) cudaFree(p); };
     for (int s = 0; s < 2; ++s) {
-        F(c->slot[s].int_indptr); F(c->slot[s].int_indices); F(c->slot[s].int_values); F(c->slot[s].bp);
+        F(c->slot[s].int_indptr); F(c->slot[s].int_indices); F(c->slot[s].int_values); F(c->slot[s].bp); F(c->slot[s].sp);
     }
     F(c->xt); F(c->T); F(c->loss_row); F(c->kl_row); F(c->lse);
     for (float* p : c->act_enc) F(p);
@@ -45,7 +45,7 @@ static void free_ctx(Ctx* c) {
     F(c->z); F(c->eps); F(c->gvec); F(c->P); F(c->hT); F(c->dbuf[0]); F(c->dbuf[1]);
     F(c->part_max); F(c->part_sum); F(c->splitk); F(c->norms); F(c->norm_partial);
     F(c->d_toff); F(c->d_tlen); F(c->loss_dev); F(c->d_err); F(c->lens_tmp);
-    F(c->h_r); F(c->wd_shadow); F(c->d_specs);
+    F(c->h_r); F(c->wd_shadow); F(c->d_specs); F(c->spmm_acc); F(c->spmm_ticket);
     for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventDestroy(c->ev[i][j]);
     delete c;
@@ -60,14 +60,14 @@ static int make_view(Ctx* c, int slot, const int32_t* row_ids, int B, BatchView*
         v->indptr = S.indptr;
         v->indices = S.indices;
         v->values = S.values;
-        v->bp = S.bp;
-        B200_CHECK(launch_batch_scan(c, S.indptr, row_ids, B, c->cfg.max_batch_nnz, S.bp, s));
     } else {
         v->indptr = S.int_indptr;
         v->indices = S.int_indices;
         v->values = S.int_has_values ? S.int_values : nullptr;
-        v->bp = S.int_indptr;   // the internal batch CSR is already compact
     }
+    v->bp = S.bp;
+    v->sp = S.sp;
+    B200_CHECK(launch_batch_scan(c, v->indptr, row_ids, B, c->cfg.max_batch_nnz, S.bp, S.sp, s));
     return 0;
 }
 
@@ -241,6 +241,7 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         TcEpi e2;
         e2.bias_grad = dbd;
         e2.bias_col = H;
+        e2.n_fastest = 1;      // the 3 N tiles of one item block run on neighbouring CTAs: P^T is read from HBM once
         tick(c, 3, 0, s);
         B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->P, Bp, 0, c->hT, Bp, 0, dWd, H, I, H + 8, B, e2, s));
         tick(c, 3, 1, s);
@@ -447,6 +448,7 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
         A_(dmalloc(&c->slot[s].int_indices, nnz));
         A_(dmalloc(&c->slot[s].int_values, nnz));
         A_(dmalloc(&c->slot[s].bp, Bm + 1));
+        A_(dmalloc(&c->slot[s].sp, Bm + 1));
     }
     A_(dmalloc(&c->xt, nnz));
     A_(dmalloc(&c->T, Bm)); A_(dmalloc(&c->loss_row, Bm)); A_(dmalloc(&c->kl_row, Bm)); A_(dmalloc(&c->lse, Bm));
@@ -459,6 +461,8 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     A_(dmalloc(&c->h_r, Bm * H));
     A_(dmalloc(&c->wd_shadow, c->tc_dec ? I * H : 1));
     A_(dmalloc(&c->d_specs, 128));
+    A_(dmalloc(&c->spmm_acc, Bm * std::max(c->max_width, H)));
+    A_(dmalloc(&c->spmm_ticket, Bm));
     A_(dmalloc(&c->dbuf[0], Bm * c->max_width)); A_(dmalloc(&c->dbuf[1], Bm * c->max_width));
     c->n_lse_tiles = (int)std::max<int64_t>(cdiv(I, 64), 1);
     A_(dmalloc(&c->part_max, (int64_t)c->n_lse_tiles * Bm)); A_(dmalloc(&c->part_sum, (int64_t)c->n_lse_tiles * Bm));
@@ -469,6 +473,8 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     A_(dmalloc(&c->loss_dev, 4)); A_(dmalloc(&c->d_err, 1)); A_(dmalloc(&c->lens_tmp, Bm + 1));
 #undef A_
     if (!rc && cudaMemset(c->d_err, 0, sizeof(int)) != cudaSuccess) rc = B200VAE_ECUDA;
+    if (!rc && cudaMemset(c->spmm_acc, 0, (size_t)Bm * std::max(c->max_width, H) * sizeof(float)) != cudaSuccess) rc = B200VAE_ECUDA;
+    if (!rc && cudaMemset(c->spmm_ticket, 0, (size_t)Bm * sizeof(int)) != cudaSuccess) rc = B200VAE_ECUDA;
     if (rc) { free_ctx(c); return rc; }
     *out = reinterpret_cast<b200vae_ctx*>(c);
     return 0;
@@ -606,7 +612,7 @@ int b200vae_topk_metrics_csr(const float* scores, int32_t B, int32_t n_items, co
                              int32_t* topk_idx, void* stream) {
     B200_REQUIRE(scores && gt_indptr && kinds_dev && ks_dev && out && B >= 1, B200VAE_EINVAL, "bad argument");
     BatchView gt;
-    gt.indptr = gt_indptr; gt.indices = gt_indices; gt.values = gt_values; gt.row_ids = nullptr; gt.bp = gt_indptr; gt.B = B;
+    gt.indptr = gt_indptr; gt.indices = gt_indices; gt.values = gt_values; gt.row_ids = nullptr; gt.bp = gt_indptr; gt.sp = nullptr; gt.B = B;
     return launch_topk_metrics(null_ctx(), scores, n_items, gt, kinds_dev, ks_dev, n_metrics, kmax, out, topk_idx,
                                (cudaStream_t)stream);
 }
@@ -616,7 +622,7 @@ int b200vae_expand_rows_raw(const int64_t* indptr, const int32_t* indices, const
     B200_REQUIRE(indptr && out && B >= 0, B200VAE_EINVAL, "bad argument");
     if (B == 0) return 0;
     BatchView v;
-    v.indptr = indptr; v.indices = indices; v.values = values; v.row_ids = row_ids; v.bp = nullptr; v.B = B;
+    v.indptr = indptr; v.indices = indices; v.values = values; v.row_ids = row_ids; v.bp = nullptr; v.sp = nullptr; v.B = B;
     return launch_expand(null_ctx(), v, n_items, out, (cudaStream_t)stream);
 }
 

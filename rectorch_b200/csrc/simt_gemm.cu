@@ -7,17 +7,25 @@
 //
 //   C[m,n] = epi( alpha * sum_k A(m,k) * B(k,n) )
 //   A(m,k) = A[m*a_rs + k*a_cs],  B(k,n) = B[k*b_rs + n*b_cs]   (any strides -> any transposes)
+//
+// Tiles are BM x 64 x 16 with BM = 64 (256 threads) or 32 (128 threads); the smaller tile is
+// picked when the 64-row grid would leave most of the 148 SMs idle (the hidden layers are only
+// ~500 x 600).  The global loads of K-block i+1 are issued into registers before the FMAs of
+// K-block i, so one L2 round trip overlaps a block of math instead of preceding it.
 #include "ctx.cuh"
 
 namespace b200 {
 
-constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+constexpr int BN = 64, BK = 16, TM = 4, TN = 4;
 
-template <int MODE>
-__global__ void __launch_bounds__(256)
+template <int MODE, int BM>
+__global__ void __launch_bounds__(BM * 4)
 k_simt_gemm(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float* __restrict__ B,
             int64_t b_rs, int64_t b_cs, float* __restrict__ C, int64_t ldc, int M, int N, int K,
             GemmEpi e) {
+    constexpr int THREADS = BM * 4;                 // (BM/TM) x (BN/TN) threads
+    constexpr int A_PER = BM * BK / THREADS;        // 4
+    constexpr int B_PER = BN * BK / THREADS;        // 4 (BM=64) or 8 (BM=32)
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
     const int tid = threadIdx.x;
@@ -31,22 +39,48 @@ k_simt_gemm(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float
 
     const bool a_kfast = (a_cs == 1);
     const bool b_nfast = (b_cs == 1);
-    for (int k0 = 0; k0 < K; k0 += BK) {
+    float ra[A_PER], rb[B_PER];
+
+    auto load_tiles = [&](int k0) {
 #pragma unroll
-        for (int i = tid; i < BM * BK; i += 256) {
+        for (int u = 0; u < A_PER; ++u) {
+            const int i = tid + u * THREADS;
             int mm, kk;
             if (a_kfast) { kk = i % BK; mm = i / BK; } else { mm = i % BM; kk = i / BM; }
-            int gm = m0 + mm, gk = k0 + kk;
-            As[kk][mm] = (gm < M && gk < K) ? A[(int64_t)gm * a_rs + (int64_t)gk * a_cs] : 0.f;
+            const int gm = m0 + mm, gk = k0 + kk;
+            ra[u] = (gm < M && gk < K) ? __ldg(A + (int64_t)gm * a_rs + (int64_t)gk * a_cs) : 0.f;
         }
 #pragma unroll
-        for (int i = tid; i < BN * BK; i += 256) {
+        for (int u = 0; u < B_PER; ++u) {
+            const int i = tid + u * THREADS;
             int nn, kk;
             if (b_nfast) { nn = i % BN; kk = i / BN; } else { kk = i % BK; nn = i / BK; }
-            int gn = n0 + nn, gk = k0 + kk;
-            Bs[kk][nn] = (gn < N && gk < K) ? B[(int64_t)gk * b_rs + (int64_t)gn * b_cs] : 0.f;
+            const int gn = n0 + nn, gk = k0 + kk;
+            rb[u] = (gn < N && gk < K) ? __ldg(B + (int64_t)gk * b_rs + (int64_t)gn * b_cs) : 0.f;
         }
+    };
+    auto store_tiles = [&]() {
+#pragma unroll
+        for (int u = 0; u < A_PER; ++u) {
+            const int i = tid + u * THREADS;
+            int mm, kk;
+            if (a_kfast) { kk = i % BK; mm = i / BK; } else { mm = i % BM; kk = i / BM; }
+            As[kk][mm] = ra[u];
+        }
+#pragma unroll
+        for (int u = 0; u < B_PER; ++u) {
+            const int i = tid + u * THREADS;
+            int nn, kk;
+            if (b_nfast) { nn = i % BN; kk = i / BN; } else { kk = i % BK; nn = i / BK; }
+            Bs[kk][nn] = rb[u];
+        }
+    };
+
+    load_tiles(0);
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        store_tiles();
         __syncthreads();
+        if (k0 + BK < K) load_tiles(k0 + BK);      // in flight during the FMAs below
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
             float a[TM], b[TN];
@@ -124,34 +158,54 @@ k_simt_gemm(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float
     }
 }
 
+template <int MODE>
+static void launch_mode(bool small, dim3 g64, dim3 g32, const float* A, int64_t a_rs, int64_t a_cs, const float* B,
+                        int64_t b_rs, int64_t b_cs, float* C, int64_t ldc, int M, int N, int K, const GemmEpi& e,
+                        cudaStream_t s) {
+    if (small) k_simt_gemm<MODE, 32><<<g32, 128, 0, s>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e);
+    else       k_simt_gemm<MODE, 64><<<g64, 256, 0, s>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e);
+}
+
 int launch_simt_gemm(Ctx* c, int mode, const float* A, int64_t a_rs, int64_t a_cs, const float* B,
                      int64_t b_rs, int64_t b_cs, float* C, int64_t ldc, int M, int N, int K,
                      const GemmEpi& e, cudaStream_t s) {
     if (M == 0 || N == 0) return 0;
-    dim3 grid((unsigned)cdiv(N, BN), (unsigned)cdiv(M, BM));
-    B200_REQUIRE(grid.y <= 65535, B200VAE_EINVAL, "simt_gemm: M too large (%d)", M);
+    dim3 g64((unsigned)cdiv(N, BN), (unsigned)cdiv(M, 64));
+    dim3 g32((unsigned)cdiv(N, BN), (unsigned)cdiv(M, 32));
+    B200_REQUIRE(g32.y <= 65535, B200VAE_EINVAL, "simt_gemm: M too large (%d)", M);
+    const int sms = c->num_sms > 0 ? c->num_sms : 148;
+    const bool small = (int64_t)g64.x * g64.y < 2 * (int64_t)sms;   // too few 64-row tiles to fill the GPU
     switch (mode) {
-        case EPI_STORE: k_simt_gemm<EPI_STORE><<<grid, 256, 0, s>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e); break;
-        case EPI_LSE:   k_simt_gemm<EPI_LSE><<<grid, 256, 0, s>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e); break;
-        default:        k_simt_gemm<EPI_PROB><<<grid, 256, 0, s>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e); break;
+        case EPI_STORE: launch_mode<EPI_STORE>(small, g64, g32, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e, s); break;
+        case EPI_LSE:   launch_mode<EPI_LSE>(small, g64, g32, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e, s); break;
+        default:        launch_mode<EPI_PROB>(small, g64, g32, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e, s); break;
     }
     c->launches++;
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-// out[n] = sum_m X[m*ldx + n]   -- fixed summation order (deterministic)
-__global__ void k_colsum(const float* __restrict__ X, int64_t ldx, int M, int N, float* __restrict__ out) {
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+// out[n] = sum_m X[m*ldx + n]: 32 columns x 32 row-lanes per CTA, fixed summation order
+// (row-lane partial sums, then a fixed-order tree over the 32 lanes) -> deterministic.
+__global__ void __launch_bounds__(1024)
+k_colsum(const float* __restrict__ X, int64_t ldx, int M, int N, float* __restrict__ out) {
+    __shared__ float sh[32][33];
+    const int n = blockIdx.x * 32 + threadIdx.x;
     float acc = 0.f;
-    for (int m = 0; m < M; ++m) acc += X[(int64_t)m * ldx + n];
-    out[n] = acc;
+    if (n < N)
+        for (int m = threadIdx.y; m < M; m += 32) acc += X[(int64_t)m * ldx + n];
+    sh[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) {
+        if (threadIdx.y < o) sh[threadIdx.y][threadIdx.x] += sh[threadIdx.y + o][threadIdx.x];
+        __syncthreads();
+    }
+    if (threadIdx.y == 0 && n < N) out[n] = sh[0][threadIdx.x];
 }
 
 int launch_colsum(Ctx* c, const float* X, int64_t ldx, int M, int N, float* out, cudaStream_t s) {
     if (N == 0) return 0;
-    k_colsum<<<(int)cdiv(N, 128), 128, 0, s>>>(X, ldx, M, N, out);
+    k_colsum<<<(int)cdiv(N, 32), dim3(32, 32), 0, s>>>(X, ldx, M, N, out);
     c->launches++;
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -16,11 +16,14 @@ namespace b200 {
 // scans
 // ------------------------------------------------------------------------------------------
 __global__ void k_batch_scan(const int64_t* __restrict__ indptr, const int32_t* __restrict__ row_ids,
-                             int B, int64_t cap, int64_t* __restrict__ bp, int* err) {
-    // single CTA, 1024 threads; chunked Hillis-Steele scan over the row lengths
+                             int B, int64_t cap, int64_t* __restrict__ bp, int32_t* __restrict__ sp, int* err) {
+    // single CTA, 1024 threads; chunked Hillis-Steele scans of the row lengths (bp) and of the
+    // number of SPMM_SEG-sized work segments per row (sp)
     __shared__ int64_t sh[1024];
+    __shared__ int32_t sg[1024];
     __shared__ int64_t carry;
-    if (threadIdx.x == 0) carry = 0;
+    __shared__ int32_t carry_s;
+    if (threadIdx.x == 0) { carry = 0; carry_s = 0; }
     __syncthreads();
     for (int base = 0; base < B; base += 1024) {
         int r = base + threadIdx.x;
@@ -29,28 +32,36 @@ __global__ void k_batch_scan(const int64_t* __restrict__ indptr, const int32_t* 
             int64_t gr = row_ids ? (int64_t)row_ids[r] : (int64_t)r;
             len = indptr[gr + 1] - indptr[gr];
         }
+        int32_t nseg = (r < B) ? (int32_t)max((int64_t)1, (len + SPMM_SEG - 1) / SPMM_SEG) : 0;
         sh[threadIdx.x] = len;
+        sg[threadIdx.x] = nseg;
         __syncthreads();
         for (int o = 1; o < 1024; o <<= 1) {
             int64_t t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0;
+            int32_t u = (threadIdx.x >= o) ? sg[threadIdx.x - o] : 0;
             __syncthreads();
             sh[threadIdx.x] += t;
+            sg[threadIdx.x] += u;
             __syncthreads();
         }
-        if (r < B) bp[r] = carry + sh[threadIdx.x] - len;
+        if (r < B) {
+            bp[r] = carry + sh[threadIdx.x] - len;
+            sp[r] = carry_s + sg[threadIdx.x] - nseg;
+        }
         __syncthreads();
-        if (threadIdx.x == 1023) carry += sh[1023];
+        if (threadIdx.x == 1023) { carry += sh[1023]; carry_s += sg[1023]; }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
         bp[B] = carry;
+        sp[B] = carry_s;
         if (carry > cap) *err = 1;
     }
 }
 
 int launch_batch_scan(Ctx* c, const int64_t* indptr, const int32_t* row_ids, int B, int64_t cap,
-                      int64_t* bp, cudaStream_t s) {
-    k_batch_scan<<<1, 1024, 0, s>>>(indptr, row_ids, B, cap, bp, c->d_err);
+                      int64_t* bp, int32_t* sp, cudaStream_t s) {
+    k_batch_scan<<<1, 1024, 0, s>>>(indptr, row_ids, B, cap, bp, sp, c->d_err);
     c->launches++;
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -171,37 +182,63 @@ int launch_row_sums(Ctx* c, const BatchView& v, float* out, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------
 // K2 spmm_gather: out[r,:] = act(bias + sum_k vals[bp[r]+k] * Wt[col_k,:])
-// one CTA per row; VEC=4 -> float4 lanes across H (H % 4 == 0, 16 B aligned rows)
+//
+// Work unit = (row, segment of <= SPMM_SEG non-zeros): histories are log-normal with a 20x tail, so a
+// CTA per row would leave the longest user running alone.  CTA b finds its row by a binary search in
+// the segment pointer sp.  Rows with one segment write their result directly; longer rows reduce
+// their partial sums with fp32 reductions in L2 into a zeroed accumulator and the CTA that finishes
+// last (per-row ticket) applies bias + activation and re-zeroes the accumulator for the next call.
+// VEC=4 -> float4 lanes across H (H % 4 == 0, 16 B aligned rows).  Entries whose value is 0
+// (dropped by nn.Dropout) are skipped without touching their weight row.
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int find_row(const int32_t* __restrict__ sp, int B, int b) {
+    int lo = 0, hi = B;          // largest r with sp[r] <= b
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (sp[mid] <= b) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256)
 k_spmm_gather(BatchView v, const float* __restrict__ vals, const float* __restrict__ Wt, int H,
-              const float* __restrict__ bias, int act, float* __restrict__ out) {
-    int r = blockIdx.x;
-    int64_t gr = v.row_ids ? (int64_t)v.row_ids[r] : (int64_t)r;
-    int64_t a = v.indptr[gr];
-    int n = (int)(v.indptr[gr + 1] - a);
-    int64_t o = v.bp[r];
+              const float* __restrict__ bias, int act, float* __restrict__ out, float* __restrict__ acc_ws,
+              int* __restrict__ ticket) {
+    if ((int)blockIdx.x >= v.sp[v.B]) return;
+    const int r = find_row(v.sp, v.B, blockIdx.x);
+    const int seg = blockIdx.x - v.sp[r];
+    const int nseg = v.sp[r + 1] - v.sp[r];
+    const int64_t gr = v.row_ids ? (int64_t)v.row_ids[r] : (int64_t)r;
+    const int64_t a = v.indptr[gr];
+    const int len = (int)(v.indptr[gr + 1] - a);
+    const int k0 = seg * SPMM_SEG, k1 = min(len, k0 + SPMM_SEG);
+    const int64_t o = v.bp[r];
     const int32_t* cols = v.indices + a;
     const float* xv = vals ? vals + o : nullptr;
     const float* raw = v.values ? v.values + a : nullptr;
+    __shared__ int s_last;
     for (int h0 = threadIdx.x * VEC; h0 < H; h0 += blockDim.x * VEC) {
         float acc[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-        int k = 0;
-        for (; k + 4 <= n; k += 4) {   // 4 independent row loads in flight
+        int k = k0;
+        for (; k + 4 <= k1; k += 4) {   // up to 4 independent row loads in flight per thread
             float w[4][VEC];
             float x[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const float* row = Wt + (int64_t)cols[k + u] * H + h0;
                 x[u] = xv ? xv[k + u] : (raw ? raw[k + u] : 1.f);
-                if (VEC == 4) {
-                    float4 t = __ldg(reinterpret_cast<const float4*>(row));
-                    w[u][0] = t.x; w[u][1 % VEC] = t.y; w[u][2 % VEC] = t.z; w[u][3 % VEC] = t.w;
-                } else {
-                    w[u][0] = __ldg(row);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) w[u][i] = 0.f;
+                if (x[u] != 0.f) {
+                    const float* row = Wt + (int64_t)cols[k + u] * H + h0;
+                    if (VEC == 4) {
+                        float4 t = __ldg(reinterpret_cast<const float4*>(row));
+                        w[u][0] = t.x; w[u][1 % VEC] = t.y; w[u][2 % VEC] = t.z; w[u][3 % VEC] = t.w;
+                    } else {
+                        w[u][0] = __ldg(row);
+                    }
                 }
             }
 #pragma unroll
@@ -209,31 +246,60 @@ k_spmm_gather(BatchView v, const float* __restrict__ vals, const float* __restri
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) acc[i] = fmaf(x[u], w[u][i], acc[i]);
         }
-        for (; k < n; ++k) {
-            const float* row = Wt + (int64_t)cols[k] * H + h0;
+        for (; k < k1; ++k) {
             float x = xv ? xv[k] : (raw ? raw[k] : 1.f);
+            if (x == 0.f) continue;
+            const float* row = Wt + (int64_t)cols[k] * H + h0;
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[i] = fmaf(x, __ldg(row + i), acc[i]);
         }
+        if (nseg == 1) {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            float y = acc[i] + (bias ? bias[h0 + i] : 0.f);
-            if (act) y = tanhf(y);
-            out[(int64_t)r * H + h0 + i] = y;
+            for (int i = 0; i < VEC; ++i) {
+                float y = acc[i] + (bias ? bias[h0 + i] : 0.f);
+                if (act) y = tanhf(y);
+                out[(int64_t)r * H + h0 + i] = y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) atomicAdd(acc_ws + (int64_t)r * H + h0 + i, acc[i]);
         }
     }
+    if (nseg > 1) {
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) s_last = (atomicAdd(ticket + r, 1) == nseg - 1);
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            for (int h = threadIdx.x; h < H; h += blockDim.x) {
+                float y = __ldcg(acc_ws + (int64_t)r * H + h) + (bias ? bias[h] : 0.f);
+                if (act) y = tanhf(y);
+                out[(int64_t)r * H + h] = y;
+                acc_ws[(int64_t)r * H + h] = 0.f;
+            }
+            if (threadIdx.x == 0) ticket[r] = 0;
+        }
+    }
+}
+
+static int spmm_grid(Ctx* c, const BatchView& v) {
+    // upper bound of the number of segments: every row has >= 1, plus nnz_cap / SEG
+    int64_t g = (int64_t)v.B + c->cfg.max_batch_nnz / SPMM_SEG + 1;
+    return (int)std::min<int64_t>(g, 1 << 30);
 }
 
 int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const float* Wt, int H,
                        const float* bias, int act, float* out, cudaStream_t s) {
     if (v.B == 0) return 0;
     bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(Wt) & 15) == 0);
+    const int grid = spmm_grid(c, v);
     if (vec) {
         int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));
-        k_spmm_gather<4><<<v.B, threads, 0, s>>>(v, vals, Wt, H, bias, act, out);
+        k_spmm_gather<4><<<grid, threads, 0, s>>>(v, vals, Wt, H, bias, act, out, c->spmm_acc, c->spmm_ticket);
     } else {
         int threads = (int)std::min<int64_t>(256, round_up(H, 32));
-        k_spmm_gather<1><<<v.B, threads, 0, s>>>(v, vals, Wt, H, bias, act, out);
+        k_spmm_gather<1><<<grid, threads, 0, s>>>(v, vals, Wt, H, bias, act, out, c->spmm_acc, c->spmm_ticket);
     }
     c->launches++;
     B200_CUDA_OK(cudaGetLastError());
@@ -242,16 +308,20 @@ int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const floa
 
 // ------------------------------------------------------------------------------------------
 // K7 spmm_scatter: dWt[col_k,:] += scale * vals[k] * dY[r,:]      (fp32 reductions in L2)
+// same (row, segment) work units as the gather
 // ------------------------------------------------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(256)
 k_spmm_scatter(BatchView v, const float* __restrict__ vals, float scale, const float* __restrict__ dY,
                int H, float* __restrict__ dWt) {
-    int r = blockIdx.x;
-    int64_t gr = v.row_ids ? (int64_t)v.row_ids[r] : (int64_t)r;
-    int64_t a = v.indptr[gr];
-    int n = (int)(v.indptr[gr + 1] - a);
-    int64_t o = v.bp[r];
+    if ((int)blockIdx.x >= v.sp[v.B]) return;
+    const int r = find_row(v.sp, v.B, blockIdx.x);
+    const int seg = blockIdx.x - v.sp[r];
+    const int64_t gr = v.row_ids ? (int64_t)v.row_ids[r] : (int64_t)r;
+    const int64_t a = v.indptr[gr];
+    const int len = (int)(v.indptr[gr + 1] - a);
+    const int k0 = seg * SPMM_SEG, k1 = min(len, k0 + SPMM_SEG);
+    const int64_t o = v.bp[r];
     const int32_t* cols = v.indices + a;
     const float* xv = vals ? vals + o : nullptr;
     const float* raw = v.values ? v.values + a : nullptr;
@@ -259,7 +329,7 @@ k_spmm_scatter(BatchView v, const float* __restrict__ vals, float scale, const f
         float d[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) d[i] = dY[(int64_t)r * H + h0 + i] * scale;
-        for (int k = 0; k < n; ++k) {
+        for (int k = k0; k < k1; ++k) {
             float x = xv ? xv[k] : (raw ? raw[k] : 1.f);
             if (x == 0.f) continue;   // dropped entries contribute nothing
             float* row = dWt + (int64_t)cols[k] * H + h0;
@@ -277,12 +347,13 @@ int launch_spmm_scatter(Ctx* c, const BatchView& v, const float* vals, float sca
                         int H, float* dWt, cudaStream_t s) {
     if (v.B == 0) return 0;
     bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(dWt) & 15) == 0);
+    const int grid = spmm_grid(c, v);
     if (vec) {
         int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));
-        k_spmm_scatter<4><<<v.B, threads, 0, s>>>(v, vals, scale, dY, H, dWt);
+        k_spmm_scatter<4><<<grid, threads, 0, s>>>(v, vals, scale, dY, H, dWt);
     } else {
         int threads = (int)std::min<int64_t>(256, round_up(H, 32));
-        k_spmm_scatter<1><<<v.B, threads, 0, s>>>(v, vals, scale, dY, H, dWt);
+        k_spmm_scatter<1><<<grid, threads, 0, s>>>(v, vals, scale, dY, H, dWt);
     }
     c->launches++;
     B200_CUDA_OK(cudaGetLastError());

@@ -5,9 +5,9 @@
 //   D[M x N] = A[M x K] * B[N x K]^T
 //
 //   TC_EPI_LSE   K4  logits = h W_d^T + b never leave the SM: each epilogue thread owns one user
-//                    row (one TMEM lane) and folds its 256-item tile into an online (max, sum exp);
-//                    output = per-(item tile, user) partials, merged by k_lse_merge.
-//                    (F.log_softmax over nets.py:417's output, models.py:813)
+//                    row (one TMEM lane) and folds its share of the 256-item tile into an online
+//                    (max, sum exp); output = per-(item half-tile, user) partials, merged by
+//                    k_lse_merge.            (F.log_softmax over nets.py:417's output, models.py:813)
 //   TC_EPI_PROB  K5  same mainloop, epilogue recomputes softmax from the saved lse and stores
 //                    P^T[item, user] = exp(logit - lse_u) * T_u/B  (coalesced: a warp's 32 lanes
 //                    are 32 consecutive users)                      (dlogits of loss.backward())
@@ -15,16 +15,20 @@
 //                    dW_d|db_d = P^T [h | 1]  and  dh = P W_d.
 //
 // Operand "majorness": K-major = the contraction index is contiguous in memory (TMA box
-// 32 floats of K x rows), MN-major = the M/N index is contiguous (box 32 floats of M/N x 32
-// K-rows, one box per 32-wide chunk).  Both map onto SWIZZLE_128B shared-memory descriptors;
-// the instruction descriptor's a_major/b_major bits select the interpretation.
+// 32 floats of K x rows, SWIZZLE_128B), MN-major = the M/N index is contiguous (box 32 floats of
+// M/N x 32 K-rows, one box per 32-wide chunk, SWIZZLE_128B with 32 B atoms -- the only MN-major
+// layout the tensor core takes for tf32).  The instruction descriptor's a_major/b_major bits
+// select the interpretation.
 //
 // Pipelines (all mbarrier based, no __syncthreads in the steady state):
-//   warp 0   TMA producer      : empty[s] -> issue loads -> full[s] (complete_tx)
-//   warp 1   MMA issuer        : full[s] -> 4 x tcgen05.mma (K=8 each) -> commit -> empty[s];
+//   warp 0    TMA producer     : empty[s] -> issue loads -> full[s] (complete_tx)
+//   warp 1    MMA issuer       : full[s] -> 4 x tcgen05.mma (K=8 each) -> commit -> empty[s];
 //                                after the last K block: commit -> tmem_full[a]
-//   warps 2-5 epilogue         : tmem_full[a] -> tcgen05.ld 32 columns at a time -> math ->
-//                                global stores -> tmem_empty[a]
+//   warps 2-9 epilogue (8)     : tmem_full[a] -> tcgen05.ld 32 columns at a time, software
+//                                pipelined (the load of chunk c+1 is in flight while chunk c is
+//                                reduced) -> math -> global stores -> tmem_empty[a].
+//                                Two warps share each TMEM lane quarter and interleave the column
+//                                chunks, so every SM sub-partition has two epilogue warps to issue from.
 // TMEM: 512 columns = 2 accumulator stages x 256 columns, so the epilogue of tile i overlaps
 // the MMAs of tile i+1.
 #include <cuda.h>
@@ -39,8 +43,12 @@ constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_B_BYTES = 256 * TC_BK * 4;     // 32 KB (max N tile)
 constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_THREADS = 192;
-constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_THREADS = 32 * TC_EPI_WARPS;
+constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
+constexpr int TC_BAR_BYTES = 128;
+constexpr int TC_BIAS_BYTES = 2 * 256 * 4;
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + TC_BAR_BYTES + TC_BIAS_BYTES;
 constexpr unsigned long long SPIN_LIMIT = 1ull << 28;
 
 // ---------------------------------------------------------------------------------------
@@ -94,7 +102,8 @@ __device__ __forceinline__ void tcgen05_mma_tf32(uint32_t d_tmem, uint64_t adesc
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+// TMEM -> registers, 32 lanes x 32 columns per warp; asynchronous until tmem_wait_ld
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -105,7 +114,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// wait for all outstanding tcgen05.ld of this thread; the registers are passed through the asm so
+// that no use of them can be scheduled above the wait
+__device__ __forceinline__ void tmem_wait_ld(float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 // SM100 shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout:
@@ -135,6 +159,7 @@ struct TcArgs {
     int M, N, K;
     int BN;                 // N tile (multiple of 16, <= 256)
     int tiles_m, tiles_n;
+    int n_fastest;          // tile order: consecutive CTAs walk N first (share the A tile through L2)
     int kb_total;           // K blocks overall
     int kb_per_split;
     int split_k;
@@ -150,6 +175,99 @@ struct TcArgs {
     int vec_ok;             // C rows are 16 B aligned
 };
 
+struct TileCoord { int m_idx, n_idx, sp; };
+__device__ __forceinline__ TileCoord decode_tile(int t, const TcArgs& a) {
+    TileCoord c;
+    const int mn = a.tiles_m * a.tiles_n;
+    c.sp = t / mn;
+    const int r = t - c.sp * mn;
+    if (a.n_fastest) { c.n_idx = r % a.tiles_n; c.m_idx = r / a.tiles_n; }
+    else             { c.m_idx = r % a.tiles_m; c.n_idx = r / a.tiles_m; }
+    return c;
+}
+
+constexpr float LOG2E_F = 1.4426950408889634f;
+
+// one 32-column chunk of the accumulator for the thread's row
+template <int MODE>
+__device__ __forceinline__ void epi_chunk(const TcArgs& a, const float* v, const float* __restrict__ bias_s, int c0, int nc,
+                                          int n0, int m, int sp, float& run_max, float& run_sum, float lse_l2, float rs_m) {
+    if (MODE == TC_EPI_LSE) {
+        float x[32];
+        if (nc == 32) {
+            float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + i);
+                x[i] = v[i] + b4.x; x[i + 1] = v[i + 1] + b4.y; x[i + 2] = v[i + 2] + b4.z; x[i + 3] = v[i + 3] + b4.w;
+                m4[0] = fmaxf(m4[0], x[i]); m4[1] = fmaxf(m4[1], x[i + 1]);
+                m4[2] = fmaxf(m4[2], x[i + 2]); m4[3] = fmaxf(m4[3], x[i + 3]);
+            }
+            const float new_max = fmaxf(run_max, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+            const float off = new_max * LOG2E_F;
+            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                s4[0] += ex2_approx(fmaf(x[i], LOG2E_F, -off));
+                s4[1] += ex2_approx(fmaf(x[i + 1], LOG2E_F, -off));
+                s4[2] += ex2_approx(fmaf(x[i + 2], LOG2E_F, -off));
+                s4[3] += ex2_approx(fmaf(x[i + 3], LOG2E_F, -off));
+            }
+            run_sum = run_sum * ex2_approx((run_max - new_max) * LOG2E_F) + ((s4[0] + s4[1]) + (s4[2] + s4[3]));
+            run_max = new_max;
+        } else {
+            float cmax = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                x[i] = (i < nc) ? v[i] + bias_s[c0 + i] : -INFINITY;
+                cmax = fmaxf(cmax, x[i]);
+            }
+            const float new_max = fmaxf(run_max, cmax);
+            const float off = new_max * LOG2E_F;
+            float csum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (i < nc) csum += ex2_approx(fmaf(x[i], LOG2E_F, -off));
+            run_sum = run_sum * ex2_approx((run_max - new_max) * LOG2E_F) + csum;
+            run_max = new_max;
+        }
+    } else if (MODE == TC_EPI_PROB) {
+        // P^T[(n0+c0+i) * ldc + m]: for a fixed i the warp's 32 lanes write 32 consecutive floats
+        if (m < a.M) {
+            float* dst = a.C + (int64_t)(n0 + c0) * a.ldc + m;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                if (i < nc) {
+                    const float x = v[i] + bias_s[c0 + i];
+                    dst[(int64_t)i * a.ldc] = tf32_rn(ex2_approx(fmaf(x, LOG2E_F, -lse_l2)) * rs_m);
+                }
+            }
+        }
+    } else {
+        if (m < a.M) {
+            float* crow = a.C + (int64_t)sp * a.split_stride + (int64_t)m * a.ldc;
+            const int col0 = n0 + c0;
+            if (a.vec_ok && col0 + 32 <= a.n_store) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + i);
+                    *reinterpret_cast<float4*>(crow + col0 + i) =
+                        make_float4(v[i] + b4.x, v[i + 1] + b4.y, v[i + 2] + b4.z, v[i + 3] + b4.w);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int col = col0 + i;
+                    if (i < nc) {
+                        if (col < a.n_store) crow[col] = v[i] + bias_s[c0 + i];
+                        else if (col == a.bias_col) a.bias_grad[m] = v[i];
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int MODE, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
@@ -162,7 +280,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + 2 + s); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4);
     uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + TC_STAGES * TC_STAGE_BYTES + 8 * (2 * TC_STAGES + 4));
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(gen_base + TC_STAGES * TC_STAGE_BYTES + 8 * (2 * TC_STAGES + 4));
+    float* bias_smem = reinterpret_cast<float*>(gen_base + TC_STAGES * TC_STAGE_BYTES + TC_BAR_BYTES);   // [2][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -170,7 +290,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), TC_EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -192,12 +312,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int m_idx = t % a.tiles_m;
-                const int n_idx = (t / a.tiles_m) % a.tiles_n;
-                const int sp = t / (a.tiles_m * a.tiles_n);
-                const int kb0 = sp * a.kb_per_split;
+                const TileCoord tc = decode_tile(t, a);
+                const int kb0 = tc.sp * a.kb_per_split;
                 const int kb1 = min(a.kb_total, kb0 + a.kb_per_split);
-                const int m0 = m_idx * TC_BM, n0 = n_idx * a.BN;
+                const int m0 = tc.m_idx * TC_BM, n0 = tc.n_idx * a.BN;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
@@ -230,8 +348,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int sp = t / (a.tiles_m * a.tiles_n);
-            const int kb0 = sp * a.kb_per_split;
+            const TileCoord tc = decode_tile(t, a);
+            const int kb0 = tc.sp * a.kb_per_split;
             const int kb1 = min(a.kb_total, kb0 + a.kb_per_split);
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
             tcgen05_fence_after();
@@ -261,81 +379,47 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     } else {
         // =============================== epilogue ===================================
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;               // which of the two warps of that quarter
+        const int et = threadIdx.x - 64;                // 0..255
         const int row_in_tile = q * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        const float LOG2E = 1.4426950408889634f;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int m_idx = t % a.tiles_m;
-            const int n_idx = (t / a.tiles_m) % a.tiles_n;
-            const int sp = t / (a.tiles_m * a.tiles_n);
-            const int m = m_idx * TC_BM + row_in_tile;
-            const int n0 = n_idx * a.BN;
+            const TileCoord tc = decode_tile(t, a);
+            const int m = tc.m_idx * TC_BM + row_in_tile;
+            const int n0 = tc.n_idx * a.BN;
             const int n_valid = min(a.BN, a.N - n0);
+            const int nch = (n_valid + 31) >> 5;
+            // the tile's bias slice travels global -> register while the MMAs are still running
+            float bias_reg = 0.f;
+            if (a.bias != nullptr && et < n_valid) bias_reg = __ldg(a.bias + n0 + et);
+            float lse_l2 = 0.f, rs_m = 0.f;
+            if (MODE == TC_EPI_PROB && m < a.M) { lse_l2 = a.lse[m] * LOG2E_F; rs_m = a.rowscale[m]; }
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
+            float* bias_s = bias_smem + acc * 256;
+            bias_s[et] = bias_reg;
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
             float run_max = -INFINITY, run_sum = 0.f;
-            float lse_m = 0.f, rs_m = 0.f;
-            if (MODE == TC_EPI_PROB && m < a.M) { lse_m = a.lse[m]; rs_m = a.rowscale[m]; }
-            for (int c0 = 0; c0 < n_valid; c0 += 32) {
-                float v[32];
-                tmem_ld32(taddr + (uint32_t)c0, v);
-                const int nc = min(32, n_valid - c0);
-                if (MODE == TC_EPI_LSE) {
-                    float cmax = -INFINITY;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (i < nc) {
-                            v[i] += a.bias ? __ldg(a.bias + n0 + c0 + i) : 0.f;
-                            cmax = fmaxf(cmax, v[i]);
-                        }
-                    }
-                    const float new_max = fmaxf(run_max, cmax);
-                    const float off = new_max * LOG2E;
-                    float csum = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (i < nc) csum += exp2f(fmaf(v[i], LOG2E, -off));
-                    run_sum = run_sum * exp2f((run_max - new_max) * LOG2E) + csum;
-                    run_max = new_max;
-                } else if (MODE == TC_EPI_PROB) {
-                    // P^T[(n0+c0+i) * ldc + m]: for fixed i the warp writes 32 consecutive floats
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (i < nc && m < a.M) {
-                            const float x = v[i] + (a.bias ? __ldg(a.bias + n0 + c0 + i) : 0.f);
-                            const float pr = exp2f((x - lse_m) * LOG2E) * rs_m;
-                            a.C[(int64_t)(n0 + c0 + i) * a.ldc + m] = tf32_rn(pr);
-                        }
-                    }
-                } else {
-                    if (m < a.M) {
-                        float* crow = a.C + (int64_t)sp * a.split_stride + (int64_t)m * a.ldc;
-                        const int col0 = n0 + c0;
-                        if (a.vec_ok && col0 + 32 <= a.n_store && (!a.bias || ((uintptr_t)a.bias & 15) == 0)) {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + col0 + i)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                                *reinterpret_cast<float4*>(crow + col0 + i) =
-                                    make_float4(v[i] + b4.x, v[i + 1] + b4.y, v[i + 2] + b4.z, v[i + 3] + b4.w);
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const int col = col0 + i;
-                                if (i < nc) {
-                                    if (col < a.n_store) crow[col] = v[i] + (a.bias ? __ldg(a.bias + col) : 0.f);
-                                    else if (col == a.bias_col) a.bias_grad[m] = v[i];
-                                }
-                            }
-                        }
-                    }
+            float va[32], vb[32];
+            int c = half;
+            if (c < nch) tmem_ld32_issue(taddr + (uint32_t)(c * 32), va);
+            for (; c < nch; c += 4) {
+                tmem_wait_ld(va);
+                if (c + 2 < nch) tmem_ld32_issue(taddr + (uint32_t)((c + 2) * 32), vb);
+                epi_chunk<MODE>(a, va, bias_s, c * 32, min(32, n_valid - c * 32), n0, m, tc.sp, run_max, run_sum, lse_l2, rs_m);
+                if (c + 2 < nch) {
+                    tmem_wait_ld(vb);
+                    if (c + 4 < nch) tmem_ld32_issue(taddr + (uint32_t)((c + 4) * 32), va);
+                    epi_chunk<MODE>(a, vb, bias_s, (c + 2) * 32, min(32, n_valid - (c + 2) * 32), n0, m, tc.sp, run_max,
+                                    run_sum, lse_l2, rs_m);
                 }
             }
             if (MODE == TC_EPI_LSE && m < a.M) {
-                a.part_max[(int64_t)n_idx * a.M + m] = run_max;
-                a.part_sum[(int64_t)n_idx * a.M + m] = run_sum;
+                const int64_t pi = (int64_t)(tc.n_idx * 2 + half) * a.M + m;
+                a.part_max[pi] = run_max;
+                a.part_sum[pi] = run_sum;
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -385,8 +469,7 @@ static int make_tmap(CUtensorMap* tm, const float* base, int64_t inner, int64_t 
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE,
                      mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     B200_REQUIRE(r == CUDA_SUCCESS, B200VAE_ECUDA,
                  "cuTensorMapEncodeTiled failed (%d): base %p inner %lld outer %lld ld %lld box %dx%d", (int)r, base,
                  (long long)inner, (long long)outer, (long long)ld, box_inner, box_outer);
@@ -401,7 +484,8 @@ static int pick_bn(int N, bool b_mn) {
     if (N >= 256) return 256;
     return (int)round_up(N, b_mn ? 32 : 16);
 }
-int tc_lse_tiles(int N) { return (int)cdiv(N, pick_bn(N, false)); }
+// number of (max, sum) partial rows the LSE epilogue writes per user: two warps per 256-item tile
+int tc_lse_tiles(int N) { return 2 * (int)cdiv(N, pick_bn(N, false)); }
 
 template <int MODE, bool A_MN, bool B_MN>
 static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args, int grid, cudaStream_t s) {
@@ -425,6 +509,7 @@ int launch_tc_gemm(Ctx* c, int mode, const float* A, int64_t lda, int a_mn, cons
     a.BN = pick_bn(N, b_mn != 0);
     a.tiles_m = (int)cdiv(M, TC_BM);
     a.tiles_n = (int)cdiv(N, a.BN);
+    a.n_fastest = e.n_fastest;
     a.kb_total = (int)cdiv(K, TC_BK);
     a.split_k = std::max(1, std::min(e.split_k, a.kb_total));
     a.kb_per_split = (int)cdiv(a.kb_total, a.split_k);
