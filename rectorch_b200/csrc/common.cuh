@@ -151,6 +151,8 @@ int launch_tc_gemm(Ctx* c, int mode, const float* A, int64_t lda, int a_mn, cons
                    int b_mn, float* C, int64_t ldc, int M, int N, int K, const TcEpi& e,
                    cudaStream_t s);
 int tc_lse_tiles(int N);
+int tc_output_tiles(int M, int N, int b_mn);   // output tiles of the current tiling (pair tiles in CTA-pair mode)
+int tc_parallel_tiles(int num_sms);            // tiles that run concurrently (SMs, or SM pairs)
 int launch_splitk_reduce(Ctx* c, const float* parts, int n_split, int64_t split_stride, float* out,
                          int64_t ld_out, int M, int N, int64_t ld_part, const float* addend,
                          int64_t ld_add, float addend_scale, const float* mulY, int64_t ldy,

@@ -247,7 +247,7 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         tick(c, 3, 1, s);
         // dh = P W_d : A = P^T given as [K=I x M=Bp] (MN-major), B = W_d [K=I x N=H] (MN-major)
         TcEpi e3;
-        int split = std::max(1, std::min(64, c->num_sms / (int)(cdiv(B, 128) * cdiv(H, 256))));
+        int split = std::max(1, std::min(64, tc_parallel_tiles(c->num_sms) / tc_output_tiles(B, H, 1)));
         e3.split_k = split;
         e3.split_stride = (int64_t)B * H;
         B200_REQUIRE((int64_t)split * B * H <= c->splitk_elems, B200VAE_ECAPACITY, "split-K workspace too small");

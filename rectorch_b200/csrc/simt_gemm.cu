@@ -10,8 +10,8 @@
 //
 // Tiles are BM x 64 x 16 with BM = 64 (256 threads) or 32 (128 threads); the smaller tile is
 // picked when the 64-row grid would leave most of the 148 SMs idle (the hidden layers are only
-// ~500 x 600).  The global loads of K-block i+1 are issued into registers before the FMAs of
-// K-block i, so one L2 round trip overlaps a block of math instead of preceding it.
+// ~500 x 600).  K blocks stream global -> shared through a 3-stage cp.async pipeline, so two L2
+// round trips are always in flight behind the FMAs of the current block.
 #include "ctx.cuh"
 
 namespace b200 {
@@ -26,8 +26,9 @@ k_simt_gemm(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float
     constexpr int THREADS = BM * 4;                 // (BM/TM) x (BN/TN) threads
     constexpr int A_PER = BM * BK / THREADS;        // 4
     constexpr int B_PER = BN * BK / THREADS;        // 4 (BM=64) or 8 (BM=32)
-    __shared__ float As[BK][BM + 4];
-    __shared__ float Bs[BK][BN + 4];
+    constexpr int NST = 3;                          // cp.async pipeline depth
+    __shared__ float As[NST][BK][BM + 4];
+    __shared__ float Bs[NST][BK][BN + 4];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -39,16 +40,20 @@ k_simt_gemm(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float
 
     const bool a_kfast = (a_cs == 1);
     const bool b_nfast = (b_cs == 1);
-    float ra[A_PER], rb[B_PER];
 
-    auto load_tiles = [&](int k0) {
+    // one K block: every thread copies its 4-byte elements global -> shared asynchronously
+    // (src-size 0 zero-fills out-of-range elements)
+    auto issue_tiles = [&](int k0, int st) {
 #pragma unroll
         for (int u = 0; u < A_PER; ++u) {
             const int i = tid + u * THREADS;
             int mm, kk;
             if (a_kfast) { kk = i % BK; mm = i / BK; } else { mm = i % BM; kk = i / BM; }
             const int gm = m0 + mm, gk = k0 + kk;
-            ra[u] = (gm < M && gk < K) ? __ldg(A + (int64_t)gm * a_rs + (int64_t)gk * a_cs) : 0.f;
+            const bool ok = (gm < M && gk < K);
+            const float* src = ok ? A + (int64_t)gm * a_rs + (int64_t)gk * a_cs : A;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&As[st][kk][mm]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");
         }
 #pragma unroll
         for (int u = 0; u < B_PER; ++u) {
@@ -56,44 +61,39 @@ k_simt_gemm(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float
             int nn, kk;
             if (b_nfast) { nn = i % BN; kk = i / BN; } else { kk = i % BK; nn = i / BK; }
             const int gn = n0 + nn, gk = k0 + kk;
-            rb[u] = (gn < N && gk < K) ? __ldg(B + (int64_t)gk * b_rs + (int64_t)gn * b_cs) : 0.f;
+            const bool ok = (gn < N && gk < K);
+            const float* src = ok ? B + (int64_t)gk * b_rs + (int64_t)gn * b_cs : B;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&Bs[st][kk][nn]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");
         }
-    };
-    auto store_tiles = [&]() {
-#pragma unroll
-        for (int u = 0; u < A_PER; ++u) {
-            const int i = tid + u * THREADS;
-            int mm, kk;
-            if (a_kfast) { kk = i % BK; mm = i / BK; } else { mm = i % BM; kk = i / BM; }
-            As[kk][mm] = ra[u];
-        }
-#pragma unroll
-        for (int u = 0; u < B_PER; ++u) {
-            const int i = tid + u * THREADS;
-            int nn, kk;
-            if (b_nfast) { nn = i % BN; kk = i / BN; } else { kk = i % BK; nn = i / BK; }
-            Bs[kk][nn] = rb[u];
-        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    load_tiles(0);
-    for (int k0 = 0; k0 < K; k0 += BK) {
-        store_tiles();
+    const int nkb = (K + BK - 1) / BK;
+#pragma unroll
+    for (int p = 0; p < NST - 1; ++p) {
+        if (p < nkb) issue_tiles(p * BK, p);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int kb = 0; kb < nkb; ++kb) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");   // K block kb has landed
         __syncthreads();
-        if (k0 + BK < K) load_tiles(k0 + BK);      // in flight during the FMAs below
+        // refill the stage that was consumed in the previous iteration
+        if (kb + NST - 1 < nkb) issue_tiles((kb + NST - 1) * BK, (kb + NST - 1) % NST);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        const int st = kb % NST;
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
             float a[TM], b[TN];
 #pragma unroll
-            for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+            for (int i = 0; i < TM; ++i) a[i] = As[st][kk][ty * TM + i];
 #pragma unroll
-            for (int j = 0; j < TN; ++j) b[j] = Bs[kk][tx * TN + j];
+            for (int j = 0; j < TN; ++j) b[j] = Bs[st][kk][tx * TN + j];
 #pragma unroll
             for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
-        __syncthreads();
     }
 
     if (MODE == EPI_STORE) {

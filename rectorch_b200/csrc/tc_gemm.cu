@@ -31,6 +31,17 @@
 //                                chunks, so every SM sub-partition has two epilogue warps to issue from.
 // TMEM: 512 columns = 2 accumulator stages x 256 columns, so the epilogue of tile i overlaps
 // the MMAs of tile i+1.
+//
+// CTA pairs (template CG2, the default): the kernel is launched in clusters of two CTAs that sit
+// on the two SMs of a TPC and execute ONE tcgen05.mma.cta_group::2 of shape M=256 x N=256: each
+// CTA stages its own 128 rows of A and only HALF of the B tile (its 128 of the 256 N rows); the
+// tensor cores of both SMs read both halves.  Per unit of math this cuts the bytes every SM pulls
+// through the L2 crossbar by a third -- these tf32 GEMMs run at the chip-wide L2->SM throughput
+// cap (~6.5 KB/clk, profiles/), not at the tensor or HBM roofline, so that is what buys time.
+//   - the peer's TMA completes its bytes on the LEADER's full barrier (leader expects 2x bytes),
+//   - only the leader's warp 1 issues MMAs; tcgen05.commit multicasts the "stage free" /
+//     "accumulator ready" arrivals to both CTAs,
+//   - both CTAs' epilogue warps arrive on the leader's tmem_empty barrier.
 #include <cuda.h>
 #include <algorithm>
 #include "ctx.cuh"
@@ -39,16 +50,19 @@ namespace b200 {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                       // floats per K block = 128 B = one swizzle row
-constexpr int TC_STAGES = 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
-constexpr int TC_B_BYTES = 256 * TC_BK * 4;     // 32 KB (max N tile)
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_PIPE_BYTES = 192 * 1024;       // operand ring: 4 x 48 KB (1 CTA) or 6 x 32 KB (CTA pair)
+template <bool CG2> struct TcCfg {
+    static constexpr int B_BYTES = (CG2 ? 128 : 256) * TC_BK * 4;   // this CTA's share of the max N tile
+    static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    static constexpr int STAGES = TC_PIPE_BYTES / STAGE_BYTES;
+};
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_EPI_THREADS = 32 * TC_EPI_WARPS;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
-constexpr int TC_BAR_BYTES = 128;
+constexpr int TC_BAR_BYTES = 256;
 constexpr int TC_BIAS_BYTES = 2 * 256 * 4;
-constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + TC_BAR_BYTES + TC_BIAS_BYTES;
+constexpr int TC_SMEM = TC_PIPE_BYTES + 1024 /*align*/ + TC_BAR_BYTES + TC_BIAS_BYTES;
 constexpr unsigned long long SPIN_LIMIT = 1ull << 28;
 
 // ---------------------------------------------------------------------------------------
@@ -88,6 +102,43 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// ---- cluster / CTA-pair variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are signalled on a barrier given as a shared::cluster address
+// (the leader CTA's full barrier)
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* tm, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_cg2(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                     uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -268,12 +319,17 @@ __device__ __forceinline__ void epi_chunk(const TcArgs& a, const float* v, const
     }
 }
 
-template <int MODE, bool A_MN, bool B_MN>
+template <int MODE, bool A_MN, bool B_MN, bool CG2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    constexpr int TC_STAGES = TcCfg<CG2>::STAGES;
+    constexpr int TC_STAGE_BYTES = TcCfg<CG2>::STAGE_BYTES;
+    constexpr int NCTA = CG2 ? 2 : 1;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + TC_STAGES * TC_STAGE_BYTES;
+    const uint32_t bar_base = smem_base + TC_PIPE_BYTES;
+    const uint32_t cta_rank = CG2 ? cluster_ctarank() : 0u;
+    const bool leader = (cta_rank == 0);
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
     auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * TC_STAGES + s); };
@@ -281,73 +337,101 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4);
     uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_ptr =
-        reinterpret_cast<volatile uint32_t*>(gen_base + TC_STAGES * TC_STAGE_BYTES + 8 * (2 * TC_STAGES + 4));
-    float* bias_smem = reinterpret_cast<float*>(gen_base + TC_STAGES * TC_STAGE_BYTES + TC_BAR_BYTES);   // [2][256]
+        reinterpret_cast<volatile uint32_t*>(gen_base + TC_PIPE_BYTES + 8 * (2 * TC_STAGES + 4));
+    float* bias_smem = reinterpret_cast<float*>(gen_base + TC_PIPE_BYTES + TC_BAR_BYTES);   // [2][256]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), TC_EPI_WARPS); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), NCTA); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), TC_EPI_WARPS * NCTA); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
+    if (CG2) cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast
     if (warp == 1) {   // TMEM allocation: all 512 columns (1 CTA / SM)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CG2) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
-    const int total_tiles = a.tiles_m * a.tiles_n * a.split_k;
-    const uint32_t b_bytes = (uint32_t)a.BN * TC_BK * 4u;
+    const int total_tiles = a.tiles_m * a.tiles_n * a.split_k;      // CG2: tiles_m counts 256-row pair tiles
+    const int bn_cta = CG2 ? (a.BN >> 1) : a.BN;                     // B rows staged by this CTA
+    const uint32_t b_bytes = (uint32_t)bn_cta * TC_BK * 4u;
+    const int tile0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = tile0; t < total_tiles; t += tile_step) {
                 const TileCoord tc = decode_tile(t, a);
                 const int kb0 = tc.sp * a.kb_per_split;
                 const int kb1 = min(a.kb_total, kb0 + a.kb_per_split);
-                const int m0 = tc.m_idx * TC_BM, n0 = tc.n_idx * a.BN;
+                const int m0 = (tc.m_idx * NCTA + (int)cta_rank) * TC_BM;
+                const int n0 = tc.n_idx * a.BN + (int)cta_rank * bn_cta;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
                     const uint32_t sb = sa + TC_A_BYTES;
-                    mbar_expect_tx(full_bar(stage), TC_A_BYTES + b_bytes);
                     const int k0 = kb * TC_BK;
-                    if (!A_MN) {
-                        tma_load_2d(sa, &tmA, full_bar(stage), k0, m0);
-                    } else {
+                    if (!CG2) {
+                        mbar_expect_tx(full_bar(stage), TC_A_BYTES + b_bytes);
+                        if (!A_MN) {
+                            tma_load_2d(sa, &tmA, full_bar(stage), k0, m0);
+                        } else {
 #pragma unroll
-                        for (int c = 0; c < TC_BM / 32; ++c) tma_load_2d(sa + c * 4096, &tmA, full_bar(stage), m0 + 32 * c, k0);
-                    }
-                    if (!B_MN) {
-                        tma_load_2d(sb, &tmB, full_bar(stage), k0, n0);
+                            for (int c = 0; c < TC_BM / 32; ++c) tma_load_2d(sa + c * 4096, &tmA, full_bar(stage), m0 + 32 * c, k0);
+                        }
+                        if (!B_MN) {
+                            tma_load_2d(sb, &tmB, full_bar(stage), k0, n0);
+                        } else {
+                            for (int c = 0; c < bn_cta / 32; ++c) tma_load_2d(sb + c * 4096, &tmB, full_bar(stage), n0 + 32 * c, k0);
+                        }
                     } else {
-                        for (int c = 0; c < a.BN / 32; ++c) tma_load_2d(sb + c * 4096, &tmB, full_bar(stage), n0 + 32 * c, k0);
+                        // both CTAs' bytes complete on the leader's full barrier
+                        const uint32_t lead_full = mapa_cluster(full_bar(stage), 0u);
+                        if (leader) mbar_expect_tx(full_bar(stage), 2u * (TC_A_BYTES + b_bytes));
+                        else        mbar_arrive_cluster(lead_full);
+                        if (!A_MN) {
+                            tma_load_2d_cg2(sa, &tmA, lead_full, k0, m0);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < TC_BM / 32; ++c) tma_load_2d_cg2(sa + c * 4096, &tmA, lead_full, m0 + 32 * c, k0);
+                        }
+                        if (!B_MN) {
+                            tma_load_2d_cg2(sb, &tmB, lead_full, k0, n0);
+                        } else {
+                            for (int c = 0; c < bn_cta / 32; ++c) tma_load_2d_cg2(sb + c * 4096, &tmB, lead_full, n0 + 32 * c, k0);
+                        }
                     }
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // =============================== MMA issuer =================================
+    } else if (warp == 1 && leader) {
+        // =============================== MMA issuer (leader CTA only) ===============
         // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1,
         // a/b_format TF32 [7,10)/[10,13)=2, a_major [15], b_major [16], N>>3 [17,23), M>>4 [24,29)
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                               ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+                               ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)((TC_BM * NCTA) >> 4) << 24);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        for (int t = tile0; t < total_tiles; t += tile_step) {
             const TileCoord tc = decode_tile(t, a);
             const int kb0 = tc.sp * a.kb_per_split;
             const int kb1 = min(a.kb_total, kb0 + a.kb_per_split);
@@ -364,19 +448,24 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     for (int j = 0; j < TC_BK / 8; ++j) {
                         const uint64_t ad = A_MN ? make_sdesc(sa + j * 1024, 4096, 512, 1) : make_sdesc(sa + j * 32, 0, 1024, 2);
                         const uint64_t bd = B_MN ? make_sdesc(sb + j * 1024, 4096, 512, 1) : make_sdesc(sb + j * 32, 0, 1024, 2);
-                        tcgen05_mma_tf32(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+                        if (CG2) tcgen05_mma_tf32_cg2(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+                        else     tcgen05_mma_tf32(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
                     }
-                    tcgen05_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
-                    if (kb == kb1 - 1) tcgen05_commit(tfull_bar(acc)); // accumulator complete
+                    if (CG2) {
+                        tcgen05_commit_cg2(empty_bar(stage));                  // frees the slot in BOTH CTAs
+                        if (kb == kb1 - 1) tcgen05_commit_cg2(tfull_bar(acc)); // wakes both CTAs' epilogues
+                    } else {
+                        tcgen05_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
+                        if (kb == kb1 - 1) tcgen05_commit(tfull_bar(acc)); // accumulator complete
+                    }
                 }
                 __syncwarp();
                 if (++stage == TC_STAGES) { stage = 0; phase ^= 1u; }
             }
-            if (kb1 <= kb0 && lane == 0) mbar_arrive(tfull_bar(acc));   // empty K range (never with sane splits)
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
-    } else {
+    } else if (warp >= 2) {
         // =============================== epilogue ===================================
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;               // which of the two warps of that quarter
@@ -384,9 +473,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int row_in_tile = q * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const uint32_t lead_tempty[2] = {CG2 ? mapa_cluster(tempty_bar(0), 0u) : 0u, CG2 ? mapa_cluster(tempty_bar(1), 0u) : 0u};
+        for (int t = tile0; t < total_tiles; t += tile_step) {
             const TileCoord tc = decode_tile(t, a);
-            const int m = tc.m_idx * TC_BM + row_in_tile;
+            const int m = (tc.m_idx * NCTA + (int)cta_rank) * TC_BM + row_in_tile;
             const int n0 = tc.n_idx * a.BN;
             const int n_valid = min(a.BN, a.N - n0);
             const int nch = (n_valid + 31) >> 5;
@@ -423,7 +513,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) {
+                if (CG2) mbar_arrive_cluster(lead_tempty[acc]);
+                else     mbar_arrive(tempty_bar(acc));
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
@@ -431,10 +524,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
     // teardown
     tcgen05_fence_before();
-    __syncthreads();
+    if (CG2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -480,23 +574,54 @@ bool tc_supported(int M, int N, int K, int64_t lda, int64_t ldb) {
     return M >= 1 && N >= 16 && K >= 8 && (lda % 4 == 0) && (ldb % 4 == 0);
 }
 
+static bool use_cg2() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200VAE_TC_1CTA");
+        v = (e && e[0] == '1') ? 0 : 1;
+    }
+    return v == 1;
+}
+// N tile: <= 256; each CTA of a pair stages BN/2 rows, so the granule doubles in pair mode
 static int pick_bn(int N, bool b_mn) {
     if (N >= 256) return 256;
-    return (int)round_up(N, b_mn ? 32 : 16);
+    const int g = (b_mn ? 32 : 16) * (use_cg2() ? 2 : 1);
+    return (int)std::min<int64_t>(256, round_up(N, g));
 }
 // number of (max, sum) partial rows the LSE epilogue writes per user: two warps per 256-item tile
 int tc_lse_tiles(int N) { return 2 * (int)cdiv(N, pick_bn(N, false)); }
 
-template <int MODE, bool A_MN, bool B_MN>
-static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args, int grid, cudaStream_t s) {
+int tc_output_tiles(int M, int N, int b_mn) {
+    return (int)(cdiv(M, use_cg2() ? 2 * TC_BM : TC_BM) * cdiv(N, pick_bn(N, b_mn != 0)));
+}
+int tc_parallel_tiles(int num_sms) { return use_cg2() ? std::max(1, num_sms / 2) : num_sms; }
+
+template <int MODE, bool A_MN, bool B_MN, bool CG2>
+static int launch_inst2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args, int grid, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        B200_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<MODE, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+        B200_CUDA_OK(cudaFuncSetAttribute(k_tc_gemm<MODE, A_MN, B_MN, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
         attr_set = true;
     }
-    k_tc_gemm<MODE, A_MN, B_MN><<<grid, TC_THREADS, TC_SMEM, s>>>(tmA, tmB, args);
-    B200_CUDA_OK(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TC_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG2 ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_gemm<MODE, A_MN, B_MN, CG2>, tmA, tmB, args));
     return 0;
+}
+template <int MODE, bool A_MN, bool B_MN>
+static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& args, int grid, cudaStream_t s) {
+    return use_cg2() ? launch_inst2<MODE, A_MN, B_MN, true>(tmA, tmB, args, grid, s)
+                     : launch_inst2<MODE, A_MN, B_MN, false>(tmA, tmB, args, grid, s);
 }
 
 int launch_tc_gemm(Ctx* c, int mode, const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb, int b_mn,
@@ -507,7 +632,8 @@ int launch_tc_gemm(Ctx* c, int mode, const float* A, int64_t lda, int a_mn, cons
     TcArgs a;
     a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
     a.BN = pick_bn(N, b_mn != 0);
-    a.tiles_m = (int)cdiv(M, TC_BM);
+    const bool cg2 = use_cg2();
+    a.tiles_m = (int)cdiv(M, cg2 ? 2 * TC_BM : TC_BM);
     a.tiles_n = (int)cdiv(N, a.BN);
     a.n_fastest = e.n_fastest;
     a.kb_total = (int)cdiv(K, TC_BK);
@@ -528,10 +654,10 @@ int launch_tc_gemm(Ctx* c, int mode, const float* A, int64_t lda, int a_mn, cons
     CUtensorMap tmA, tmB;
     if (!a_mn) B200_CHECK(make_tmap(&tmA, A, K, M, lda, TC_BK, TC_BM, false));
     else       B200_CHECK(make_tmap(&tmA, A, M, K, lda, 32, TC_BK, true));
-    if (!b_mn) B200_CHECK(make_tmap(&tmB, B, K, N, ldb, TC_BK, a.BN, false));
+    if (!b_mn) B200_CHECK(make_tmap(&tmB, B, K, N, ldb, TC_BK, cg2 ? a.BN / 2 : a.BN, false));
     else       B200_CHECK(make_tmap(&tmB, B, N, K, ldb, 32, TC_BK, true));
     const int total = a.tiles_m * a.tiles_n * a.split_k;
-    const int grid = std::min(total, c->num_sms);
+    const int grid = cg2 ? 2 * std::min(total, std::max(1, c->num_sms / 2)) : std::min(total, c->num_sms);
     int rc;
 #define INST(MODE_, AM, BM_) rc = launch_inst<MODE_, AM, BM_>(tmA, tmB, a, grid, s)
     if (mode == TC_EPI_LSE) { B200_REQUIRE(!a_mn && !b_mn, B200VAE_EINVAL, "LSE epilogue expects K-major operands"); INST(TC_EPI_LSE, false, false); }
