@@ -211,6 +211,10 @@ int64_t b200vae_launch_count(b200vae_ctx* ctx, int reset);
  * 2 = decoder bwd recompute (K5), 3 = dW_d GEMM, 4 = dh GEMM.  Enable with
  * b200vae_set_timing(ctx, 1); values are valid after the stream is synchronised. */
 int  b200vae_set_timing(b200vae_ctx* ctx, int enable);
+/* "launcher_name milliseconds\n" for every launch of the most recent step run with timing enabled
+ * (CUDA events recorded after each launch on the launching stream; sync the stream first).
+ * Returns the number of events. */
+int  b200vae_timing_report(b200vae_ctx* ctx, char* buf, int cap);
 float b200vae_kernel_ms(b200vae_ctx* ctx, int which);
 
 #ifdef __cplusplus

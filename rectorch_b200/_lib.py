@@ -75,6 +75,7 @@ _SIGS = {
     "b200vae_launch_count": (c_int64, [c_void_p, c_int]),
     "b200vae_set_timing": (c_int, [c_void_p, c_int]),
     "b200vae_kernel_ms": (c_float, [c_void_p, c_int]),
+    "b200vae_timing_report": (c_int, [c_void_p, c_char_p, c_int]),
 }
 
 EXPORTS = tuple(sorted(_SIGS))

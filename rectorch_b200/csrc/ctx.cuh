@@ -69,6 +69,9 @@ struct Ctx {
     int64_t* lens_tmp = nullptr;      // [max_batch+1]
 
     // timing instrumentation
+    std::vector<cudaEvent_t> tev;     // one event after every launch of the current step (timing mode)
+    std::vector<const char*> tnames;
+    int tcount = 0;
     bool timing = false;
     cudaEvent_t ev[5][2];
     bool ev_valid[5] = {false, false, false, false, false};
@@ -76,6 +79,22 @@ struct Ctx {
     bool use_tc = true;
     bool tc_dec = false;              // decoder-last shapes are tcgen05-eligible
 };
+
+// bookkeeping after every kernel launch: launch counter + (timing mode) an event named after the launcher
+inline void note(Ctx* c, const char* name, cudaStream_t s) {
+    c->launches++;
+    if (c->timing) {
+        if (c->tcount == (int)c->tev.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            c->tev.push_back(e);
+            c->tnames.push_back(name);
+        }
+        c->tnames[c->tcount] = name;
+        cudaEventRecord(c->tev[c->tcount], s);
+        c->tcount++;
+    }
+}
 
 inline void tick(Ctx* c, int which, int edge, cudaStream_t s) {
     if (c->timing) {

@@ -54,7 +54,7 @@ int launch_reparam_kl(Ctx* c, const float* enc_out, int B, int L, bool train, co
     int threads = 256;
     k_reparam_kl<<<(int)cdiv((int64_t)B * 32, threads), threads, 0, s>>>(
         enc_out, B, L, train ? 1 : 0, eps_tape, seed, step, row_offset, row_ids, z, eps_out, kl_row);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -79,7 +79,7 @@ int launch_dz_to_denc(Ctx* c, const float* dz, const float* enc_out, const float
     int64_t n = (int64_t)B * L;
     if (n == 0) return 0;
     k_dz_to_denc<<<(int)cdiv(n, 256), 256, 0, s>>>(dz, enc_out, eps, B, L, beta_over_B, train ? 1 : 0, denc);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -120,7 +120,7 @@ int launch_loss_final(Ctx* c, const float* loss_row, const float* kl_row, int B,
                       float beta, float lam, const float* norms, int n_tensors, float* loss_out,
                       cudaStream_t s) {
     k_loss_final<<<1, 256, 0, s>>>(loss_row, kl_row, B, inv_Bg, beta, lam, norms, n_tensors, loss_out);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -160,7 +160,7 @@ int launch_tensor_norms(Ctx* c, const float* w, const int64_t* offs, const int64
     dim3 grid(64, n_tensors);
     k_norm_partial<<<grid, 256, 0, s>>>(w, offs, lens, partial);
     k_norm_final<<<n_tensors, 32, 0, s>>>(partial, 64, norms);
-    c->launches += 2;
+    note(c, __func__, s); c->launches++;
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -240,7 +240,7 @@ int launch_adam(Ctx* c, float* w, const float* g, float* m, float* v, int64_t n,
         k_adam<true><<<blocks, 256, 0, s>>>(w, g, m, v, n, -lr_over_bc1, b1c, beta2, b2c, bc2_sqrt, eps, wd, lam, norm_ptr, shadow, sh_lo, sh_hi);
     else
         k_adam<false><<<blocks, 256, 0, s>>>(w, g, m, v, n, -lr_over_bc1, b1c, beta2, b2c, bc2_sqrt, eps, 0.f, 0.f, nullptr, shadow, sh_lo, sh_hi);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -254,7 +254,7 @@ int launch_round_tf32(Ctx* c, const float* x, float* y, int64_t n, cudaStream_t 
     if (n == 0) return 0;
     int blocks = (int)std::min<int64_t>(cdiv(n, 256), (int64_t)c->num_sms * 8);
     k_round_tf32<<<blocks, 256, 0, s>>>(x, y, n);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -269,7 +269,7 @@ __global__ void k_tanh_grad(float* __restrict__ d, const float* __restrict__ y, 
 int launch_tanh_grad(Ctx* c, float* d, const float* y, int64_t n, cudaStream_t s) {
     if (n == 0) return 0;
     k_tanh_grad<<<(int)cdiv(n, 256), 256, 0, s>>>(d, y, n);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -281,7 +281,7 @@ __global__ void k_axpy(float* __restrict__ y, const float* __restrict__ x, float
 int launch_axpy(Ctx* c, float* y, const float* x, float a, int64_t n, cudaStream_t s) {
     if (n == 0) return 0;
     k_axpy<<<(int)cdiv(n, 256), 256, 0, s>>>(y, x, a, n);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -48,6 +48,7 @@ static void free_ctx(Ctx* c) {
     F(c->h_r); F(c->wd_shadow); F(c->d_specs); F(c->spmm_acc); F(c->spmm_ticket);
     for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventDestroy(c->ev[i][j]);
+    for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
     delete c;
 }
 
@@ -191,6 +192,7 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
     B200_REQUIRE(Bg >= B, B200VAE_EINVAL, "B_global (%d) < B (%d)", Bg, B);
     const int I = c->n_items;
     const float inv_Bg = 1.0f / (float)Bg;
+    if (c->timing) { c->tcount = 0; note(c, "step_start", s); c->launches--; }
     FwdState st;
     B200_CHECK(make_view(c, 0, row_ids, B, &st.in, s));
     if (use_target) {
@@ -219,7 +221,7 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
     // ---------------- backward: decoder output layer ----------------
     float* rowscale = c->loss_row;   // loss_row is consumed; reuse as T/Bg
     k_scale_rows<<<(int)cdiv(B, 256), 256, 0, s>>>(c->T, inv_Bg, B, rowscale);
-    c->launches++;
+    note(c, __func__, s);
     float* dWd = c->g + DL.w_off;
     float* dbd = c->g + DL.b_off;
     float* d0 = c->dbuf[0];
@@ -237,7 +239,7 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         // dW_d | db_d = P^T [I x B] * [h | 1]  : A = P^T (K-major), B = hT [(H+8) x Bp] (K-major)
         dim3 tg((unsigned)cdiv(Bp, 32), (unsigned)cdiv(H + 8, 32));
         k_transpose_ones<<<tg, dim3(32, 8), 0, s>>>(st.h_last, B, H, Bp, c->hT);
-        c->launches++;
+        note(c, __func__, s);
         TcEpi e2;
         e2.bias_grad = dbd;
         e2.bias_col = H;
@@ -308,6 +310,7 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
     }
     const Layer& e0 = c->enc[0];
     B200_CUDA_OK(cudaMemsetAsync(c->g + e0.w_off, 0, (size_t)I * e0.out * sizeof(float), s));
+    if (c->timing) { note(c, "memset_dW1", s); c->launches--; }
     B200_CHECK(launch_spmm_scatter(c, st.in, c->xt, 1.0f, cur, e0.out, c->g + e0.w_off, s));
     B200_CHECK(launch_colsum(c, cur, e0.out, B, e0.out, c->g + e0.b_off, s));
     return 0;
@@ -768,6 +771,22 @@ float b200vae_kernel_ms(b200vae_ctx* ctx, int which) {
     float ms = -1.f;
     if (cudaEventElapsedTime(&ms, c->ev[which][0], c->ev[which][1]) != cudaSuccess) return -1.f;
     return ms;
+}
+
+int b200vae_timing_report(b200vae_ctx* ctx, char* buf, int cap) {
+    // "name ms\n" per launch of the most recent instrumented step (valid after a stream sync)
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    if (!c || !buf || cap <= 0) return B200VAE_EINVAL;
+    int pos = 0;
+    buf[0] = 0;
+    for (int i = 1; i < c->tcount; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->tev[i - 1], c->tev[i]) != cudaSuccess) ms = -1.f;
+        int n = snprintf(buf + pos, cap - pos, "%s %.6f\n", c->tnames[i], ms);
+        if (n <= 0 || n >= cap - pos) break;
+        pos += n;
+    }
+    return c->tcount;
 }
 
 int b200vae_check_error_flag(b200vae_ctx* ctx) {

@@ -8,29 +8,31 @@
 //   C[m,n] = epi( alpha * sum_k A(m,k) * B(k,n) )
 //   A(m,k) = A[m*a_rs + k*a_cs],  B(k,n) = B[k*b_rs + n*b_cs]   (any strides -> any transposes)
 //
-// Tiles are BM x 64 x 16 with BM = 64 (256 threads) or 32 (128 threads); the smaller tile is
-// picked when the 64-row grid would leave most of the 148 SMs idle (the hidden layers are only
+// Tiles are 64 x 64 x 16 (256 threads, 4x4 per thread) or 32 x 32 x 16 (128 threads, 2x4); the
+// smaller tile is picked when the 64-row grid would leave most of the 148 SMs idle (the hidden layers are only
 // ~500 x 600).  K blocks stream global -> shared through a 3-stage cp.async pipeline, so two L2
 // round trips are always in flight behind the FMAs of the current block.
 #include "ctx.cuh"
 
 namespace b200 {
 
-constexpr int BN = 64, BK = 16, TM = 4, TN = 4;
+constexpr int BK = 16;
 
-template <int MODE, int BM>
-__global__ void __launch_bounds__(BM * 4)
+template <int MODE, int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
 k_simt_gemm(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float* __restrict__ B,
             int64_t b_rs, int64_t b_cs, float* __restrict__ C, int64_t ldc, int M, int N, int K,
             GemmEpi e) {
-    constexpr int THREADS = BM * 4;                 // (BM/TM) x (BN/TN) threads
-    constexpr int A_PER = BM * BK / THREADS;        // 4
-    constexpr int B_PER = BN * BK / THREADS;        // 4 (BM=64) or 8 (BM=32)
+    constexpr int TXN = BN / TN;                    // threads across N
+    constexpr int THREADS = (BM / TM) * TXN;
+    constexpr int A_PER = BM * BK / THREADS;
+    constexpr int B_PER = BN * BK / THREADS;
+    static_assert(BM * BK % THREADS == 0 && BN * BK % THREADS == 0, "tile / thread mismatch");
     constexpr int NST = 3;                          // cp.async pipeline depth
     __shared__ float As[NST][BK][BM + 4];
     __shared__ float Bs[NST][BK][BN + 4];
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
+    const int tx = tid % TXN, ty = tid / TXN;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     float acc[TM][TN];
 #pragma unroll
@@ -117,6 +119,7 @@ k_simt_gemm(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float
             }
         }
     } else if (MODE == EPI_LSE) {
+        static_assert(MODE != EPI_LSE || (TXN == 16 && BN == 64), "LSE epilogue is written for 64-column tiles");
         // per (row, 64-column tile): running max and sum of exp(logit - max)
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
@@ -158,29 +161,180 @@ k_simt_gemm(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float
     }
 }
 
-template <int MODE>
-static void launch_mode(bool small, dim3 g64, dim3 g32, const float* A, int64_t a_rs, int64_t a_cs, const float* B,
-                        int64_t b_rs, int64_t b_cs, float* C, int64_t ldc, int M, int N, int K, const GemmEpi& e,
-                        cudaStream_t s) {
-    if (small) k_simt_gemm<MODE, 32><<<g32, 128, 0, s>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e);
-    else       k_simt_gemm<MODE, 64><<<g64, 256, 0, s>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e);
+// ------------------------------------------------------------------------------------------
+// Vectorised variant for the aligned case (all hidden layers of real configurations):
+// 32 x 64 x 16 tiles, 128 threads, 4x4 per thread.  Each operand is staged in the shared-memory
+// orientation that matches its contiguous global dimension, so every global->shared copy is a
+// 16-byte cp.async (8x fewer LDGSTS than the scalar kernel) and every fragment read is one
+// LDS.128 per 4 K-steps.  Measured on B200: the scalar kernel was bound by LDGSTS/LDS issue
+// (~28 us for 500x400x600), not by FMAs.
+// ------------------------------------------------------------------------------------------
+template <bool A_KFAST, bool B_KFAST>
+__global__ void __launch_bounds__(128)
+k_simt_gemm_v(const float* __restrict__ A, int64_t a_ld, const float* __restrict__ B, int64_t b_ld,
+              float* __restrict__ C, int64_t ldc, int M, int N, int K, GemmEpi e) {
+    constexpr int VBM = 32, VBN = 64, NST = 3;
+    // A: [m][k] if K is contiguous (a_ld = row pitch of m) else [k][m] (a_ld = row pitch of k); same for B with n
+    __shared__ __align__(16) float As[NST][A_KFAST ? VBM : BK][(A_KFAST ? BK : VBM) + 4];
+    __shared__ __align__(16) float Bs[NST][B_KFAST ? VBN : BK][(B_KFAST ? BK : VBN) + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * VBM, n0 = blockIdx.x * VBN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    auto cp16 = [](void* dst, const float* src, int bytes) {
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+    };
+    auto issue = [&](int k0, int st) {
+        {   // A: 128 chunks of 4 floats, one per thread
+            if (A_KFAST) {
+                const int row = tid >> 2, kq = (tid & 3) * 4;
+                const int gm = m0 + row, gk = k0 + kq;
+                const int bytes = (gm < M) ? max(0, min(16, (K - gk) * 4)) : 0;
+                cp16(&As[st][row][kq], bytes > 0 ? A + (int64_t)gm * a_ld + gk : A, bytes);
+            } else {
+                const int kk = tid >> 3, mq = (tid & 7) * 4;
+                const int gk = k0 + kk, gm = m0 + mq;
+                const int bytes = (gk < K) ? max(0, min(16, (M - gm) * 4)) : 0;
+                cp16(&As[st][kk][mq], bytes > 0 ? A + (int64_t)gk * a_ld + gm : A, bytes);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {   // B: 256 chunks
+            const int c = tid + u * 128;
+            if (B_KFAST) {
+                const int row = c >> 2, kq = (c & 3) * 4;
+                const int gn = n0 + row, gk = k0 + kq;
+                const int bytes = (gn < N) ? max(0, min(16, (K - gk) * 4)) : 0;
+                cp16(&Bs[st][row][kq], bytes > 0 ? B + (int64_t)gn * b_ld + gk : B, bytes);
+            } else {
+                const int kk = c >> 4, nq = (c & 15) * 4;
+                const int gk = k0 + kk, gn = n0 + nq;
+                const int bytes = (gk < K) ? max(0, min(16, (N - gn) * 4)) : 0;
+                cp16(&Bs[st][kk][nq], bytes > 0 ? B + (int64_t)gk * b_ld + gn : B, bytes);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int nkb = (K + BK - 1) / BK;
+#pragma unroll
+    for (int p = 0; p < NST - 1; ++p) {
+        if (p < nkb) issue(p * BK, p);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int kb = 0; kb < nkb; ++kb) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");
+        __syncthreads();
+        if (kb + NST - 1 < nkb) issue((kb + NST - 1) * BK, (kb + NST - 1) % NST);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        const int st = kb % NST;
+#pragma unroll
+        for (int kk0 = 0; kk0 < BK; kk0 += 4) {
+            float a[4][4], b[4][4];   // [row or col][k step]
+            if (A_KFAST) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 t = *reinterpret_cast<const float4*>(&As[st][ty * 4 + i][kk0]);
+                    a[i][0] = t.x; a[i][1] = t.y; a[i][2] = t.z; a[i][3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 t = *reinterpret_cast<const float4*>(&As[st][kk0 + q][ty * 4]);
+                    a[0][q] = t.x; a[1][q] = t.y; a[2][q] = t.z; a[3][q] = t.w;
+                }
+            }
+            if (B_KFAST) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 t = *reinterpret_cast<const float4*>(&Bs[st][tx * 4 + j][kk0]);
+                    b[j][0] = t.x; b[j][1] = t.y; b[j][2] = t.z; b[j][3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 t = *reinterpret_cast<const float4*>(&Bs[st][kk0 + q][tx * 4]);
+                    b[0][q] = t.x; b[1][q] = t.y; b[2][q] = t.z; b[3][q] = t.w;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i][q], b[j][q], acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float y = e.alpha * acc[i][j];
+            if (e.bias) y += e.bias[gn];
+            if (e.addend) y += e.addend_scale * e.addend[(int64_t)gm * e.ld_addend + gn];
+            if (e.act) y = tanhf(y);
+            if (e.mulY) {
+                const float t = e.mulY[(int64_t)gm * e.ldy + gn];
+                y *= (1.f - t * t);
+            }
+            C[(int64_t)gm * ldc + gn] = y;
+        }
+    }
 }
 
 int launch_simt_gemm(Ctx* c, int mode, const float* A, int64_t a_rs, int64_t a_cs, const float* B,
                      int64_t b_rs, int64_t b_cs, float* C, int64_t ldc, int M, int N, int K,
                      const GemmEpi& e, cudaStream_t s) {
     if (M == 0 || N == 0) return 0;
-    dim3 g64((unsigned)cdiv(N, BN), (unsigned)cdiv(M, 64));
-    dim3 g32((unsigned)cdiv(N, BN), (unsigned)cdiv(M, 32));
+    dim3 g64((unsigned)cdiv(N, 64), (unsigned)cdiv(M, 64));
+    dim3 g32((unsigned)cdiv(N, 32), (unsigned)cdiv(M, 32));
     B200_REQUIRE(g32.y <= 65535, B200VAE_EINVAL, "simt_gemm: M too large (%d)", M);
     const int sms = c->num_sms > 0 ? c->num_sms : 148;
-    const bool small = (int64_t)g64.x * g64.y < 2 * (int64_t)sms;   // too few 64-row tiles to fill the GPU
-    switch (mode) {
-        case EPI_STORE: launch_mode<EPI_STORE>(small, g64, g32, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e, s); break;
-        case EPI_LSE:   launch_mode<EPI_LSE>(small, g64, g32, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e, s); break;
-        default:        launch_mode<EPI_PROB>(small, g64, g32, A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e, s); break;
+    // the hidden layers are ~500 x 600: 64x64 tiles would occupy half the SMs with one 4-warp CTA each
+    // (one warp per scheduler = every dependency stall is exposed).  32x32 tiles with a 2x4 micro-tile
+    // give ~450 CTAs of 4 warps -> 3 CTAs / SM to switch between.
+    const bool small = (int64_t)g64.x * g64.y < 4 * (int64_t)sms;
+    if (mode == EPI_STORE) {
+        // aligned operands -> vectorised kernel
+        const bool a_k = (a_cs == 1), a_m = (a_rs == 1);
+        const bool b_k = (b_rs == 1), b_n = (b_cs == 1);
+        const int64_t a_ld = a_k ? a_rs : a_cs, b_ld = b_k ? b_cs : b_rs;
+        const bool ok = (a_k || a_m) && (b_k || b_n) && (a_ld % 4 == 0) && (b_ld % 4 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
+        if (ok) {
+            dim3 gv((unsigned)cdiv(N, 64), (unsigned)cdiv(M, 32));
+            if (a_k && b_k)       k_simt_gemm_v<true, true><<<gv, 128, 0, s>>>(A, a_ld, B, b_ld, C, ldc, M, N, K, e);
+            else if (a_k && !b_k) k_simt_gemm_v<true, false><<<gv, 128, 0, s>>>(A, a_ld, B, b_ld, C, ldc, M, N, K, e);
+            else if (!a_k && b_k) k_simt_gemm_v<false, true><<<gv, 128, 0, s>>>(A, a_ld, B, b_ld, C, ldc, M, N, K, e);
+            else                  k_simt_gemm_v<false, false><<<gv, 128, 0, s>>>(A, a_ld, B, b_ld, C, ldc, M, N, K, e);
+            note(c, __func__, s);
+            B200_CUDA_OK(cudaGetLastError());
+            return 0;
+        }
     }
-    c->launches++;
+    switch (mode) {
+        case EPI_STORE:
+            if (small) k_simt_gemm<EPI_STORE, 32, 32, 2, 4><<<g32, 128, 0, s>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e);
+            else       k_simt_gemm<EPI_STORE, 64, 64, 4, 4><<<g64, 256, 0, s>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e);
+            break;
+        case EPI_LSE:
+            k_simt_gemm<EPI_LSE, 64, 64, 4, 4><<<g64, 256, 0, s>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e);
+            break;
+        default:
+            k_simt_gemm<EPI_PROB, 64, 64, 4, 4><<<g64, 256, 0, s>>>(A, a_rs, a_cs, B, b_rs, b_cs, C, ldc, M, N, K, e);
+            break;
+    }
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -206,7 +360,7 @@ k_colsum(const float* __restrict__ X, int64_t ldx, int M, int N, float* __restri
 int launch_colsum(Ctx* c, const float* X, int64_t ldx, int M, int N, float* out, cudaStream_t s) {
     if (N == 0) return 0;
     k_colsum<<<(int)cdiv(N, 32), dim3(32, 32), 0, s>>>(X, ldx, M, N, out);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -234,7 +388,7 @@ int launch_lse_merge(Ctx* c, const float* pmax, const float* psum, int n_tiles, 
     if (M == 0) return 0;
     int threads = 256;
     k_lse_merge<<<(int)cdiv((int64_t)M * 32, threads), threads, 0, s>>>(pmax, psum, n_tiles, M, lse);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }

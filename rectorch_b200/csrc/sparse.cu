@@ -62,7 +62,7 @@ __global__ void k_batch_scan(const int64_t* __restrict__ indptr, const int32_t* 
 int launch_batch_scan(Ctx* c, const int64_t* indptr, const int32_t* row_ids, int B, int64_t cap,
                       int64_t* bp, int32_t* sp, cudaStream_t s) {
     k_batch_scan<<<1, 1024, 0, s>>>(indptr, row_ids, B, cap, bp, sp, c->d_err);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -97,7 +97,7 @@ __global__ void k_scan_i64(const int64_t* __restrict__ lens, int n, int64_t cap,
 
 int launch_scan_i64(Ctx* c, const int64_t* lens, int n, int64_t cap, int64_t* out, cudaStream_t s) {
     k_scan_i64<<<1, 1024, 0, s>>>(lens, n, cap, out, c->d_err);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -154,7 +154,7 @@ int launch_batch_prep(Ctx* c, const BatchView& in, float p, uint64_t seed, uint6
     int blocks = (int)cdiv((int64_t)in.B * 32, threads);
     k_batch_prep<<<blocks, threads, 0, s>>>(in, p, seed, step, row_offset, keep_tape, train ? 1 : 0,
                                             c->cfg.max_batch_nnz, xt);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -175,7 +175,7 @@ int launch_row_sums(Ctx* c, const BatchView& v, float* out, cudaStream_t s) {
     if (v.B == 0) return 0;
     int threads = 256;
     k_row_sums<<<(int)cdiv((int64_t)v.B * 32, threads), threads, 0, s>>>(v, out);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -301,7 +301,7 @@ int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const floa
         int threads = (int)std::min<int64_t>(256, round_up(H, 32));
         k_spmm_gather<1><<<grid, threads, 0, s>>>(v, vals, Wt, H, bias, act, out, c->spmm_acc, c->spmm_ticket);
     }
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -355,7 +355,7 @@ int launch_spmm_scatter(Ctx* c, const BatchView& v, const float* vals, float sca
         int threads = (int)std::min<int64_t>(256, round_up(H, 32));
         k_spmm_scatter<1><<<grid, threads, 0, s>>>(v, vals, scale, dY, H, dWt);
     }
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -377,7 +377,7 @@ int launch_bias_scatter(Ctx* c, const BatchView& v, float scale, float* db, cuda
     if (v.B == 0) return 0;
     int threads = 256;
     k_bias_scatter<<<(int)cdiv((int64_t)v.B * 32, threads), threads, 0, s>>>(v, scale, db);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -399,7 +399,7 @@ __global__ void k_dense_count(const float* __restrict__ dense, int B, int I, int
 int launch_dense_count(Ctx* c, const float* dense, int B, int I, int64_t* lens, cudaStream_t s) {
     int threads = 256;
     k_dense_count<<<(int)cdiv((int64_t)B * 32, threads), threads, 0, s>>>(dense, B, I, lens);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -431,7 +431,7 @@ int launch_dense_fill(Ctx* c, const float* dense, int B, int I, const int64_t* i
     int threads = 256;
     k_dense_fill<<<(int)cdiv((int64_t)B * 32, threads), threads, 0, s>>>(
         dense, B, I, indptr, c->cfg.max_batch_nnz, indices, values);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -451,7 +451,7 @@ int launch_expand(Ctx* c, const BatchView& v, int I, float* out, cudaStream_t s)
     B200_CUDA_OK(cudaMemsetAsync(out, 0, (size_t)v.B * I * sizeof(float), s));
     int threads = 256;
     k_expand<<<(int)cdiv((int64_t)v.B * 32, threads), threads, 0, s>>>(v, I, out);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -472,7 +472,7 @@ int launch_mask_seen(Ctx* c, const BatchView& v, int I, float* scores, cudaStrea
     if (v.B == 0) return 0;
     int threads = 256;
     k_mask_seen<<<(int)cdiv((int64_t)v.B * 32, threads), threads, 0, s>>>(v, I, scores);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -506,7 +506,7 @@ int launch_row_loss(Ctx* c, const BatchView& tgt, const float* h, const float* g
     int threads = 256;
     k_row_loss<<<(int)cdiv((int64_t)tgt.B * 32, threads), threads, 0, s>>>(tgt, h, gvec, H, bias, lse,
                                                                             T, loss_row);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -119,7 +119,9 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t local_addr, uint32_t c
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default (cta-scope release) semantics: a cluster-scope release would drain this thread's
+    // outstanding TMA traffic first and serialise the peer's load stream (measured: 2x slower GEMM)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion bytes are signalled on a barrier given as a shared::cluster address
 // (the leader CTA's full barrier)
@@ -224,6 +226,7 @@ struct TcArgs {
     const float* rowscale;
     float* bias_grad;
     int vec_ok;             // C rows are 16 B aligned
+    int dbg;                // B200VAE_TC_DBG: 1 = no operand loads (MMA issue-rate probe, garbage results)
 };
 
 struct TileCoord { int m_idx, n_idx, sp; };
@@ -373,7 +376,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
-        if (lane == 0) {
+        if (lane == 0 && !(a.dbg & 1)) {
             int stage = 0;
             uint32_t phase = 0;
             for (int t = tile0; t < total_tiles; t += tile_step) {
@@ -439,7 +442,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             tcgen05_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
             for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(full_bar(stage), phase);
+                if (!(a.dbg & 1)) mbar_wait(full_bar(stage), phase);
                 tcgen05_fence_after();
                 if (lane == 0) {
                     const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
@@ -646,6 +649,11 @@ int launch_tc_gemm(Ctx* c, int mode, const float* A, int64_t lda, int a_mn, cons
     a.bias_col = e.bias_col;
     a.n_store = (e.bias_col >= 0) ? e.bias_col : N;
     a.vec_ok = (C && ((uintptr_t)C & 15) == 0 && (ldc % 4 == 0) && (e.split_stride % 4 == 0)) ? 1 : 0;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* ev = getenv("B200VAE_TC_DBG"); dbg = ev ? atoi(ev) : 0; }
+        a.dbg = dbg;
+    }
     if (mode == TC_EPI_STORE && e.split_k > 1 && a.split_k != e.split_k) {
         // the caller sized its reduction for e.split_k partials: zero the ones we will not write
         B200_CUDA_OK(cudaMemsetAsync(C + (int64_t)a.split_k * e.split_stride, 0,
@@ -667,7 +675,7 @@ int launch_tc_gemm(Ctx* c, int mode, const float* A, int64_t lda, int a_mn, cons
     else if (!a_mn && b_mn) INST(TC_EPI_STORE, false, true);
     else INST(TC_EPI_STORE, true, true);
 #undef INST
-    c->launches++;
+    note(c, __func__, s);
     return rc;
 }
 
@@ -695,7 +703,7 @@ int launch_splitk_reduce(Ctx* c, const float* parts, int n_split, int64_t split_
     if (n == 0) return 0;
     k_splitk_reduce<<<(int)cdiv(n, 256), 256, 0, s>>>(parts, n_split, split_stride, out, ld_out, M, N, ld_part, addend, ld_add,
                                                        addend_scale, mulY, ldy);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -198,7 +198,7 @@ int launch_topk_metrics(Ctx* c, const float* scores, int I, const BatchView& gt,
                  "topk: k must be in [1, min(%d, n_items)] (got %d)", TOPK_MAX, kmax);
     B200_REQUIRE(n_metrics <= TOPK_THREADS, B200VAE_EINVAL, "topk: too many metrics");
     k_topk_metrics<<<gt.B, TOPK_THREADS, 0, s>>>(scores, I, gt, kinds, ks, n_metrics, kmax, out, topk_idx);
-    c->launches++;
+    note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -326,6 +326,16 @@ class Engine:
     def set_timing(self, on):
         check(_lib.lib().b200vae_set_timing(self._ctx, 1 if on else 0))
 
+    def timing_report(self):
+        """[(launcher, ms)] for every launch of the most recent instrumented step."""
+        buf = ctypes.create_string_buffer(1 << 15)
+        _lib.lib().b200vae_timing_report(self._ctx, buf, len(buf))
+        out = []
+        for line in buf.value.decode().splitlines():
+            name, ms = line.rsplit(" ", 1)
+            out.append((name, float(ms)))
+        return out
+
     def kernel_ms(self, which):
         return float(_lib.lib().b200vae_kernel_ms(self._ctx, which))
 
