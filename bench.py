@@ -97,6 +97,37 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port on the host cores
 # ------------------------------------------------------------------------------------------------
+def pick_cpu_threads():
+    """All the host threads the reference can actually use: start from the affinity mask / cgroup quota and
+    keep the count that makes a [500 x 600] x [600 x 50000] sgemm (the reference's dominant op) fastest --
+    on shared hosts os.cpu_count() oversubscribes the container's CPU quota and is several times slower."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            avail = max(1, min(avail, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    cands = sorted({max(1, avail), max(1, avail // 2), max(1, avail // 4), min(avail, 32), min(avail, 16), min(avail, 8)})
+    a = torch.randn(500, 600)
+    b = torch.randn(600, 50000)
+    best, best_t = cands[-1], float("inf")
+    for n in cands:
+        torch.set_num_threads(n)
+        torch.mm(a, b)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            torch.mm(a, b)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = n, dt
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_reference_run(steps, warmup, budget_s, batch=None, n_rows=None):
     """Times oracle.train_step (dense [B x I] tensors, explicit backward + Adam, torch CPU ops with all
     host threads) including the sampler's CSR->dense expansion and the RNG draws, like the reference's
@@ -104,8 +135,7 @@ def cpu_reference_run(steps, warmup, budget_s, batch=None, n_rows=None):
     from oracle import multvae_oracle as O
     from rectorch_b200 import synth
     from rectorch_b200.nets import MultiVAE_net
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = pick_cpu_threads()
     B = batch or CFG["batch"]
     total = steps + warmup
     n_rows = n_rows or B * total

@@ -169,17 +169,38 @@ k_simt_gemm(const float* __restrict__ A, int64_t a_rs, int64_t a_cs, const float
 // LDS.128 per 4 K-steps.  Measured on B200: the scalar kernel was bound by LDGSTS/LDS issue
 // (~28 us for 500x400x600), not by FMAs.
 // ------------------------------------------------------------------------------------------
+//
+// Intra-CTA split-K: the hidden layers give only ~400 warps of 4x4 micro-tiles for 148 SMs (one
+// warp per scheduler -> every LDS->FFMA dependency is exposed; ncu: 23 % issue-active, stalled on
+// the short scoreboard).  KSPLIT groups of 4 warps each run the pipeline on a quarter of K for the
+// SAME output tile with their own operand ring and named barrier, then reduce through shared
+// memory in a fixed order (deterministic), giving every scheduler 4 warps to switch between.
+constexpr int V_KSPLIT = 4;
 template <bool A_KFAST, bool B_KFAST>
-__global__ void __launch_bounds__(128)
+struct VSmem {
+    float As[3][A_KFAST ? 32 : BK][(A_KFAST ? BK : 32) + 4];
+    float Bs[3][B_KFAST ? 64 : BK][(B_KFAST ? BK : 64) + 4];
+};
+
+template <bool A_KFAST, bool B_KFAST>
+__global__ void __launch_bounds__(128 * V_KSPLIT)
 k_simt_gemm_v(const float* __restrict__ A, int64_t a_ld, const float* __restrict__ B, int64_t b_ld,
               float* __restrict__ C, int64_t ldc, int M, int N, int K, GemmEpi e) {
     constexpr int VBM = 32, VBN = 64, NST = 3;
     // A: [m][k] if K is contiguous (a_ld = row pitch of m) else [k][m] (a_ld = row pitch of k); same for B with n
-    __shared__ __align__(16) float As[NST][A_KFAST ? VBM : BK][(A_KFAST ? BK : VBM) + 4];
-    __shared__ __align__(16) float Bs[NST][B_KFAST ? VBN : BK][(B_KFAST ? BK : VBN) + 4];
-    const int tid = threadIdx.x;
+    extern __shared__ __align__(16) uint8_t vsmem_raw[];
+    const int grp = threadIdx.x >> 7;                 // K-split group
+    VSmem<A_KFAST, B_KFAST>& sm = reinterpret_cast<VSmem<A_KFAST, B_KFAST>*>(vsmem_raw)[grp];
+    auto& As = sm.As;
+    auto& Bs = sm.Bs;
+    const int tid = threadIdx.x & 127;
     const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * VBM, n0 = blockIdx.x * VBN;
+    // this group's K range, in whole K blocks
+    const int nkb_all = (K + BK - 1) / BK;
+    const int kb_per = (nkb_all + V_KSPLIT - 1) / V_KSPLIT;
+    const int kb_lo = min(nkb_all, grp * kb_per), kb_hi = min(nkb_all, kb_lo + kb_per);
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); };
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -222,16 +243,16 @@ k_simt_gemm_v(const float* __restrict__ A, int64_t a_ld, const float* __restrict
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    const int nkb = (K + BK - 1) / BK;
+    const int nkb = kb_hi - kb_lo;
 #pragma unroll
     for (int p = 0; p < NST - 1; ++p) {
-        if (p < nkb) issue(p * BK, p);
+        if (p < nkb) issue((kb_lo + p) * BK, p);
         else asm volatile("cp.async.commit_group;" ::: "memory");
     }
     for (int kb = 0; kb < nkb; ++kb) {
         asm volatile("cp.async.wait_group %0;" ::"n"(NST - 2) : "memory");
-        __syncthreads();
-        if (kb + NST - 1 < nkb) issue((kb + NST - 1) * BK, (kb + NST - 1) % NST);
+        group_sync();
+        if (kb + NST - 1 < nkb) issue((kb_lo + kb + NST - 1) * BK, (kb + NST - 1) % NST);
         else asm volatile("cp.async.commit_group;" ::: "memory");
         const int st = kb % NST;
 #pragma unroll
@@ -253,7 +274,9 @@ k_simt_gemm_v(const float* __restrict__ A, int64_t a_ld, const float* __restrict
             if (B_KFAST) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float4 t = *reinterpret_cast<const float4*>(&Bs[st][tx * 4 + j][kk0]);
+                    // columns tx, tx+16, tx+32, tx+48: consecutive lanes read consecutive rows (80 B apart),
+                    // which is bank-conflict free; 4 consecutive columns per lane would be a 4-way conflict
+                    const float4 t = *reinterpret_cast<const float4*>(&Bs[st][tx + 16 * j][kk0]);
                     b[j][0] = t.x; b[j][1] = t.y; b[j][2] = t.z; b[j][3] = t.w;
                 }
             } else {
@@ -271,13 +294,34 @@ k_simt_gemm_v(const float* __restrict__ A, int64_t a_ld, const float* __restrict
                     for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i][q], b[j][q], acc[i][j]);
         }
     }
+    // fixed-order reduction of the K-split partial tiles: groups 1..3 park their accumulators in their
+    // own (now idle) operand ring, group 0 adds them in group order and runs the epilogue
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    float* red = reinterpret_cast<float*>(&sm);        // >= 32*64 floats per group
+    if (grp > 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<float4*>(red + ((ty * 4 + i) * 16 + tx) * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    }
+    __syncthreads();
+    if (grp > 0) return;
+#pragma unroll
+    for (int g = 1; g < V_KSPLIT; ++g) {
+        const float* rg = reinterpret_cast<const float*>(&reinterpret_cast<VSmem<A_KFAST, B_KFAST>*>(vsmem_raw)[g]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 t = *reinterpret_cast<const float4*>(rg + ((ty * 4 + i) * 16 + tx) * 4);
+            acc[i][0] += t.x; acc[i][1] += t.y; acc[i][2] += t.z; acc[i][3] += t.w;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int gm = m0 + ty * 4 + i;
         if (gm >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int gn = n0 + tx * 4 + j;
+            const int gn = n0 + (B_KFAST ? tx + 16 * j : tx * 4 + j);
             if (gn >= N) continue;
             float y = e.alpha * acc[i][j];
             if (e.bias) y += e.bias[gn];
@@ -290,6 +334,19 @@ k_simt_gemm_v(const float* __restrict__ A, int64_t a_ld, const float* __restrict
             C[(int64_t)gm * ldc + gn] = y;
         }
     }
+}
+
+template <bool A_KFAST, bool B_KFAST>
+static int launch_v(dim3 grid, const float* A, int64_t a_ld, const float* B, int64_t b_ld, float* C, int64_t ldc, int M,
+                    int N, int K, const GemmEpi& e, cudaStream_t s) {
+    constexpr int smem = (int)sizeof(VSmem<A_KFAST, B_KFAST>) * V_KSPLIT;
+    static bool attr = false;
+    if (!attr) {
+        B200_CUDA_OK(cudaFuncSetAttribute(k_simt_gemm_v<A_KFAST, B_KFAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    k_simt_gemm_v<A_KFAST, B_KFAST><<<grid, 128 * V_KSPLIT, smem, s>>>(A, a_ld, B, b_ld, C, ldc, M, N, K, e);
+    return 0;
 }
 
 int launch_simt_gemm(Ctx* c, int mode, const float* A, int64_t a_rs, int64_t a_cs, const float* B,
@@ -313,10 +370,10 @@ int launch_simt_gemm(Ctx* c, int mode, const float* A, int64_t a_rs, int64_t a_c
                         ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(B) & 15) == 0);
         if (ok) {
             dim3 gv((unsigned)cdiv(N, 64), (unsigned)cdiv(M, 32));
-            if (a_k && b_k)       k_simt_gemm_v<true, true><<<gv, 128, 0, s>>>(A, a_ld, B, b_ld, C, ldc, M, N, K, e);
-            else if (a_k && !b_k) k_simt_gemm_v<true, false><<<gv, 128, 0, s>>>(A, a_ld, B, b_ld, C, ldc, M, N, K, e);
-            else if (!a_k && b_k) k_simt_gemm_v<false, true><<<gv, 128, 0, s>>>(A, a_ld, B, b_ld, C, ldc, M, N, K, e);
-            else                  k_simt_gemm_v<false, false><<<gv, 128, 0, s>>>(A, a_ld, B, b_ld, C, ldc, M, N, K, e);
+            if (a_k && b_k)       B200_CHECK((launch_v<true, true>(gv, A, a_ld, B, b_ld, C, ldc, M, N, K, e, s)));
+            else if (a_k && !b_k) B200_CHECK((launch_v<true, false>(gv, A, a_ld, B, b_ld, C, ldc, M, N, K, e, s)));
+            else if (!a_k && b_k) B200_CHECK((launch_v<false, true>(gv, A, a_ld, B, b_ld, C, ldc, M, N, K, e, s)));
+            else                  B200_CHECK((launch_v<false, false>(gv, A, a_ld, B, b_ld, C, ldc, M, N, K, e, s)));
             note(c, __func__, s);
             B200_CUDA_OK(cudaGetLastError());
             return 0;
