@@ -121,6 +121,12 @@ int  b200vae_forward_backward(b200vae_ctx* ctx, const int32_t* row_ids, int32_t 
                               const uint8_t* keep_tape, const float* eps_tape,
                               float* loss_out, void* stream);
 
+/* Make `stream` wait until the most recent b200vae_forward_backward has finished writing the
+ * gradients of the decoder output layer (the arena range starting at that layer's w_off, i.e. the
+ * tail of the gradient arena).  Data-parallel callers start the all-reduce of that half (~50 % of the
+ * bytes) on a side stream while the encoder half of the backward pass is still running. */
+int  b200vae_wait_wd_ready(b200vae_ctx* ctx, void* stream);
+
 /* K8: fused Adam over the whole arena (torch.optim.Adam.step as configured at
  * models.py:657-659 / 768-770), with the MultiDAE extras folded into the gradient read:
  * g += lam * w/||w||_2 (per tensor) + weight_decay * w.  `step` is the 1-based count. */

@@ -78,6 +78,7 @@ struct Ctx {
 
     bool use_tc = true;
     bool tc_dec = false;              // decoder-last shapes are tcgen05-eligible
+    cudaEvent_t ev_wd = nullptr;      // recorded when dW_d / db_d (tail of the gradient arena) are final
 };
 
 // bookkeeping after every kernel launch: launch counter + (timing mode) an event named after the launcher

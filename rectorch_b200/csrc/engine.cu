@@ -49,6 +49,7 @@ static void free_ctx(Ctx* c) {
     for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventDestroy(c->ev[i][j]);
     for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
+    if (c->ev_wd) cudaEventDestroy(c->ev_wd);
     delete c;
 }
 
@@ -284,6 +285,9 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
     // sparse part of dlogits = -t/Bg
     B200_CHECK(launch_spmm_scatter(c, st.tgt, nullptr, -inv_Bg, st.h_last, H, dWd, s));
     B200_CHECK(launch_bias_scatter(c, st.tgt, -inv_Bg, dbd, s));
+    // the decoder-output gradients (the tail of the gradient arena) are final from here on: a data-parallel
+    // caller can start reducing them while the rest of the backward pass runs (b200vae_wait_wd_ready)
+    B200_CUDA_OK(cudaEventRecord(c->ev_wd, s));
 
     // ---------------- backward: hidden decoder layers ----------------
     // invariant: `cur` holds d(loss)/d(pre-activation of the layer below the one being processed)
@@ -411,6 +415,7 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     c->use_tc = cfg->use_tensor_cores != 0;
     for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventCreate(&c->ev[i][j]);
+    cudaEventCreateWithFlags(&c->ev_wd, cudaEventDisableTiming);
     if (cfg->dec_dims[cfg->n_dec] != c->n_items || cfg->enc_dims[cfg->n_enc] != c->latent) {
         set_error("enc_dims/dec_dims are inconsistent (n_items %d vs %d, latent %d vs %d)", c->n_items,
                   cfg->dec_dims[cfg->n_dec], cfg->enc_dims[cfg->n_enc], c->latent);
@@ -787,6 +792,13 @@ int b200vae_timing_report(b200vae_ctx* ctx, char* buf, int cap) {
         pos += n;
     }
     return c->tcount;
+}
+
+int b200vae_wait_wd_ready(b200vae_ctx* ctx, void* stream) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    B200_REQUIRE(c, B200VAE_EINVAL, "null context");
+    B200_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_wd, 0));
+    return 0;
 }
 
 int b200vae_check_error_flag(b200vae_ctx* ctx) {

@@ -14,6 +14,7 @@ initialised (one process per GPU) users are sharded row-wise by the sampler, gra
 summed with ONE ``all_reduce`` of the flat gradient arena per step, and every rank applies
 the identical Adam update.
 """
+import ctypes
 import logging
 import os
 import time
@@ -117,6 +118,7 @@ class AETrainer(TorchNNTrainer):
         self.device = self._engine.device
         self._make_optimizer(learning_rate)
         self._loss_hist = torch.zeros(4 * 4096, dtype=torch.float32, device=self.device)
+        self._comm_stream = torch.cuda.Stream(device=self.device)
 
     # ---- optimizer <-> arena coupling --------------------------------------------------------------
     def _make_optimizer(self, lr):
@@ -192,8 +194,19 @@ class AETrainer(TorchNNTrainer):
         else:
             # row-sharded data parallelism: local gradients are already scaled by 1/B_global
             eng.forward_backward(B_global=B_local * world, step=eng.adam_steps + 1, row_offset=row_offset, **kw)
-            dist.all_reduce(eng.g, op=dist.ReduceOp.SUM)
-            dist.all_reduce(loss_slot, op=dist.ReduceOp.SUM)
+            # ONE logical all-reduce of the gradient arena, issued as two NCCL calls so that the half that is
+            # final first (decoder output layer, the arena's tail) travels over NVLink while the encoder half
+            # of the backward pass is still computing
+            cut = eng.w_off[-1]
+            side = self._comm_stream
+            check(_lib.lib().b200vae_wait_wd_ready(eng._ctx, ctypes.c_void_p(side.cuda_stream)))
+            with torch.cuda.stream(side):
+                w_tail = dist.all_reduce(eng.g[cut:], op=dist.ReduceOp.SUM, async_op=True)
+            w_head = dist.all_reduce(eng.g[:cut], op=dist.ReduceOp.SUM, async_op=True)
+            w_loss = dist.all_reduce(loss_slot, op=dist.ReduceOp.SUM, async_op=True)
+            w_tail.wait()
+            w_head.wait()
+            w_loss.wait()
             eng.adam(lr, betas, eps, wd, lam)
         self._step_tensor += 1.0
 
