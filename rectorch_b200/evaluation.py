@@ -61,9 +61,7 @@ def _evaluate_device(model, test_loader, metric_list):
     if not specs:
         return {}
     eng = model.network.engine
-    tr, te = test_loader.device_csr(eng.device)
-    eng.bind_csr(0, tr)
-    eng.bind_csr(1, te)
+    model._bind_sampler(test_loader)        # CSR slots 0 (input) / 1 (held-out) now point at this sampler
     model.network.eval()
     parts = []
     for rb in test_loader.iter_rows(eng.device):

@@ -21,6 +21,7 @@ if [ "$1" == "tc" ] || [ -z "$1" ]; then
 fi
 if [ "$1" == "rest" ] || [ -z "$1" ]; then
   run kernels 400 tests/test_gpu_kernels.py -k "not tc_gemm and not truncates and not lse"
+  run api 600 tests/test_gpu_api.py tests/test_gpu_multi.py
   run parity_fixture 600 tests/test_gpu_parity.py -k "fixture"
   run parity_oracle 900 tests/test_gpu_parity.py -k "not fixture"
   timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1

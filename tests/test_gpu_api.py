@@ -1,0 +1,194 @@
+"""GPU: the reference's own API-conformance tests for the hot path, ported 1:1 to the drop-in
+classes (rectorch/tests/test_nets.py:33-75, test_models.py:159-283, test_evaluation.py:32-64) with
+the network moved to the GPU.  Tiny 2-item nets exercise the generic (unaligned) kernels."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+from scipy.sparse import csr_matrix
+
+from rectorch_b200.evaluation import ValidFunc, evaluate
+from rectorch_b200.models import MultiDAE, MultiVAE, RecSysModel
+from rectorch_b200.nets import MultiDAE_net, MultiVAE_net
+from rectorch_b200.samplers import DataSampler, Sampler
+
+pytestmark = pytest.mark.gpu
+
+
+def test_MultiDAE_net():
+    net = MultiDAE_net([1, 2], [2, 1], .1).cuda()
+    x = torch.FloatTensor([[1, 1], [2, 2]])
+    y = net(x)
+    assert isinstance(net.dropout, torch.nn.Dropout) and net.dropout.p == .1
+    assert y.dtype == torch.float32 and y.shape == x.shape
+    net.eval()
+    y1, y2 = net(x), net(x.cuda())
+    assert torch.equal(y1, y2)                       # eval mode is deterministic
+    z = net.encode(x)
+    assert z.shape == (2, 1)
+    assert torch.allclose(net.decode(z), y1, atol=1e-6)
+
+
+def test_MultiVAE_net():
+    net = MultiVAE_net([1, 2], [2, 1], .1).cuda()
+    x = torch.FloatTensor([[1, 1], [2, 2]])
+    torch.manual_seed(98765)
+    mu, logvar = net.encode(x)
+    torch.manual_seed(98765)
+    y, mu2, logvar2 = net(x)
+    assert isinstance(net.dropout, torch.nn.Dropout) and net.dropout.p == .1
+    for t in (y, mu, logvar, mu2, logvar2):
+        assert t.dtype == torch.float32
+    assert mu.equal(mu2) and logvar.equal(logvar2)    # same seed -> same dropout draw
+    assert y.shape == x.shape
+    net.eval()
+    y_eval, mu_e, _ = net(x)
+    assert torch.allclose(net.decode(mu_e), y_eval, atol=1e-6)      # eval: z = mu
+    assert torch.equal(net._reparameterize(mu_e, mu_e), mu_e)
+
+
+def _common_trainer_checks(model, net, lam=None):
+    for a in ("network", "device", "learning_rate", "optimizer"):
+        assert hasattr(model, a)
+    assert model.learning_rate == 1e-3 and model.network == net
+    assert model.device.type == "cuda"
+    assert isinstance(model.optimizer, torch.optim.Adam)
+    assert str(model) == repr(model)
+    if lam is not None:
+        assert model.lam == lam
+
+
+def test_MultiDAE():
+    net = MultiDAE_net([1, 2], [2, 1], dropout=.1).cuda()
+    model = MultiDAE(net)
+    _common_trainer_checks(model, net, .2)
+    gt = torch.FloatTensor([[1, 1], [2, 1]])
+    pred = torch.FloatTensor([[1, 1], [1, 1]])
+    assert model.loss_function(pred, gt) != torch.FloatTensor([.0]).cuda()
+    train = csr_matrix((np.array([1., 1., 1.]), (np.array([0, 0, 1]), np.array([0, 1, 1]))))
+    sampler = DataSampler(train, batch_size=1, shuffle=False)
+    x = torch.FloatTensor([[1, 1], [2, 2]])
+    model.predict(x, True)
+    out_1 = model.predict(x, False)[0]
+    model.train(sampler, num_epochs=10, verbose=4)
+    out_2 = model.predict(x, False)[0]
+    assert not torch.all(out_1.eq(out_2)), "the outputs should be different"
+    tmp = tempfile.NamedTemporaryFile()
+    model.save_model(tmp.name, 1)
+    model2 = MultiDAE(MultiDAE_net([1, 2], [2, 1], dropout=.1).cuda())
+    chk = model2.load_model(tmp.name)
+    assert chk["epoch"] == 1 and set(chk) == {"epoch", "state_dict", "optimizer"}
+    assert torch.all(model.predict(x, False)[0].eq(model2.predict(x, False)[0])), "the outputs should be the same"
+    # the loaded optimizer state is live: one more identical step keeps the two models identical
+    torch.manual_seed(5)
+    l1 = model.train_batch(x)
+    torch.manual_seed(5)
+    l2 = model2.train_batch(x)
+    assert abs(l1 - l2) < 1e-6 * abs(l1)
+    assert torch.allclose(model.predict(x, False)[0], model2.predict(x, False)[0], atol=1e-7)
+
+
+def test_MultiVAE():
+    net = MultiVAE_net([1, 2], [2, 1], .1).cuda()
+    model = MultiVAE(net)
+    _common_trainer_checks(model, net)
+    gt = torch.FloatTensor([[1, 1], [2, 1]])
+    pred = torch.FloatTensor([[1, 1], [1, 1]])
+    mu, logvar = model.network.encode(gt)
+    assert model.loss_function(torch.sigmoid(pred), gt, mu, logvar) != torch.FloatTensor([.0]).cuda()
+    # analytic value of the loss kernels: mean(2 ln2, 3 ln2) = 1.7328680
+    zero = torch.zeros(2, 1)
+    assert abs(float(model.loss_function(pred, gt, zero, zero)) - 1.7328680) < 1e-6
+    train = csr_matrix((np.array([1., 1., 1.]), (np.array([0, 0, 1]), np.array([0, 1, 1]))))
+    sampler = DataSampler(train, batch_size=1, shuffle=False)
+    x = torch.FloatTensor([[1, 1], [2, 2]])
+    model.predict(x, True)
+    out_1 = model.predict(x, False)[0]
+    model.train(sampler, num_epochs=10, verbose=4)
+    out_2 = model.predict(x, False)[0]
+    assert not torch.all(out_1.eq(out_2)), "the outputs should be different"
+    assert model.gradient_updates == 20.
+    tmp = tempfile.NamedTemporaryFile()
+    model.save_model(tmp.name, 1)
+    model2 = MultiVAE(MultiVAE_net([1, 2], [2, 1], .1).cuda())
+    model2.load_model(tmp.name)
+    assert torch.all(model.predict(x, False)[0].eq(model2.predict(x, False)[0])), "the outputs should be the same"
+    assert model2.gradient_updates == 20.
+    # validation + best-checkpoint policy (models.py:879-892)
+    sampler = DataSampler(train, train, batch_size=1, shuffle=False)
+    tmp2 = tempfile.NamedTemporaryFile()
+    model = MultiVAE(MultiVAE_net([1, 2], [2, 1], .1).cuda(), 1., 5)
+    model.train(sampler, valid_data=sampler, valid_metric="ndcg@1", num_epochs=10, best_path=tmp2.name)
+    model2 = MultiVAE(MultiVAE_net([1, 2], [2, 1], .1).cuda(), 1., 5)
+    assert model2.gradient_updates == 0
+    model2.load_model(tmp2.name)
+    assert model2.gradient_updates > 0
+    with pytest.raises(AssertionError):
+        model.train(sampler, valid_data=sampler, valid_metric=None, num_epochs=1)
+
+
+def test_checkpoint_is_reference_shaped():
+    """state_dict keys / shapes and the optimizer state layout are what stock rectorch saves
+    (models.py:485-488, 898-902): nn.Linear (out, in) weights, torch Adam state with step/exp_avg/exp_avg_sq."""
+    net = MultiVAE_net([3, 5, 7]).cuda()
+    model = MultiVAE(net)
+    model.train_batch(torch.ones(2, 7))
+    sd = net.state_dict()
+    assert list(sd) == ["enc_layers.0.weight", "enc_layers.0.bias", "enc_layers.1.weight", "enc_layers.1.bias",
+                        "dec_layers.0.weight", "dec_layers.0.bias", "dec_layers.1.weight", "dec_layers.1.bias"]
+    assert sd["enc_layers.0.weight"].shape == (5, 7) and sd["enc_layers.1.weight"].shape == (6, 5)
+    assert sd["dec_layers.1.weight"].shape == (7, 5)
+    osd = model.optimizer.state_dict()
+    assert len(osd["state"]) == 8 and osd["param_groups"][0]["lr"] == 1e-3
+    st0 = osd["state"][0]
+    assert set(st0) == {"step", "exp_avg", "exp_avg_sq"} and float(st0["step"]) == 1.0
+    assert st0["exp_avg"].shape == (5, 7) and st0["exp_avg"].abs().sum() > 0
+    # a stock torch module can take the weights
+    ref = torch.nn.Linear(7, 5)
+    ref.load_state_dict({"weight": sd["enc_layers.0.weight"].cpu(), "bias": sd["enc_layers.0.bias"].cpu()})
+
+
+class _FakeModel(RecSysModel):
+    def predict(self, x, *args, **kwargs):
+        return (x + 1, )
+
+
+class _FakeSampler(Sampler):
+    def __len__(self):
+        return 1
+
+    def __iter__(self):
+        yield (torch.FloatTensor([[4, 3, 2, 1.], [1, 2, 3, 4.]]), torch.FloatTensor([[0, 0, 1., 1.], [0, 0, 1., 1.]]))
+
+
+def test_evaluate_generic_protocol():
+    """rectorch/tests/test_evaluation.py:32-64 with a non-engine model: generic predict -> Metrics path."""
+    res = evaluate(_FakeModel(), _FakeSampler(), ["ndcg@3", "recall@2"])
+    assert set(res) == {"ndcg@3", "recall@2"}
+    assert abs(res["ndcg@3"][0] - 0.3065735964) < 1e-5 and abs(res["ndcg@3"][1] - 1.0) < 1e-6
+    assert res["recall@2"][0] == 0 and res["recall@2"][1] == 1
+    vf = ValidFunc(evaluate)
+    assert str(vf) == repr(vf) and "evaluate" in str(vf)
+    out = vf(_FakeModel(), _FakeSampler(), "recall@2")
+    assert out.shape == (2,)
+    with pytest.raises(AssertionError):
+        ValidFunc(lambda a, b: None)
+
+
+def test_train_epoch_on_sampler_matches_batch_loop():
+    """The fast epoch loop (row batches, losses read back per log window) visits the same batches and
+    produces the same weights as calling train_batch on the dense batches the sampler yields."""
+    from rectorch_b200 import synth
+    csr = synth.make_matrix(300, 2048, seed=9, mu=3.0, sigma=0.5, min_len=3, max_len=200)
+    def make():
+        torch.manual_seed(1)
+        return MultiDAE(MultiDAE_net([64, 2048], None, 0.0).cuda())     # p = 0: no RNG in the step
+    m1, m2 = make(), make()
+    s = DataSampler(csr, batch_size=64, shuffle=False)
+    loss_epoch = m1.train_epoch(1, s, verbose=1)
+    losses = [m2.train_batch(tr, te) for tr, te in s]
+    assert abs(loss_epoch - float(np.mean(losses))) < 1e-5 * abs(loss_epoch)
+    for a, b in zip(m1.network.state_dict().values(), m2.network.state_dict().values()):
+        assert torch.allclose(a, b, atol=1e-6)
