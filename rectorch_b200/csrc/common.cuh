@@ -51,7 +51,7 @@ struct BatchView {
     int32_t        B;
 };
 
-constexpr int SPMM_SEG = 64;   // non-zeros per sparse gather/scatter work unit
+constexpr int SPMM_SEG = 32;   // non-zeros per sparse gather/scatter work unit
 
 struct Layer {
     int in, out;              // nn.Linear(in, out)
@@ -83,8 +83,9 @@ struct Ctx;   // engine.cu
 int launch_batch_scan(Ctx* c, const int64_t* indptr, const int32_t* row_ids, int B, int64_t cap,
                       int64_t* bp, int32_t* sp, cudaStream_t s);
 int launch_batch_prep(Ctx* c, const BatchView& in, float p, uint64_t seed, uint64_t step,
-                      int64_t row_offset, const uint8_t* keep_tape, bool train, float* xt,
+                      int64_t row_offset, const uint8_t* keep_tape, bool train, float* xt, float* row_sum_out,
                       cudaStream_t s);
+int launch_spmm_zero(Ctx* c, const BatchView& v, const float* vals, int H, float* dWt, cudaStream_t s);
 int launch_row_sums(Ctx* c, const BatchView& v, float* out, cudaStream_t s);
 int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const float* Wt, int H,
                        const float* bias, int act, float* out, cudaStream_t s);
@@ -98,8 +99,8 @@ int launch_scan_i64(Ctx* c, const int64_t* lens, int n, int64_t cap, int64_t* ou
 int launch_expand(Ctx* c, const BatchView& v, int I, float* out, cudaStream_t s);
 int launch_mask_seen(Ctx* c, const BatchView& v, int I, float* scores, cudaStream_t s);
 int launch_row_loss(Ctx* c, const BatchView& tgt, const float* h, const float* gvec, int H,
-                    const float* bias, const float* lse, const float* T, float* loss_row,
-                    cudaStream_t s);
+                    const float* bias, const float* pmax, const float* psum, int n_tiles, float* lse,
+                    const float* T, float inv_Bg, float* loss_row, float* rowscale, cudaStream_t s);
 
 // simt_gemm.cu
 int launch_simt_gemm(Ctx* c, int mode, const float* A, int64_t a_rs, int64_t a_cs, const float* B,

@@ -39,7 +39,7 @@ static void free_ctx(Ctx* c) {
     for (int s = 0; s < 2; ++s) {
         F(c->slot[s].int_indptr); F(c->slot[s].int_indices); F(c->slot[s].int_values); F(c->slot[s].bp); F(c->slot[s].sp);
     }
-    F(c->xt); F(c->T); F(c->loss_row); F(c->kl_row); F(c->lse);
+    F(c->xt); F(c->T); F(c->loss_row); F(c->kl_row); F(c->lse); F(c->rowscale);
     for (float* p : c->act_enc) F(p);
     for (float* p : c->act_dec) F(p);
     F(c->z); F(c->eps); F(c->gvec); F(c->P); F(c->hT); F(c->dbuf[0]); F(c->dbuf[1]);
@@ -107,8 +107,8 @@ struct FwdState {
 // encoder + reparameterisation + hidden decoder layers.  Leaves z and h_last in the ctx.
 static int forward_hidden(Ctx* c, FwdState* st, int B, bool train, float p, uint64_t seed, uint64_t step,
                           int64_t row_offset, const uint8_t* keep_tape, const float* eps_tape,
-                          cudaStream_t s) {
-    B200_CHECK(launch_batch_prep(c, st->in, p, seed, step, row_offset, keep_tape, train, c->xt, s));
+                          float* row_sum_out, cudaStream_t s) {
+    B200_CHECK(launch_batch_prep(c, st->in, p, seed, step, row_offset, keep_tape, train, c->xt, row_sum_out, s));
     const Layer& e0 = c->enc[0];
     B200_CHECK(launch_spmm_gather(c, st->in, c->xt, c->w + e0.w_off, e0.out, c->w + e0.b_off,
                                   e0.tanh_act ? 1 : 0, c->act_enc[0], s));
@@ -143,14 +143,21 @@ __global__ void k_scale_rows(const float* __restrict__ T, float a, int B, float*
     if (i < B) rs[i] = T[i] * a;
 }
 
-// h [B x H] -> hT [(H+8) x Bp]: rows 0..H-1 = h^T, row H = 1 (bias-gradient column), rest 0.
-__global__ void k_transpose_ones(const float* __restrict__ h, int B, int H, int Bp, float* __restrict__ hT) {
+// h [B x H] -> h_r [B x H] (tf32-rounded copy) and hT [(H+8) x Bp]: rows 0..H-1 = h_r^T, row H = 1
+// (bias-gradient column), rest 0.
+__global__ void k_transpose_ones(const float* __restrict__ h, int B, int H, int Bp, float* __restrict__ hT,
+                                 float* __restrict__ h_r) {
     __shared__ float tile[32][33];
     int b0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
     int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
     for (int i = ty; i < 32; i += 8) {
         int b = b0 + i, hh = h0 + tx;
-        tile[i][tx] = (b < B && hh < H) ? tf32_rn(h[(int64_t)b * H + hh]) : ((hh == H && b < B) ? 1.f : 0.f);
+        float val = (hh == H && b < B) ? 1.f : 0.f;
+        if (b < B && hh < H) {
+            val = tf32_rn(h[(int64_t)b * H + hh]);
+            h_r[(int64_t)b * H + hh] = val;
+        }
+        tile[i][tx] = val;
     }
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
@@ -159,27 +166,36 @@ __global__ void k_transpose_ones(const float* __restrict__ h, int B, int H, int 
     }
 }
 
-static int dec_lse(Ctx* c, const float* h, int B, int H, float* lse, cudaStream_t s) {
+// fused decoder GEMM + per-tile (max, sum exp) partials; the merge happens in row_loss.  With
+// `for_backward` the tf32 operand prep also emits the transposed hT the dW_d GEMM needs.
+static int dec_lse(Ctx* c, const float* h, int B, int H, int* n_tiles, bool for_backward, cudaStream_t s) {
     const Layer& L = c->dec.back();
     const float* W = c->w + L.w_off;
     const float* b = c->w + L.b_off;
     int I = c->n_items;
     if (c->tc_dec) {
-        // tensor-core operands: tf32-rounded copies (h_r made here, W_d shadow kept by Adam)
-        B200_CHECK(launch_round_tf32(c, h, c->h_r, (int64_t)B * H, s));
+        // tensor-core operands: tf32-rounded copies (h_r / hT made here, W_d shadow kept by Adam)
+        if (for_backward) {
+            const int Bp = (int)round_up(B, 4);
+            dim3 tg((unsigned)cdiv(Bp, 32), (unsigned)cdiv(H + 8, 32));
+            k_transpose_ones<<<tg, dim3(32, 8), 0, s>>>(h, B, H, Bp, c->hT, c->h_r);
+            note(c, "prep_h_tf32", s);
+        } else {
+            B200_CHECK(launch_round_tf32(c, h, c->h_r, (int64_t)B * H, s));
+        }
         TcEpi e;
         e.bias = b;
         e.part_max = c->part_max;
         e.part_sum = c->part_sum;
         B200_CHECK(launch_tc_gemm(c, TC_EPI_LSE, c->h_r, H, 0, c->wd_shadow, H, 0, nullptr, 0, B, I, H, e, s));
-        B200_CHECK(launch_lse_merge(c, c->part_max, c->part_sum, tc_lse_tiles(I), B, lse, s));
+        *n_tiles = tc_lse_tiles(I);
     } else {
         GemmEpi e;
         e.bias = b;
         e.part_max = c->part_max;
         e.part_sum = c->part_sum;
         B200_CHECK(launch_simt_gemm(c, EPI_LSE, h, H, 1, W, 1, H, nullptr, 0, B, I, H, e, s));
-        B200_CHECK(launch_lse_merge(c, c->part_max, c->part_sum, (int)cdiv(I, 64), B, lse, s));
+        *n_tiles = (int)cdiv(I, 64);
     }
     return 0;
 }
@@ -202,16 +218,19 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         st.tgt = st.in;
     }
     // ---------------- forward ----------------
-    B200_CHECK(launch_row_sums(c, st.tgt, c->T, s));
-    B200_CHECK(forward_hidden(c, &st, B, true, p, seed, step, row_offset, keep_tape, eps_tape, s));
+    if (use_target) B200_CHECK(launch_row_sums(c, st.tgt, c->T, s));
+    B200_CHECK(forward_hidden(c, &st, B, true, p, seed, step, row_offset, keep_tape, eps_tape,
+                              use_target ? nullptr : c->T, s));
     const Layer& DL = c->dec.back();
     const int H = st.H;
     const float* Wd = c->w + DL.w_off;
+    int n_lse_tiles = 0;
     tick(c, 0, 0, s);
-    B200_CHECK(dec_lse(c, st.h_last, B, H, c->lse, s));
+    B200_CHECK(dec_lse(c, st.h_last, B, H, &n_lse_tiles, true, s));
     tick(c, 0, 1, s);
     B200_CHECK(launch_spmm_gather(c, st.tgt, nullptr, Wd, H, nullptr, 0, c->gvec, s));
-    B200_CHECK(launch_row_loss(c, st.tgt, st.h_last, c->gvec, H, c->w + DL.b_off, c->lse, c->T, c->loss_row, s));
+    B200_CHECK(launch_row_loss(c, st.tgt, st.h_last, c->gvec, H, c->w + DL.b_off, c->part_max, c->part_sum, n_lse_tiles,
+                               c->lse, c->T, inv_Bg, c->loss_row, c->rowscale, s));
     const bool dae_reg = (!c->cfg.is_vae) && lam != 0.f;
     if (dae_reg)
         B200_CHECK(launch_tensor_norms(c, c->w, c->d_toff, c->d_tlen, c->n_tensors, c->norm_partial, c->norms, s));
@@ -220,9 +239,7 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
                                  dae_reg ? c->norms : nullptr, c->n_tensors, loss_out, s));
 
     // ---------------- backward: decoder output layer ----------------
-    float* rowscale = c->loss_row;   // loss_row is consumed; reuse as T/Bg
-    k_scale_rows<<<(int)cdiv(B, 256), 256, 0, s>>>(c->T, inv_Bg, B, rowscale);
-    note(c, __func__, s);
+    float* rowscale = c->rowscale;   // T_u / B_global, written by row_loss
     float* dWd = c->g + DL.w_off;
     float* dbd = c->g + DL.b_off;
     float* d0 = c->dbuf[0];
@@ -237,10 +254,7 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         tick(c, 2, 0, s);
         B200_CHECK(launch_tc_gemm(c, TC_EPI_PROB, c->h_r, H, 0, c->wd_shadow, H, 0, c->P, Bp, B, I, H, e, s));
         tick(c, 2, 1, s);
-        // dW_d | db_d = P^T [I x B] * [h | 1]  : A = P^T (K-major), B = hT [(H+8) x Bp] (K-major)
-        dim3 tg((unsigned)cdiv(Bp, 32), (unsigned)cdiv(H + 8, 32));
-        k_transpose_ones<<<tg, dim3(32, 8), 0, s>>>(st.h_last, B, H, Bp, c->hT);
-        note(c, __func__, s);
+        // dW_d | db_d = P^T [I x B] * [h | 1]  : A = P^T (K-major), B = hT [(H+8) x Bp] (K-major, from dec_lse)
         TcEpi e2;
         e2.bias_grad = dbd;
         e2.bias_col = H;
@@ -313,8 +327,13 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         std::swap(cur, nxt);
     }
     const Layer& e0 = c->enc[0];
-    B200_CUDA_OK(cudaMemsetAsync(c->g + e0.w_off, 0, (size_t)I * e0.out * sizeof(float), s));
-    if (c->timing) { note(c, "memset_dW1", s); c->launches--; }
+    if (!c->dw1_clean) {
+        B200_CUDA_OK(cudaMemsetAsync(c->g + e0.w_off, 0, (size_t)I * e0.out * sizeof(float), s));
+        if (c->timing) { note(c, "memset_dW1", s); c->launches--; }
+    }
+    c->dw1_clean = false;
+    c->last_in = st.in;
+    c->last_in_valid = true;
     B200_CHECK(launch_spmm_scatter(c, st.in, c->xt, 1.0f, cur, e0.out, c->g + e0.w_off, s));
     B200_CHECK(launch_colsum(c, cur, e0.out, B, e0.out, c->g + e0.b_off, s));
     return 0;
@@ -350,6 +369,17 @@ static int adam_step(Ctx* c, float lr, float beta1, float beta2, float eps, floa
     return 0;
 }
 
+// Single-process fused step only: Adam has consumed the gradients, so zeroing the encoder-0 rows this
+// batch touched restores the all-zero invariant and the next step skips its 4*I*H-byte memset.
+static int rezero_enc0_grad(Ctx* c, cudaStream_t s) {
+    if (!c->last_in_valid) return 0;
+    const Layer& e0 = c->enc[0];
+    B200_CHECK(launch_spmm_zero(c, c->last_in, c->xt, e0.out, c->g + e0.w_off, s));
+    c->dw1_clean = true;
+    c->last_in_valid = false;
+    return 0;
+}
+
 static int predict(Ctx* c, const int32_t* row_ids, int B, int remove_train, int train_mode, float p,
                    uint64_t seed, uint64_t step, float* scores, float* mu, float* logvar, cudaStream_t s) {
     B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
@@ -357,7 +387,7 @@ static int predict(Ctx* c, const int32_t* row_ids, int B, int remove_train, int 
     FwdState st;
     B200_CHECK(make_view(c, 0, row_ids, B, &st.in, s));
     st.tgt = st.in;
-    B200_CHECK(forward_hidden(c, &st, B, train_mode != 0, p, seed, step, 0, nullptr, nullptr, s));
+    B200_CHECK(forward_hidden(c, &st, B, train_mode != 0, p, seed, step, 0, nullptr, nullptr, nullptr, s));
     const int L = c->latent, I = c->n_items;
     if (c->cfg.is_vae) {
         const float* eo = c->act_enc.back();
@@ -459,7 +489,7 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
         A_(dmalloc(&c->slot[s].sp, Bm + 1));
     }
     A_(dmalloc(&c->xt, nnz));
-    A_(dmalloc(&c->T, Bm)); A_(dmalloc(&c->loss_row, Bm)); A_(dmalloc(&c->kl_row, Bm)); A_(dmalloc(&c->lse, Bm));
+    A_(dmalloc(&c->T, Bm)); A_(dmalloc(&c->loss_row, Bm)); A_(dmalloc(&c->kl_row, Bm)); A_(dmalloc(&c->lse, Bm)); A_(dmalloc(&c->rowscale, Bm));
     for (auto& L : c->enc) { float* p = nullptr; A_(dmalloc(&p, Bm * L.out)); c->act_enc.push_back(p); }
     for (size_t i = 0; i + 1 < c->dec.size(); ++i) { float* p = nullptr; A_(dmalloc(&p, Bm * c->dec[i].out)); c->act_dec.push_back(p); }
     A_(dmalloc(&c->z, Bm * c->latent)); A_(dmalloc(&c->eps, Bm * c->latent));
@@ -594,7 +624,8 @@ int b200vae_train_step(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int 
     B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, B200VAE_EINVAL, "dropout_p must be in [0,1)");
     B200_CHECK(forward_backward(c, row_ids, B, B, use_target, beta, lam, dropout_p, seed, (uint64_t)step, 0,
                                 keep_tape, eps_tape, loss_out, (cudaStream_t)stream));
-    return adam_step(c, lr, beta1, beta2, eps, weight_decay, lam, step, (cudaStream_t)stream);
+    B200_CHECK(adam_step(c, lr, beta1, beta2, eps, weight_decay, lam, step, (cudaStream_t)stream));
+    return rezero_enc0_grad(c, (cudaStream_t)stream);
 }
 
 // ---- context-free helpers used by rectorch_b200.metrics / models.loss_function ---------------
@@ -672,6 +703,7 @@ int b200vae_train_step_host(b200vae_ctx* ctx, const int64_t* indptr_host, const 
     S.int_has_values = values_host != nullptr;
     B200_CHECK(forward_backward(c, nullptr, B, B, 0, beta, lam, dropout_p, seed, (uint64_t)step, 0, nullptr, nullptr, c->loss_dev, s));
     B200_CHECK(adam_step(c, lr, 0.9f, 0.999f, 1e-8f, weight_decay, lam, step, s));
+    B200_CHECK(rezero_enc0_grad(c, s));
     B200_CUDA_OK(cudaMemcpyAsync(loss_host, c->loss_dev, 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
     return 0;

@@ -108,7 +108,7 @@ int launch_scan_i64(Ctx* c, const int64_t* lens, int n, int64_t cap, int64_t* ou
 // ------------------------------------------------------------------------------------------
 __global__ void k_batch_prep(BatchView v, float p, uint64_t seed, uint64_t step, int64_t row_offset,
                              const uint8_t* __restrict__ keep_tape, int train, int64_t cap,
-                             float* __restrict__ xt) {
+                             float* __restrict__ xt, float* __restrict__ row_sum_out) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= v.B) return;
@@ -116,12 +116,17 @@ __global__ void k_batch_prep(BatchView v, float p, uint64_t seed, uint64_t step,
     int64_t a = v.indptr[gr], b = v.indptr[gr + 1];
     int64_t o = v.bp[warp];
     if (o + (b - a) > cap) return;   // capacity overflow flagged by the scan
-    float ss = 0.f;
+    float ss = 0.f, sx = 0.f;
     for (int64_t k = a + lane; k < b; k += 32) {
         float x = v.values ? v.values[k] : 1.f;
         ss += x * x;
+        sx += x;
     }
     ss = warp_sum(ss);
+    if (row_sum_out) {               // T_u = sum_j x_uj when the input is also the target
+        sx = warp_sum(sx);
+        if (lane == 0) row_sum_out[warp] = sx;
+    }
     float denom = fmaxf(sqrtf(ss), 1e-12f);
     bool drop = train && p > 0.f;
     float inv_keep = 1.0f / (1.0f - p);
@@ -147,13 +152,13 @@ __global__ void k_batch_prep(BatchView v, float p, uint64_t seed, uint64_t step,
 }
 
 int launch_batch_prep(Ctx* c, const BatchView& in, float p, uint64_t seed, uint64_t step,
-                      int64_t row_offset, const uint8_t* keep_tape, bool train, float* xt,
+                      int64_t row_offset, const uint8_t* keep_tape, bool train, float* xt, float* row_sum_out,
                       cudaStream_t s) {
     if (in.B == 0) return 0;
     int threads = 256;
     int blocks = (int)cdiv((int64_t)in.B * 32, threads);
     k_batch_prep<<<blocks, threads, 0, s>>>(in, p, seed, step, row_offset, keep_tape, train ? 1 : 0,
-                                            c->cfg.max_batch_nnz, xt);
+                                            c->cfg.max_batch_nnz, xt, row_sum_out);
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -223,11 +228,11 @@ k_spmm_gather(BatchView v, const float* __restrict__ vals, const float* __restri
 #pragma unroll
         for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
         int k = k0;
-        for (; k + 4 <= k1; k += 4) {   // up to 4 independent row loads in flight per thread
-            float w[4][VEC];
-            float x[4];
+        for (; k + 8 <= k1; k += 8) {   // up to 8 independent row loads in flight per thread
+            float w[8][VEC];
+            float x[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 x[u] = xv ? xv[k + u] : (raw ? raw[k + u] : 1.f);
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) w[u][i] = 0.f;
@@ -242,7 +247,7 @@ k_spmm_gather(BatchView v, const float* __restrict__ vals, const float* __restri
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 8; ++u)
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) acc[i] = fmaf(x[u], w[u][i], acc[i]);
         }
@@ -354,6 +359,46 @@ int launch_spmm_scatter(Ctx* c, const BatchView& v, const float* vals, float sca
     } else {
         int threads = (int)std::min<int64_t>(256, round_up(H, 32));
         k_spmm_scatter<1><<<grid, threads, 0, s>>>(v, vals, scale, dY, H, dWt);
+    }
+    note(c, __func__, s);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Re-zero exactly the gradient rows a batch touched (after Adam consumed them): the dense encoder-0
+// gradient stays all-zero between steps without a 4*I*H-byte memset per step.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+k_spmm_zero(BatchView v, const float* __restrict__ vals, int H, float* __restrict__ dWt) {
+    if ((int)blockIdx.x >= v.sp[v.B]) return;
+    const int r = find_row(v.sp, v.B, blockIdx.x);
+    const int seg = blockIdx.x - v.sp[r];
+    const int64_t gr = v.row_ids ? (int64_t)v.row_ids[r] : (int64_t)r;
+    const int64_t a = v.indptr[gr];
+    const int len = (int)(v.indptr[gr + 1] - a);
+    const int k0 = seg * SPMM_SEG, k1 = min(len, k0 + SPMM_SEG);
+    const float* xv = vals ? vals + v.bp[r] : nullptr;
+    const int32_t* cols = v.indices + a;
+    for (int h0 = threadIdx.x * VEC; h0 < H; h0 += blockDim.x * VEC) {
+        for (int k = k0; k < k1; ++k) {
+            if (xv && xv[k] == 0.f) continue;
+            float* row = dWt + (int64_t)cols[k] * H + h0;
+            if (VEC == 4) *reinterpret_cast<float4*>(row) = make_float4(0.f, 0.f, 0.f, 0.f);
+            else *row = 0.f;
+        }
+    }
+}
+
+int launch_spmm_zero(Ctx* c, const BatchView& v, const float* vals, int H, float* dWt, cudaStream_t s) {
+    if (v.B == 0) return 0;
+    bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(dWt) & 15) == 0);
+    const int grid = spmm_grid(c, v);
+    if (vec) {
+        int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));
+        k_spmm_zero<4><<<grid, threads, 0, s>>>(v, vals, H, dWt);
+    } else {
+        int threads = (int)std::min<int64_t>(256, round_up(H, 32));
+        k_spmm_zero<1><<<grid, threads, 0, s>>>(v, vals, H, dWt);
     }
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
@@ -482,11 +527,31 @@ int launch_mask_seen(Ctx* c, const BatchView& v, int I, float* scores, cudaStrea
 // one warp per row
 // ------------------------------------------------------------------------------------------
 __global__ void k_row_loss(BatchView tgt, const float* __restrict__ h, const float* __restrict__ gvec,
-                           int H, const float* __restrict__ bias, const float* __restrict__ lse,
-                           const float* __restrict__ T, float* __restrict__ loss_row) {
+                           int H, const float* __restrict__ bias, const float* __restrict__ pmax,
+                           const float* __restrict__ psum, int n_tiles, float* __restrict__ lse,
+                           const float* __restrict__ T, float inv_Bg, float* __restrict__ loss_row,
+                           float* __restrict__ rowscale) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= tgt.B) return;
+    const int M = tgt.B;
+    // merge of the per-tile (max, sum exp) partials of the fused decoder kernel -> lse_u
+    float l;
+    if (pmax) {
+        float mx = -INFINITY;
+        for (int t = lane; t < n_tiles; t += 32) mx = fmaxf(mx, pmax[(int64_t)t * M + warp]);
+        mx = warp_max(mx);
+        float sacc = 0.f;
+        for (int t = lane; t < n_tiles; t += 32) {
+            float pm = pmax[(int64_t)t * M + warp];
+            if (pm != -INFINITY) sacc += psum[(int64_t)t * M + warp] * expf(pm - mx);
+        }
+        sacc = warp_sum(sacc);
+        l = mx + logf(sacc);
+        if (lane == 0) lse[warp] = l;
+    } else {
+        l = lse[warp];
+    }
     float dot = 0.f;
     for (int i = lane; i < H; i += 32) dot = fmaf(h[(int64_t)warp * H + i], gvec[(int64_t)warp * H + i], dot);
     int64_t gr = tgt.row_ids ? (int64_t)tgt.row_ids[warp] : (int64_t)warp;
@@ -496,16 +561,19 @@ __global__ void k_row_loss(BatchView tgt, const float* __restrict__ h, const flo
         tb = fmaf(tgt.values ? tgt.values[k] : 1.f, bias[tgt.indices[k]], tb);
     dot = warp_sum(dot);
     tb = warp_sum(tb);
-    if (lane == 0) loss_row[warp] = T[warp] * lse[warp] - dot - tb;
+    if (lane == 0) {
+        loss_row[warp] = T[warp] * l - dot - tb;
+        if (rowscale) rowscale[warp] = T[warp] * inv_Bg;     // dlogits = softmax * T/B - t/B
+    }
 }
 
 int launch_row_loss(Ctx* c, const BatchView& tgt, const float* h, const float* gvec, int H,
-                    const float* bias, const float* lse, const float* T, float* loss_row,
-                    cudaStream_t s) {
+                    const float* bias, const float* pmax, const float* psum, int n_tiles, float* lse,
+                    const float* T, float inv_Bg, float* loss_row, float* rowscale, cudaStream_t s) {
     if (tgt.B == 0) return 0;
     int threads = 256;
-    k_row_loss<<<(int)cdiv((int64_t)tgt.B * 32, threads), threads, 0, s>>>(tgt, h, gvec, H, bias, lse,
-                                                                            T, loss_row);
+    k_row_loss<<<(int)cdiv((int64_t)tgt.B * 32, threads), threads, 0, s>>>(tgt, h, gvec, H, bias, pmax, psum, n_tiles,
+                                                                            lse, T, inv_Bg, loss_row, rowscale);
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -587,9 +587,9 @@ static bool use_cg2() {
 }
 // N tile: <= 256; each CTA of a pair stages BN/2 rows, so the granule doubles in pair mode
 static int pick_bn(int N, bool b_mn) {
-    if (N >= 256) return 256;
     const int g = (b_mn ? 32 : 16) * (use_cg2() ? 2 : 1);
-    return (int)std::min<int64_t>(256, round_up(N, g));
+    const int64_t tiles = cdiv(N, 256);                 // fewest tiles, then the smallest tile that covers N
+    return (int)std::min<int64_t>(256, round_up(cdiv(N, tiles), g));
 }
 // number of (max, sum) partial rows the LSE epilogue writes per user: two warps per 256-item tile
 int tc_lse_tiles(int N) { return 2 * (int)cdiv(N, pick_bn(N, false)); }
