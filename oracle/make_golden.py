@@ -133,7 +133,7 @@ def metrics_known_answers():
     print("metrics_small ok")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and os.environ.get("GOLDEN_CHECKPOINT_ONLY", "0") != "1":
     metrics_known_answers()
     # config #1 of BASELINE.json: MultiDAE [100-50-100], 1K x 100, density 0.1, batch 32
     run_case("cfg1_dae", False, [50, 100], 1000, 100, 32, 32, 0.5, 0, 1000, lam=0.2,
@@ -147,3 +147,26 @@ if __name__ == "__main__":
     # MultiDAE single hidden layer [I-200]-like shape (config #3 structure, scaled down)
     run_case("small_dae", False, [40, 800], 300, 800, 100, 3, 0.3, 3, 4000, lam=0.2,
              heldout=True)
+
+
+def reference_checkpoint():
+    """A checkpoint written by the UNMODIFIED reference (MultiVAE.save_model, models.py:897-903) after a few
+    training steps, plus the reference's eval-mode scores for a probe batch: the drop-in must load it."""
+    torch.manual_seed(7)
+    net = MultiVAE_net([4, 12, 40], None, 0.5)
+    model = MultiVAE(net, beta=0.5, anneal_steps=4)
+    csr = synth.make_matrix(64, 40, seed=5, density=0.15)
+    sampler = DataSampler(csr.to_scipy(), batch_size=16, shuffle=False)
+    torch.manual_seed(11)
+    model.train(sampler, num_epochs=2, verbose=4)
+    path = os.path.join(OUT, "ref_checkpoint_vae.pth")
+    model.save_model(path, 2)
+    x = torch.from_numpy(csr.rows(0, 16).toarray())
+    scores, mu, logvar = model.predict(x, True)
+    np.savez_compressed(os.path.join(OUT, "ref_checkpoint_vae_probe.npz"), x=x.numpy(), scores=scores.numpy(),
+                        mu=mu.numpy(), logvar=logvar.numpy(), gradient_updates=model.gradient_updates)
+    print("reference checkpoint written (%d bytes)" % os.path.getsize(path))
+
+
+if __name__ == "__main__":
+    reference_checkpoint()

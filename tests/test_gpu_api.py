@@ -192,3 +192,51 @@ def test_train_epoch_on_sampler_matches_batch_loop():
     assert abs(loss_epoch - float(np.mean(losses))) < 1e-5 * abs(loss_epoch)
     for a, b in zip(m1.network.state_dict().values(), m2.network.state_dict().values()):
         assert torch.allclose(a, b, atol=1e-6)
+
+
+def test_loads_checkpoint_written_by_the_reference(golden_dir):
+    """tests/golden/ref_checkpoint_vae.pth was written by the UNMODIFIED reference's MultiVAE.save_model
+    (oracle/make_golden.py::reference_checkpoint).  The drop-in loads it (weights, Adam state, gradient_updates),
+    reproduces the reference's eval-mode scores and keeps training from it."""
+    probe = np.load(os.path.join(golden_dir, "ref_checkpoint_vae_probe.npz"))
+    model = MultiVAE(MultiVAE_net([4, 12, 40], None, 0.5).cuda(), beta=0.5, anneal_steps=4)
+    chk = model.load_model(os.path.join(golden_dir, "ref_checkpoint_vae.pth"))
+    assert chk["epoch"] == 2 and model.gradient_updates == float(probe["gradient_updates"]) == 8.0
+    x = torch.from_numpy(probe["x"])
+    scores, mu, logvar = model.predict(x, True)
+    ref = probe["scores"]
+    got = scores.cpu().numpy()
+    assert np.array_equal(np.isinf(ref), np.isinf(got))
+    fin = np.isfinite(ref)
+    assert np.abs(got[fin] - ref[fin]).max() < 1e-5
+    assert np.abs(mu.cpu().numpy() - probe["mu"]).max() < 1e-5
+    assert np.abs(logvar.cpu().numpy() - probe["logvar"]).max() < 1e-5
+    st = model.optimizer.state_dict()["state"]
+    assert float(st[0]["step"]) == 8.0 and st[0]["exp_avg"].abs().sum() > 0
+    assert model._engine.adam_steps == 8
+    loss = model.train_batch(x)                     # continues from the restored optimizer state
+    assert np.isfinite(loss) and model._engine.adam_steps == 9
+
+
+def test_cfg5_shapes_functional():
+    """BASELINE config #5 shapes on one GPU's share: MultiVAE [200000-1024-512], 256 users per rank.
+    Size-independent properties only (no CPU oracle at this size): finite decreasing loss, NLL > 0,
+    decoder-bias gradient sums to ~0, seen items masked in predict."""
+    from rectorch_b200 import synth
+    n_items, B = 200000, 256
+    csr = synth.make_matrix(1024, n_items, seed=31)
+    torch.manual_seed(0)
+    model = MultiVAE(MultiVAE_net([512, 1024, n_items]).cuda(), beta=0.2, anneal_steps=20000)
+    sampler = DataSampler(csr, None, batch_size=B, shuffle=False)
+    rb = next(iter(sampler.iter_rows()))
+    losses = [model.train_batch(rb) for _ in range(6)]
+    assert np.isfinite(losses).all() and losses[-1] < losses[0]
+    eng = model._engine
+    assert eng.use_tc and eng.n_elems > 4 * 10 ** 8
+    buf = eng.forward_backward(rows=rb.rows, beta=0.2, dropout_p=0.5, seed=3, step=7)
+    c = buf.tolist()
+    assert np.isfinite(c).all() and c[1] > 0
+    _, gb = eng._views(eng.g, len(eng.shapes) - 1)
+    assert abs(gb.sum().item()) < 1e-3 * gb.abs().sum().item() + 1e-6
+    scores = model.predict(rb, True)[0]
+    assert scores.shape == (B, n_items) and torch.isinf(scores).sum().item() == int(csr.rows(0, B).nnz)
