@@ -339,24 +339,31 @@ def run_b200(args):
     adam_bytes = 28.0 * P + 4.0 * I * H          # w,g,m,v read; w,m,v written; + tf32 shadow of W_d written
     k4_bytes = 4.0 * I * H + 4.0 * I + 4.0 * B * H + 8.0 * B * (-(-I // 256))
     k4_flops = 2.0 * B * I * H
+    # DRAM traffic per launch from the committed `ncu --set full` captures (profiles/r1_ncu_*.txt):
+    # dram__bytes_read.sum + dram__bytes_write.sum.  Only valid for the cfg2 shapes they were taken on.
+    NCU_TRAFFIC = {1: 966.66e6 + 786.93e6, 0: 121.47e6 + 4.11e6, 2: 121.82e6 + 51.88e6, 3: 101.46e6 + 67.96e6,
+                   4: 220.22e6 + 4.40e6}
     dom = int(np.argmax(kms))
     roof_dom = None
     if dom == 1:
         ach = adam_bytes / (kms[1] * 1e-3) / 1e9
         roof_dom = {"kernel": names[1], "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms": float(kms[1]), "peak_src": peaks["src"]}
+                    "frac": ach / peaks["hbm_gbs"], "traffic": NCU_TRAFFIC[1], "algorithmic_bytes": adam_bytes,
+                    "ms": float(kms[1]), "peak_src": peaks["src"] + " (copy bandwidth, MEASURED_PEAKS.json)"}
     else:
         flops = {0: k4_flops, 2: k4_flops, 3: 2.0 * B * I * (H + 8), 4: 2.0 * B * I * H}[dom]
         ach = flops / (kms[dom] * 1e-3) / 1e12
         pk = peaks["bf16_tflops_sustained"] / 2.0
         roof_dom = {"kernel": names[dom], "bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s",
-                    "frac": ach / pk, "traffic": None, "ms": float(kms[dom]),
+                    "frac": ach / pk, "traffic": NCU_TRAFFIC.get(dom), "ms": float(kms[dom]),
                     "peak_src": peaks["src"] + " bf16 sustained / 2 (tf32)"}
     k4_gbs = k4_bytes / (kms[0] * 1e-3) / 1e9 if kms[0] > 0 else None
     k4_tf = k4_flops / (kms[0] * 1e-3) / 1e12 if kms[0] > 0 else None
     roof_k4 = {"kernel": names[0], "ms": float(kms[0]), "hbm_gbs": k4_gbs, "hbm_frac": (k4_gbs or 0) / peaks["hbm_gbs"],
                "tflops_tf32": k4_tf, "tensor_frac_of_bf16_half": (k4_tf or 0) / (peaks["bf16_tflops"] / 2.0),
-               "algorithmic_bytes": k4_bytes, "flops": k4_flops}
+               "algorithmic_bytes": k4_bytes, "flops": k4_flops, "traffic": NCU_TRAFFIC[0],
+               "note": "timed group = tf32 operand prep + tcgen05 GEMM/LSE kernel; at B=500 the kernel is tensor/L2->SM "
+                       "bound (ncu: 65 % tensor-pipe active, DRAM reads == algorithmic bytes), see profiles/ for the batch sweep"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

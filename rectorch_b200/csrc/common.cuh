@@ -145,6 +145,8 @@ struct TcEpi {
     int bias_col = -1;
     int split_k = 1;                   // TC_EPI_STORE: partial products C[s] at C + s*split_stride
     int64_t split_stride = 0;
+    int transpose_out = 0;             // TC_EPI_STORE: write C[n*ldc + m] (a warp stores 32 consecutive m = 128 B);
+                                       // bias_col then names the ROW m whose values go to bias_grad[n]
     int n_fastest = 0;                 // walk N tiles first (A tile shared through L2 by consecutive CTAs)
 };
 bool tc_supported(int M, int N, int K, int64_t lda, int64_t ldb);

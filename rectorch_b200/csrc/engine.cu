@@ -254,13 +254,15 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         tick(c, 2, 0, s);
         B200_CHECK(launch_tc_gemm(c, TC_EPI_PROB, c->h_r, H, 0, c->wd_shadow, H, 0, c->P, Bp, B, I, H, e, s));
         tick(c, 2, 1, s);
-        // dW_d | db_d = P^T [I x B] * [h | 1]  : A = P^T (K-major), B = hT [(H+8) x Bp] (K-major, from dec_lse)
+        // (dW_d | db_d)^T = [h | 1]^T [(H+8) x B] * P [B x I]: A = hT (K-major, from dec_lse), B = P^T (K-major).
+        // Computing the transpose puts the hidden index on the TMEM lanes, so each epilogue store
+        // instruction writes 32 consecutive floats of a dW_d row (full 128 B lines) instead of 32 rows x 16 B.
         TcEpi e2;
         e2.bias_grad = dbd;
-        e2.bias_col = H;
-        e2.n_fastest = 1;      // the 3 N tiles of one item block run on neighbouring CTAs: P^T is read from HBM once
+        e2.bias_col = H;       // row H of the product (the ones row of hT) is the bias gradient
+        e2.transpose_out = 1;
         tick(c, 3, 0, s);
-        B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->P, Bp, 0, c->hT, Bp, 0, dWd, H, I, H + 8, B, e2, s));
+        B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->hT, Bp, 0, c->P, Bp, 0, dWd, H, H + 8, I, B, e2, s));
         tick(c, 3, 1, s);
         // dh = P W_d : A = P^T given as [K=I x M=Bp] (MN-major), B = W_d [K=I x N=H] (MN-major)
         TcEpi e3;

@@ -219,6 +219,7 @@ struct TcArgs {
     int64_t split_stride;
     int n_store;            // STORE: columns < n_store go to C
     int bias_col;           // STORE: this column goes to bias_grad[m] (or -1)
+    int transpose_out;      // STORE: C[n*ldc + m]; rows m < n_store are stored, row m == bias_col -> bias_grad[n]
     const float* bias;
     float* part_max;
     float* part_sum;
@@ -295,6 +296,20 @@ __device__ __forceinline__ void epi_chunk(const TcArgs& a, const float* v, const
                     const float x = v[i] + bias_s[c0 + i];
                     dst[(int64_t)i * a.ldc] = tf32_rn(ex2_approx(fmaf(x, LOG2E_F, -lse_l2)) * rs_m);
                 }
+            }
+        }
+    } else if (a.transpose_out) {
+        // D^T: for a fixed column the warp's 32 lanes (consecutive m) write 32 consecutive floats
+        if (m < a.M) {
+            if (m < a.n_store) {
+                float* dst = a.C + (int64_t)(n0 + c0) * a.ldc + m;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < nc) dst[(int64_t)i * a.ldc] = v[i];
+            } else if (m == a.bias_col) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < nc) a.bias_grad[n0 + c0 + i] = v[i];
             }
         }
     } else {
@@ -647,7 +662,8 @@ int launch_tc_gemm(Ctx* c, int mode, const float* A, int64_t lda, int a_mn, cons
     a.bias = e.bias; a.part_max = e.part_max; a.part_sum = e.part_sum; a.lse = e.lse; a.rowscale = e.rowscale;
     a.bias_grad = e.bias_grad;
     a.bias_col = e.bias_col;
-    a.n_store = (e.bias_col >= 0) ? e.bias_col : N;
+    a.transpose_out = e.transpose_out;
+    a.n_store = (e.bias_col >= 0) ? e.bias_col : (e.transpose_out ? M : N);
     a.vec_ok = (C && ((uintptr_t)C & 15) == 0 && (ldc % 4 == 0) && (e.split_stride % 4 == 0)) ? 1 : 0;
     {
         static int dbg = -1;
