@@ -92,6 +92,8 @@ int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const floa
 int launch_spmm_scatter(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
                         int H, float* dWt, cudaStream_t s);
 int launch_bias_scatter(Ctx* c, const BatchView& v, float scale, float* db, cudaStream_t s);
+int launch_spmm_scatter_bias(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
+                             int H, float* dWt, float* db, cudaStream_t s);
 int launch_dense_count(Ctx* c, const float* dense, int B, int I, int64_t* lens, cudaStream_t s);
 int launch_dense_fill(Ctx* c, const float* dense, int B, int I, const int64_t* indptr,
                       int32_t* indices, float* values, cudaStream_t s);
@@ -121,9 +123,10 @@ int launch_loss_final(Ctx* c, const float* loss_row, const float* kl_row, int B,
                       cudaStream_t s);
 int launch_tensor_norms(Ctx* c, const float* w, const int64_t* offs, const int64_t* lens,
                         int n_tensors, float* partial, float* norms, cudaStream_t s);
-int launch_adam(Ctx* c, float* w, const float* g, float* m, float* v, int64_t n, float lr_over_bc1,
+int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float lr_over_bc1,
                 float beta1, float beta2, float bc2_sqrt, float eps, float wd, float lam,
-                const float* norm_ptr, float* shadow, int64_t sh_lo, int64_t sh_hi, cudaStream_t s);
+                const float* norm_ptr, float* shadow, int64_t sh_lo, int64_t sh_hi, int64_t z_lo, int64_t z_hi,
+                cudaStream_t s);
 int launch_round_tf32(Ctx* c, const float* x, float* y, int64_t n, cudaStream_t s);
 int launch_tanh_grad(Ctx* c, float* d, const float* y, int64_t n, cudaStream_t s);
 int launch_axpy(Ctx* c, float* y, const float* x, float a, int64_t n, cudaStream_t s);

@@ -42,9 +42,7 @@ struct Ctx {
     float* kl_row = nullptr;          // [B]
     float* lse = nullptr;             // [B]
     float* rowscale = nullptr;        // [B] T_u / B_global
-    bool dw1_clean = false;           // encoder-0 gradient rows are all zero (sparse re-zero done after Adam)
-    BatchView last_in;                // input batch of the most recent forward_backward
-    bool last_in_valid = false;
+    bool dw1_clean = false;           // encoder-0 gradient is all zero (the Adam kernel re-zeroes what it consumed)
     std::vector<float*> act_enc;      // per encoder layer output [B x out]
     std::vector<float*> act_dec;      // per decoder layer output, except the last
     float* z = nullptr;               // [B x latent]

@@ -185,9 +185,10 @@ __device__ __forceinline__ void adam_one(float& w, float g, float& m, float& v, 
 
 template <bool EXTRAS>
 __global__ void __launch_bounds__(256)
-k_adam(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
        int64_t n, float neg_step, float b1c, float b2, float b2c, float bc2_sqrt, float eps, float wd,
-       float lam, const float* __restrict__ norm_ptr, float* __restrict__ shadow, int64_t sh_lo, int64_t sh_hi) {
+       float lam, const float* __restrict__ norm_ptr, float* __restrict__ shadow, int64_t sh_lo, int64_t sh_hi,
+       int64_t z_lo, int64_t z_hi) {
     float reg = 0.f;
     if (EXTRAS && norm_ptr) {
         float nrm = *norm_ptr;
@@ -196,7 +197,7 @@ k_adam(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m
     int64_t n4 = n >> 2;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     float4* w4 = reinterpret_cast<float4*>(w);
-    const float4* g4 = reinterpret_cast<const float4*>(g);
+    float4* g4 = reinterpret_cast<float4*>(g);
     float4* m4 = reinterpret_cast<float4*>(m);
     float4* v4 = reinterpret_cast<float4*>(v);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -209,6 +210,10 @@ k_adam(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m
         m4[i] = mm;
         v4[i] = vv;
         const int64_t e0 = i << 2;
+        // the encoder-0 gradient is accumulated by sparse scatters into an all-zero buffer: restore the zeros
+        // here, touching only the (few) rows that actually received a gradient
+        if (e0 >= z_lo && e0 < z_hi && (gg.x != 0.f || gg.y != 0.f || gg.z != 0.f || gg.w != 0.f))
+            g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (shadow && e0 >= sh_lo && e0 < sh_hi)   // tf32 image of W_d for the tensor-core GEMMs
             *reinterpret_cast<float4*>(shadow + (e0 - sh_lo)) =
                 make_float4(tf32_rn(ww.x), tf32_rn(ww.y), tf32_rn(ww.z), tf32_rn(ww.w));
@@ -216,7 +221,9 @@ k_adam(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m
     // tail (n not a multiple of 4)
     for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         float ww = w[i], mm = m[i], vv = v[i];
-        adam_one(ww, g[i], mm, vv, neg_step, b1c, b2, b2c, bc2_sqrt, eps, EXTRAS ? wd : 0.f, reg);
+        const float gi = g[i];
+        adam_one(ww, gi, mm, vv, neg_step, b1c, b2, b2c, bc2_sqrt, eps, EXTRAS ? wd : 0.f, reg);
+        if (i >= z_lo && i < z_hi && gi != 0.f) g[i] = 0.f;
         w[i] = ww;
         m[i] = mm;
         v[i] = vv;
@@ -224,9 +231,10 @@ k_adam(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m
     }
 }
 
-int launch_adam(Ctx* c, float* w, const float* g, float* m, float* v, int64_t n, float lr_over_bc1,
+int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float lr_over_bc1,
                 float beta1, float beta2, float bc2_sqrt, float eps, float wd, float lam,
-                const float* norm_ptr, float* shadow, int64_t sh_lo, int64_t sh_hi, cudaStream_t s) {
+                const float* norm_ptr, float* shadow, int64_t sh_lo, int64_t sh_hi, int64_t z_lo, int64_t z_hi,
+                cudaStream_t s) {
     if (n == 0) return 0;
     B200_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(m) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0,
@@ -237,9 +245,9 @@ int launch_adam(Ctx* c, float* w, const float* g, float* m, float* v, int64_t n,
     bool extras = (wd != 0.f) || (lam != 0.f && norm_ptr);
     float b1c = 1.f - beta1, b2c = 1.f - beta2;
     if (extras)
-        k_adam<true><<<blocks, 256, 0, s>>>(w, g, m, v, n, -lr_over_bc1, b1c, beta2, b2c, bc2_sqrt, eps, wd, lam, norm_ptr, shadow, sh_lo, sh_hi);
+        k_adam<true><<<blocks, 256, 0, s>>>(w, g, m, v, n, -lr_over_bc1, b1c, beta2, b2c, bc2_sqrt, eps, wd, lam, norm_ptr, shadow, sh_lo, sh_hi, z_lo, z_hi);
     else
-        k_adam<false><<<blocks, 256, 0, s>>>(w, g, m, v, n, -lr_over_bc1, b1c, beta2, b2c, bc2_sqrt, eps, 0.f, 0.f, nullptr, shadow, sh_lo, sh_hi);
+        k_adam<false><<<blocks, 256, 0, s>>>(w, g, m, v, n, -lr_over_bc1, b1c, beta2, b2c, bc2_sqrt, eps, 0.f, 0.f, nullptr, shadow, sh_lo, sh_hi, z_lo, z_hi);
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;

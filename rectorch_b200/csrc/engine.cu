@@ -299,8 +299,7 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         tick(c, 4, 1, s);
     }
     // sparse part of dlogits = -t/Bg
-    B200_CHECK(launch_spmm_scatter(c, st.tgt, nullptr, -inv_Bg, st.h_last, H, dWd, s));
-    B200_CHECK(launch_bias_scatter(c, st.tgt, -inv_Bg, dbd, s));
+    B200_CHECK(launch_spmm_scatter_bias(c, st.tgt, nullptr, -inv_Bg, st.h_last, H, dWd, dbd, s));
     // the decoder-output gradients (the tail of the gradient arena) are final from here on: a data-parallel
     // caller can start reducing them while the rest of the backward pass runs (b200vae_wait_wd_ready)
     B200_CUDA_OK(cudaEventRecord(c->ev_wd, s));
@@ -334,8 +333,6 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         if (c->timing) { note(c, "memset_dW1", s); c->launches--; }
     }
     c->dw1_clean = false;
-    c->last_in = st.in;
-    c->last_in_valid = true;
     B200_CHECK(launch_spmm_scatter(c, st.in, c->xt, 1.0f, cur, e0.out, c->g + e0.w_off, s));
     B200_CHECK(launch_colsum(c, cur, e0.out, B, e0.out, c->g + e0.b_off, s));
     return 0;
@@ -353,9 +350,12 @@ static int adam_step(Ctx* c, float lr, float beta1, float beta2, float eps, floa
     const Layer& DL = c->dec.back();
     float* shadow = c->tc_dec ? c->wd_shadow : nullptr;
     const int64_t sh_lo = DL.w_off, sh_hi = DL.w_off + (int64_t)DL.in * DL.out;
+    // Adam re-zeroes the encoder-0 gradient rows it consumed (sparse writes), so forward_backward never memsets
+    const Layer& E0 = c->enc[0];
+    const int64_t z_lo = E0.w_off, z_hi = E0.w_off + (int64_t)E0.in * E0.out;
     if (wd == 0.f && lam == 0.f) {
         B200_CHECK(launch_adam(c, c->w, c->g, c->m, c->v, c->n_elems, step_size, beta1, beta2, bc2_sqrt, eps, 0.f, 0.f, nullptr,
-                               shadow, sh_lo, sh_hi, s));
+                               shadow, sh_lo, sh_hi, z_lo, z_hi, s));
     } else {
         if (lam != 0.f)
             B200_CHECK(launch_tensor_norms(c, c->w, c->d_toff, c->d_tlen, c->n_tensors, c->norm_partial, c->norms, s));
@@ -364,21 +364,12 @@ static int adam_step(Ctx* c, float lr, float beta1, float beta2, float eps, floa
             const bool is_wd = (o == DL.w_off);
             B200_CHECK(launch_adam(c, c->w + o, c->g + o, c->m + o, c->v + o, c->tlen[t], step_size, beta1,
                                    beta2, bc2_sqrt, eps, wd, lam, lam != 0.f ? c->norms + t : nullptr,
-                                   is_wd ? shadow : nullptr, 0, is_wd ? c->tlen[t] : 0, s));
+                                   is_wd ? shadow : nullptr, 0, is_wd ? c->tlen[t] : 0,
+                                   0, (o == z_lo) ? c->tlen[t] : 0, s));
         }
     }
     tick(c, 1, 1, s);
-    return 0;
-}
-
-// Single-process fused step only: Adam has consumed the gradients, so zeroing the encoder-0 rows this
-// batch touched restores the all-zero invariant and the next step skips its 4*I*H-byte memset.
-static int rezero_enc0_grad(Ctx* c, cudaStream_t s) {
-    if (!c->last_in_valid) return 0;
-    const Layer& e0 = c->enc[0];
-    B200_CHECK(launch_spmm_zero(c, c->last_in, c->xt, e0.out, c->g + e0.w_off, s));
     c->dw1_clean = true;
-    c->last_in_valid = false;
     return 0;
 }
 
@@ -626,8 +617,7 @@ int b200vae_train_step(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int 
     B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, B200VAE_EINVAL, "dropout_p must be in [0,1)");
     B200_CHECK(forward_backward(c, row_ids, B, B, use_target, beta, lam, dropout_p, seed, (uint64_t)step, 0,
                                 keep_tape, eps_tape, loss_out, (cudaStream_t)stream));
-    B200_CHECK(adam_step(c, lr, beta1, beta2, eps, weight_decay, lam, step, (cudaStream_t)stream));
-    return rezero_enc0_grad(c, (cudaStream_t)stream);
+    return adam_step(c, lr, beta1, beta2, eps, weight_decay, lam, step, (cudaStream_t)stream);
 }
 
 // ---- context-free helpers used by rectorch_b200.metrics / models.loss_function ---------------
@@ -705,7 +695,6 @@ int b200vae_train_step_host(b200vae_ctx* ctx, const int64_t* indptr_host, const 
     S.int_has_values = values_host != nullptr;
     B200_CHECK(forward_backward(c, nullptr, B, B, 0, beta, lam, dropout_p, seed, (uint64_t)step, 0, nullptr, nullptr, c->loss_dev, s));
     B200_CHECK(adam_step(c, lr, 0.9f, 0.999f, 1e-8f, weight_decay, lam, step, s));
-    B200_CHECK(rezero_enc0_grad(c, s));
     B200_CUDA_OK(cudaMemcpyAsync(loss_host, c->loss_dev, 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
     return 0;

@@ -318,7 +318,7 @@ int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const floa
 template <int VEC>
 __global__ void __launch_bounds__(256)
 k_spmm_scatter(BatchView v, const float* __restrict__ vals, float scale, const float* __restrict__ dY,
-               int H, float* __restrict__ dWt) {
+               int H, float* __restrict__ dWt, float* __restrict__ db) {
     if ((int)blockIdx.x >= v.sp[v.B]) return;
     const int r = find_row(v.sp, v.B, blockIdx.x);
     const int seg = blockIdx.x - v.sp[r];
@@ -330,6 +330,12 @@ k_spmm_scatter(BatchView v, const float* __restrict__ vals, float scale, const f
     const int32_t* cols = v.indices + a;
     const float* xv = vals ? vals + o : nullptr;
     const float* raw = v.values ? v.values + a : nullptr;
+    if (db) {   // db[col_k] += scale * value_k   (sparse part of the bias gradient, same CSR walk)
+        for (int k = k0 + threadIdx.x; k < k1; k += blockDim.x) {
+            float x = xv ? xv[k] : (raw ? raw[k] : 1.f);
+            if (x != 0.f) atomicAdd(db + cols[k], scale * x);
+        }
+    }
     for (int h0 = threadIdx.x * VEC; h0 < H; h0 += blockDim.x * VEC) {
         float d[VEC];
 #pragma unroll
@@ -350,15 +356,20 @@ k_spmm_scatter(BatchView v, const float* __restrict__ vals, float scale, const f
 
 int launch_spmm_scatter(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
                         int H, float* dWt, cudaStream_t s) {
+    return launch_spmm_scatter_bias(c, v, vals, scale, dY, H, dWt, nullptr, s);
+}
+
+int launch_spmm_scatter_bias(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
+                             int H, float* dWt, float* db, cudaStream_t s) {
     if (v.B == 0) return 0;
     bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(dWt) & 15) == 0);
     const int grid = spmm_grid(c, v);
     if (vec) {
         int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));
-        k_spmm_scatter<4><<<grid, threads, 0, s>>>(v, vals, scale, dY, H, dWt);
+        k_spmm_scatter<4><<<grid, threads, 0, s>>>(v, vals, scale, dY, H, dWt, db);
     } else {
         int threads = (int)std::min<int64_t>(256, round_up(H, 32));
-        k_spmm_scatter<1><<<grid, threads, 0, s>>>(v, vals, scale, dY, H, dWt);
+        k_spmm_scatter<1><<<grid, threads, 0, s>>>(v, vals, scale, dY, H, dWt, db);
     }
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
