@@ -85,6 +85,8 @@ int launch_batch_scan(Ctx* c, const int64_t* indptr, const int32_t* row_ids, int
 int launch_batch_prep(Ctx* c, const BatchView& in, float p, uint64_t seed, uint64_t step,
                       int64_t row_offset, const uint8_t* keep_tape, bool train, float* xt, float* row_sum_out,
                       cudaStream_t s);
+int launch_target_fixup(Ctx* c, const BatchView& tgt, float* PT, int64_t ldp, const float* rowscale, float inv_Bg,
+                        float* loss_row, cudaStream_t s);
 int launch_spmm_zero(Ctx* c, const BatchView& v, const float* vals, int H, float* dWt, cudaStream_t s);
 int launch_row_sums(Ctx* c, const BatchView& v, float* out, cudaStream_t s);
 int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const float* Wt, int H,

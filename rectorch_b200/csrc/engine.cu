@@ -228,15 +228,18 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
     tick(c, 0, 0, s);
     B200_CHECK(dec_lse(c, st.h_last, B, H, &n_lse_tiles, true, s));
     tick(c, 0, 1, s);
-    B200_CHECK(launch_spmm_gather(c, st.tgt, nullptr, Wd, H, nullptr, 0, c->gvec, s));
-    B200_CHECK(launch_row_loss(c, st.tgt, st.h_last, c->gvec, H, c->w + DL.b_off, c->part_max, c->part_sum, n_lse_tiles,
-                               c->lse, c->T, inv_Bg, c->loss_row, c->rowscale, s));
+    if (c->tc_dec) {
+        // merge the LSE partials, T/B; the sparse loss term is taken from P^T after the recompute kernel (target_fixup)
+        B200_CHECK(launch_row_loss(c, st.tgt, st.h_last, nullptr, H, c->w + DL.b_off, c->part_max, c->part_sum, n_lse_tiles,
+                                   c->lse, c->T, inv_Bg, c->loss_row, c->rowscale, s));
+    } else {
+        B200_CHECK(launch_spmm_gather(c, st.tgt, nullptr, Wd, H, nullptr, 0, c->gvec, s));
+        B200_CHECK(launch_row_loss(c, st.tgt, st.h_last, c->gvec, H, c->w + DL.b_off, c->part_max, c->part_sum, n_lse_tiles,
+                                   c->lse, c->T, inv_Bg, c->loss_row, c->rowscale, s));
+    }
     const bool dae_reg = (!c->cfg.is_vae) && lam != 0.f;
     if (dae_reg)
         B200_CHECK(launch_tensor_norms(c, c->w, c->d_toff, c->d_tlen, c->n_tensors, c->norm_partial, c->norms, s));
-    B200_CHECK(launch_loss_final(c, c->loss_row, c->cfg.is_vae ? c->kl_row : nullptr, B, inv_Bg,
-                                 c->cfg.is_vae ? beta : 0.f, dae_reg ? lam : 0.f,
-                                 dae_reg ? c->norms : nullptr, c->n_tensors, loss_out, s));
 
     // ---------------- backward: decoder output layer ----------------
     float* rowscale = c->rowscale;   // T_u / B_global, written by row_loss
@@ -254,6 +257,8 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         tick(c, 2, 0, s);
         B200_CHECK(launch_tc_gemm(c, TC_EPI_PROB, c->h_r, H, 0, c->wd_shadow, H, 0, c->P, Bp, B, I, H, e, s));
         tick(c, 2, 1, s);
+        // sparse part of dlogits + the sparse loss term, straight on P^T
+        B200_CHECK(launch_target_fixup(c, st.tgt, c->P, Bp, rowscale, inv_Bg, c->loss_row, s));
         // (dW_d | db_d)^T = [h | 1]^T [(H+8) x B] * P [B x I]: A = hT (K-major, from dec_lse), B = P^T (K-major).
         // Computing the transpose puts the hidden index on the TMEM lanes, so each epilogue store
         // instruction writes 32 consecutive floats of a dW_d row (full 128 B lines) instead of 32 rows x 16 B.
@@ -272,8 +277,8 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         B200_REQUIRE((int64_t)split * B * H <= c->splitk_elems, B200VAE_ECAPACITY, "split-K workspace too small");
         tick(c, 4, 0, s);
         B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->P, Bp, 1, c->wd_shadow, H, 1, c->splitk, H, B, H, I, e3, s));
-        B200_CHECK(launch_splitk_reduce(c, c->splitk, split, e3.split_stride, d0, H, B, H, H, c->gvec, H,
-                                        -inv_Bg, st.h_last_tanh, H, s));
+        B200_CHECK(launch_splitk_reduce(c, c->splitk, split, e3.split_stride, d0, H, B, H, H, nullptr, 0,
+                                        0.f, st.h_last_tanh, H, s));
         tick(c, 4, 1, s);
     } else {
         GemmEpi e;
@@ -298,8 +303,11 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         B200_CHECK(launch_simt_gemm(c, EPI_STORE, c->P, I, 1, Wd, H, 1, d0, H, B, H, I, e3, s));
         tick(c, 4, 1, s);
     }
-    // sparse part of dlogits = -t/Bg
-    B200_CHECK(launch_spmm_scatter_bias(c, st.tgt, nullptr, -inv_Bg, st.h_last, H, dWd, dbd, s));
+    // sparse part of dlogits = -t/Bg (the tensor-core path already folded it into P^T)
+    if (!c->tc_dec) B200_CHECK(launch_spmm_scatter_bias(c, st.tgt, nullptr, -inv_Bg, st.h_last, H, dWd, dbd, s));
+    B200_CHECK(launch_loss_final(c, c->loss_row, c->cfg.is_vae ? c->kl_row : nullptr, B, inv_Bg,
+                                 c->cfg.is_vae ? beta : 0.f, dae_reg ? lam : 0.f,
+                                 dae_reg ? c->norms : nullptr, c->n_tensors, loss_out, s));
     // the decoder-output gradients (the tail of the gradient arena) are final from here on: a data-parallel
     // caller can start reducing them while the rest of the backward pass runs (b200vae_wait_wd_ready)
     B200_CUDA_OK(cudaEventRecord(c->ev_wd, s));

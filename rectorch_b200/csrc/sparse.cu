@@ -563,19 +563,56 @@ __global__ void k_row_loss(BatchView tgt, const float* __restrict__ h, const flo
     } else {
         l = lse[warp];
     }
-    float dot = 0.f;
-    for (int i = lane; i < H; i += 32) dot = fmaf(h[(int64_t)warp * H + i], gvec[(int64_t)warp * H + i], dot);
-    int64_t gr = tgt.row_ids ? (int64_t)tgt.row_ids[warp] : (int64_t)warp;
-    int64_t a = tgt.indptr[gr], b = tgt.indptr[gr + 1];
-    float tb = 0.f;
-    for (int64_t k = a + lane; k < b; k += 32)
-        tb = fmaf(tgt.values ? tgt.values[k] : 1.f, bias[tgt.indices[k]], tb);
-    dot = warp_sum(dot);
-    tb = warp_sum(tb);
+    float dot = 0.f, tb = 0.f;
+    if (gvec) {     // fp32 path: sum_j t_j logit_j = h . g + sum_j t_j b_j
+        for (int i = lane; i < H; i += 32) dot = fmaf(h[(int64_t)warp * H + i], gvec[(int64_t)warp * H + i], dot);
+        int64_t gr = tgt.row_ids ? (int64_t)tgt.row_ids[warp] : (int64_t)warp;
+        int64_t a = tgt.indptr[gr], b = tgt.indptr[gr + 1];
+        for (int64_t k = a + lane; k < b; k += 32)
+            tb = fmaf(tgt.values ? tgt.values[k] : 1.f, bias[tgt.indices[k]], tb);
+        dot = warp_sum(dot);
+        tb = warp_sum(tb);
+    }
     if (lane == 0) {
-        loss_row[warp] = T[warp] * l - dot - tb;
+        if (gvec) loss_row[warp] = T[warp] * l - dot - tb;
         if (rowscale) rowscale[warp] = T[warp] * inv_Bg;     // dlogits = softmax * T/B - t/B
     }
+}
+
+// Tensor-core path: after the recompute kernel stored P^T[j,u] = softmax_uj * T_u/B (dense part of dlogits),
+// walk the TARGET non-zeros once:
+//   loss_u  = -sum_j t_uj * log(P_uj / (T_u/B))            (== sum_j t_uj (lse_u - logit_uj), models.py:813)
+//   P^T[j,u] -= t_uj / B                                    (sparse part of dlogits)
+// so dW_d, db_d and dh come out of the two GEMMs complete: no gather of W_d rows for the loss and no
+// scatter into dW_d.  One warp per user row; ~nnz_B scattered 4-byte read-modify-writes.
+__global__ void k_target_fixup(BatchView tgt, float* __restrict__ PT, int64_t ldp, const float* __restrict__ rowscale,
+                               float inv_Bg, float* __restrict__ loss_row) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= tgt.B) return;
+    const float rs = rowscale[warp];
+    int64_t gr = tgt.row_ids ? (int64_t)tgt.row_ids[warp] : (int64_t)warp;
+    int64_t a = tgt.indptr[gr], b = tgt.indptr[gr + 1];
+    float acc = 0.f;
+    for (int64_t k = a + lane; k < b; k += 32) {
+        const float t = tgt.values ? tgt.values[k] : 1.f;
+        float* q = PT + (int64_t)tgt.indices[k] * ldp + warp;
+        const float p = *q;
+        acc = fmaf(t, logf(p / rs), acc);
+        *q = tf32_rn(p - t * inv_Bg);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) loss_row[warp] = -acc;
+}
+
+int launch_target_fixup(Ctx* c, const BatchView& tgt, float* PT, int64_t ldp, const float* rowscale, float inv_Bg,
+                        float* loss_row, cudaStream_t s) {
+    if (tgt.B == 0) return 0;
+    int threads = 256;
+    k_target_fixup<<<(int)cdiv((int64_t)tgt.B * 32, threads), threads, 0, s>>>(tgt, PT, ldp, rowscale, inv_Bg, loss_row);
+    note(c, __func__, s);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
 }
 
 int launch_row_loss(Ctx* c, const BatchView& tgt, const float* h, const float* gvec, int H,
