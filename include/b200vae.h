@@ -133,6 +133,13 @@ int  b200vae_wait_wd_ready(b200vae_ctx* ctx, void* stream);
 int  b200vae_adam_step(b200vae_ctx* ctx, float lr, float beta1, float beta2, float eps,
                        float weight_decay, float lam, int64_t step, void* stream);
 
+/* Same update restricted to the arena elements [elem_lo, elem_hi) (tensor boundaries).  Lets a data-parallel
+ * caller update the half of the parameters whose gradient all-reduce has finished while the other half's
+ * all-reduce is still in flight.  All ranges of one optimisation step use the same `step`. */
+int  b200vae_adam_step_range(b200vae_ctx* ctx, float lr, float beta1, float beta2, float eps,
+                             float weight_decay, float lam, int64_t step, int64_t elem_lo, int64_t elem_hi,
+                             void* stream);
+
 /* forward_backward + adam_step in one call (single-GPU fast path). */
 int  b200vae_train_step(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int use_target,
                         float beta, float lam, float dropout_p, uint64_t seed, int64_t step,

@@ -346,8 +346,11 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
     return 0;
 }
 
+// Adam over the arena range [r_lo, r_hi) (whole arena: 0, n_elems).  Ranges must not cut a tensor.
 static int adam_step(Ctx* c, float lr, float beta1, float beta2, float eps, float wd, float lam,
-                     int64_t step, cudaStream_t s) {
+                     int64_t step, cudaStream_t s, int64_t r_lo = 0, int64_t r_hi = -1) {
+    if (r_hi < 0) r_hi = c->n_elems;
+    B200_REQUIRE(r_lo >= 0 && r_lo < r_hi && r_hi <= c->n_elems && r_lo % 4 == 0, B200VAE_EINVAL, "bad Adam range");
     B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
     B200_REQUIRE(step >= 1, B200VAE_EINVAL, "adam step must be >= 1");
     double bc1 = 1.0 - std::pow((double)beta1, (double)step);
@@ -362,13 +365,16 @@ static int adam_step(Ctx* c, float lr, float beta1, float beta2, float eps, floa
     const Layer& E0 = c->enc[0];
     const int64_t z_lo = E0.w_off, z_hi = E0.w_off + (int64_t)E0.in * E0.out;
     if (wd == 0.f && lam == 0.f) {
-        B200_CHECK(launch_adam(c, c->w, c->g, c->m, c->v, c->n_elems, step_size, beta1, beta2, bc2_sqrt, eps, 0.f, 0.f, nullptr,
-                               shadow, sh_lo, sh_hi, z_lo, z_hi, s));
+        // kernel indices are relative to the pointers it gets: shift the shadow / re-zero windows by r_lo
+        // (the shadow pointer is pre-offset so that shadow[(e - r_lo) - (sh_lo - r_lo)] addresses element e - sh_lo)
+        B200_CHECK(launch_adam(c, c->w + r_lo, c->g + r_lo, c->m + r_lo, c->v + r_lo, r_hi - r_lo, step_size, beta1, beta2,
+                               bc2_sqrt, eps, 0.f, 0.f, nullptr, shadow, sh_lo - r_lo, sh_hi - r_lo, z_lo - r_lo, z_hi - r_lo, s));
     } else {
         if (lam != 0.f)
             B200_CHECK(launch_tensor_norms(c, c->w, c->d_toff, c->d_tlen, c->n_tensors, c->norm_partial, c->norms, s));
         for (int t = 0; t < c->n_tensors; ++t) {
             int64_t o = c->toff[t];
+            if (o < r_lo || o >= r_hi) continue;
             const bool is_wd = (o == DL.w_off);
             B200_CHECK(launch_adam(c, c->w + o, c->g + o, c->m + o, c->v + o, c->tlen[t], step_size, beta1,
                                    beta2, bc2_sqrt, eps, wd, lam, lam != 0.f ? c->norms + t : nullptr,
@@ -377,7 +383,7 @@ static int adam_step(Ctx* c, float lr, float beta1, float beta2, float eps, floa
         }
     }
     tick(c, 1, 1, s);
-    c->dw1_clean = true;
+    if (r_lo <= z_lo && r_hi >= z_hi) c->dw1_clean = true;
     return 0;
 }
 
@@ -597,6 +603,13 @@ int b200vae_forward_backward(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B
     B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, B200VAE_EINVAL, "dropout_p must be in [0,1)");
     return forward_backward(c, row_ids, B, B_global, use_target, beta, lam, dropout_p, seed, step, row_offset,
                             keep_tape, eps_tape, loss_out, (cudaStream_t)stream);
+}
+
+int b200vae_adam_step_range(b200vae_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay,
+                            float lam, int64_t step, int64_t elem_lo, int64_t elem_hi, void* stream) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    B200_REQUIRE(c, B200VAE_EINVAL, "null context");
+    return adam_step(c, lr, beta1, beta2, eps, weight_decay, lam, step, (cudaStream_t)stream, elem_lo, elem_hi);
 }
 
 int b200vae_sync_weights(b200vae_ctx* ctx, void* stream) {

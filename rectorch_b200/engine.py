@@ -248,6 +248,14 @@ class Engine:
         check(_lib.lib().b200vae_adam_step(self._ctx, float(lr), float(betas[0]), float(betas[1]), float(eps),
                                            float(weight_decay), float(lam), self.adam_steps, stream_ptr()))
 
+    def adam_range(self, lr, betas, eps, weight_decay, lam, lo, hi, first):
+        """Adam on arena elements [lo, hi); ``first`` advances the step counter (one step = all its ranges)."""
+        if first:
+            self.adam_steps += 1
+        check(_lib.lib().b200vae_adam_step_range(self._ctx, float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                                 float(weight_decay), float(lam), self.adam_steps, int(lo), int(hi),
+                                                 stream_ptr()))
+
     def train_step(self, rows=None, dense=None, dense_target=None, use_target=False, beta=1.0, lam=0.0,
                    dropout_p=0.5, seed=0, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                    keep_tape=None, eps_tape=None):

@@ -204,10 +204,12 @@ class AETrainer(TorchNNTrainer):
                 w_tail = dist.all_reduce(eng.g[cut:], op=dist.ReduceOp.SUM, async_op=True)
             w_head = dist.all_reduce(eng.g[:cut], op=dist.ReduceOp.SUM, async_op=True)
             w_loss = dist.all_reduce(loss_slot, op=dist.ReduceOp.SUM, async_op=True)
+            # the decoder half is updated while the encoder half is still being reduced
             w_tail.wait()
+            eng.adam_range(lr, betas, eps, wd, lam, cut, eng.n_elems, first=True)
             w_head.wait()
+            eng.adam_range(lr, betas, eps, wd, lam, 0, cut, first=False)
             w_loss.wait()
-            eng.adam(lr, betas, eps, wd, lam)
         self._step_tensor += 1.0
 
     def _loss_from(self, comps, beta, lam):
