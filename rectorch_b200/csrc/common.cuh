@@ -51,7 +51,8 @@ struct BatchView {
     int32_t        B;
 };
 
-constexpr int SPMM_SEG = 32;   // non-zeros per sparse gather/scatter work unit
+constexpr int SPMM_SEG = 32;
+constexpr int NORM_PARTS = 512;   // partial sums per tensor in the parameter-norm reduction   // non-zeros per sparse gather/scatter work unit
 
 struct Layer {
     int in, out;              // nn.Linear(in, out)

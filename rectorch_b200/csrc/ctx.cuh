@@ -42,6 +42,7 @@ struct Ctx {
     float* kl_row = nullptr;          // [B]
     float* lse = nullptr;             // [B]
     float* rowscale = nullptr;        // [B] T_u / B_global
+    bool norms_valid = false;         // c->norms hold the per-tensor norms of the CURRENT weights
     bool dw1_clean = false;           // encoder-0 gradient is all zero (the Adam kernel re-zeroes what it consumed)
     std::vector<float*> act_enc;      // per encoder layer output [B x out]
     std::vector<float*> act_dec;      // per decoder layer output, except the last

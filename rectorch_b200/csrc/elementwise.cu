@@ -157,9 +157,9 @@ __global__ void k_norm_final(const float* __restrict__ partial, int n_parts, flo
 
 int launch_tensor_norms(Ctx* c, const float* w, const int64_t* offs, const int64_t* lens, int n_tensors,
                         float* partial, float* norms, cudaStream_t s) {
-    dim3 grid(64, n_tensors);
+    dim3 grid(NORM_PARTS, n_tensors);     // enough CTAs on the two item-sized tensors to stream at HBM rate
     k_norm_partial<<<grid, 256, 0, s>>>(w, offs, lens, partial);
-    k_norm_final<<<n_tensors, 32, 0, s>>>(partial, 64, norms);
+    k_norm_final<<<n_tensors, 32, 0, s>>>(partial, NORM_PARTS, norms);
     note(c, __func__, s); c->launches++;
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -238,8 +238,10 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
                                    c->lse, c->T, inv_Bg, c->loss_row, c->rowscale, s));
     }
     const bool dae_reg = (!c->cfg.is_vae) && lam != 0.f;
-    if (dae_reg)
+    if (dae_reg) {
         B200_CHECK(launch_tensor_norms(c, c->w, c->d_toff, c->d_tlen, c->n_tensors, c->norm_partial, c->norms, s));
+        c->norms_valid = true;      // the weights do not change before this step's Adam: it reuses them
+    }
 
     // ---------------- backward: decoder output layer ----------------
     float* rowscale = c->rowscale;   // T_u / B_global, written by row_loss
@@ -370,7 +372,7 @@ static int adam_step(Ctx* c, float lr, float beta1, float beta2, float eps, floa
         B200_CHECK(launch_adam(c, c->w + r_lo, c->g + r_lo, c->m + r_lo, c->v + r_lo, r_hi - r_lo, step_size, beta1, beta2,
                                bc2_sqrt, eps, 0.f, 0.f, nullptr, shadow, sh_lo - r_lo, sh_hi - r_lo, z_lo - r_lo, z_hi - r_lo, s));
     } else {
-        if (lam != 0.f)
+        if (lam != 0.f && !c->norms_valid)
             B200_CHECK(launch_tensor_norms(c, c->w, c->d_toff, c->d_tlen, c->n_tensors, c->norm_partial, c->norms, s));
         for (int t = 0; t < c->n_tensors; ++t) {
             int64_t o = c->toff[t];
@@ -383,6 +385,7 @@ static int adam_step(Ctx* c, float lr, float beta1, float beta2, float eps, floa
         }
     }
     tick(c, 1, 1, s);
+    if (r_hi >= c->n_elems) c->norms_valid = false;      // last (or only) range of the step: weights have moved
     if (r_lo <= z_lo && r_hi >= z_hi) c->dw1_clean = true;
     return 0;
 }
@@ -513,7 +516,7 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     A_(dmalloc(&c->part_max, (int64_t)c->n_lse_tiles * Bm)); A_(dmalloc(&c->part_sum, (int64_t)c->n_lse_tiles * Bm));
     c->splitk_elems = c->tc_dec ? (int64_t)64 * Bm * H : 1;
     A_(dmalloc(&c->splitk, c->splitk_elems));
-    A_(dmalloc(&c->norms, c->n_tensors)); A_(dmalloc(&c->norm_partial, (int64_t)c->n_tensors * 64));
+    A_(dmalloc(&c->norms, c->n_tensors)); A_(dmalloc(&c->norm_partial, (int64_t)c->n_tensors * NORM_PARTS));
     A_(dmalloc(&c->d_toff, c->n_tensors)); A_(dmalloc(&c->d_tlen, c->n_tensors));
     A_(dmalloc(&c->loss_dev, 4)); A_(dmalloc(&c->d_err, 1)); A_(dmalloc(&c->lens_tmp, Bm + 1));
 #undef A_

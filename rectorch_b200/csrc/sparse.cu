@@ -585,31 +585,34 @@ __global__ void k_row_loss(BatchView tgt, const float* __restrict__ h, const flo
 //   P^T[j,u] -= t_uj / B                                    (sparse part of dlogits)
 // so dW_d, db_d and dh come out of the two GEMMs complete: no gather of W_d rows for the loss and no
 // scatter into dW_d.  One warp per user row; ~nnz_B scattered 4-byte read-modify-writes.
-__global__ void k_target_fixup(BatchView tgt, float* __restrict__ PT, int64_t ldp, const float* __restrict__ rowscale,
-                               float inv_Bg, float* __restrict__ loss_row) {
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (warp >= tgt.B) return;
-    const float rs = rowscale[warp];
-    int64_t gr = tgt.row_ids ? (int64_t)tgt.row_ids[warp] : (int64_t)warp;
+__global__ void __launch_bounds__(128)
+k_target_fixup(BatchView tgt, float* __restrict__ PT, int64_t ldp, const float* __restrict__ rowscale,
+               float inv_Bg, float* __restrict__ loss_row) {
+    // one CTA per user row: all of the row's non-zeros are in flight at once (the accesses are
+    // scattered 4-byte read-modify-writes, i.e. pure latency)
+    __shared__ float sh[4];
+    const int u = blockIdx.x;
+    const float rs = rowscale[u];
+    int64_t gr = tgt.row_ids ? (int64_t)tgt.row_ids[u] : (int64_t)u;
     int64_t a = tgt.indptr[gr], b = tgt.indptr[gr + 1];
     float acc = 0.f;
-    for (int64_t k = a + lane; k < b; k += 32) {
+    for (int64_t k = a + threadIdx.x; k < b; k += blockDim.x) {
         const float t = tgt.values ? tgt.values[k] : 1.f;
-        float* q = PT + (int64_t)tgt.indices[k] * ldp + warp;
+        float* q = PT + (int64_t)tgt.indices[k] * ldp + u;
         const float p = *q;
         acc = fmaf(t, logf(p / rs), acc);
         *q = tf32_rn(p - t * inv_Bg);
     }
     acc = warp_sum(acc);
-    if (lane == 0) loss_row[warp] = -acc;
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) loss_row[u] = -((sh[0] + sh[1]) + (sh[2] + sh[3]));
 }
 
 int launch_target_fixup(Ctx* c, const BatchView& tgt, float* PT, int64_t ldp, const float* rowscale, float inv_Bg,
                         float* loss_row, cudaStream_t s) {
     if (tgt.B == 0) return 0;
-    int threads = 256;
-    k_target_fixup<<<(int)cdiv((int64_t)tgt.B * 32, threads), threads, 0, s>>>(tgt, PT, ldp, rowscale, inv_Bg, loss_row);
+    k_target_fixup<<<tgt.B, 128, 0, s>>>(tgt, PT, ldp, rowscale, inv_Bg, loss_row);
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
