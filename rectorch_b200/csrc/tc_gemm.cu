@@ -57,9 +57,11 @@ template <bool CG2> struct TcCfg {
     static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
     static constexpr int STAGES = TC_PIPE_BYTES / STAGE_BYTES;
 };
-constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_EPI_THREADS = 32 * TC_EPI_WARPS;
-constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
+// Epilogue warps per CTA: 2 per TMEM lane quarter for the register-hungry log-sum-exp epilogue (measured:
+// 4 per quarter caps it at 96 registers and costs 15 %), 4 per quarter for the store-heavy epilogues
+// (softmax / plain store: more stores in flight, -9 %).  Warps sharing a quarter interleave the 32-column chunks.
+__host__ __device__ constexpr int tc_epi_warps(int mode) { return mode == TC_EPI_LSE ? 8 : 16; }
+__host__ __device__ constexpr int tc_threads(int mode) { return 64 + 32 * tc_epi_warps(mode); }
 constexpr int TC_BAR_BYTES = 256;
 constexpr int TC_BIAS_BYTES = 2 * 256 * 4;
 constexpr int TC_SMEM = TC_PIPE_BYTES + 1024 /*align*/ + TC_BAR_BYTES + TC_BIAS_BYTES;
@@ -338,8 +340,11 @@ __device__ __forceinline__ void epi_chunk(const TcArgs& a, const float* v, const
 }
 
 template <int MODE, bool A_MN, bool B_MN, bool CG2>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads(MODE), 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    constexpr int TC_EPI_WARPS = tc_epi_warps(MODE);
+    constexpr int TC_EPI_SUB = TC_EPI_WARPS / 4;
+    constexpr int TC_EPI_THREADS = 32 * TC_EPI_WARPS;
     constexpr int TC_STAGES = TcCfg<CG2>::STAGES;
     constexpr int TC_STAGE_BYTES = TcCfg<CG2>::STAGE_BYTES;
     constexpr int NCTA = CG2 ? 2 : 1;
@@ -486,7 +491,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     } else if (warp >= 2) {
         // =============================== epilogue ===================================
         const int q = warp & 3;                         // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;               // which of the two warps of that quarter
+        const int half = (warp - 2) >> 2;               // which of the TC_EPI_SUB warps of that quarter
         const int et = threadIdx.x - 64;                // 0..255
         const int row_in_tile = q * 32 + lane;
         int acc = 0;
@@ -500,32 +505,32 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int nch = (n_valid + 31) >> 5;
             // the tile's bias slice travels global -> register while the MMAs are still running
             float bias_reg = 0.f;
-            if (a.bias != nullptr && et < n_valid) bias_reg = __ldg(a.bias + n0 + et);
+            if (a.bias != nullptr && et < n_valid && et < 256) bias_reg = __ldg(a.bias + n0 + et);
             float lse_l2 = 0.f, rs_m = 0.f;
             if (MODE == TC_EPI_PROB && m < a.M) { lse_l2 = a.lse[m] * LOG2E_F; rs_m = a.rowscale[m]; }
             mbar_wait(tfull_bar(acc), acc_phase);
             tcgen05_fence_after();
             float* bias_s = bias_smem + acc * 256;
-            bias_s[et] = bias_reg;
+            if (et < 256) bias_s[et] = bias_reg;
             asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
             float run_max = -INFINITY, run_sum = 0.f;
             float va[32], vb[32];
             int c = half;
             if (c < nch) tmem_ld32_issue(taddr + (uint32_t)(c * 32), va);
-            for (; c < nch; c += 4) {
+            for (; c < nch; c += 2 * TC_EPI_SUB) {
                 tmem_wait_ld(va);
-                if (c + 2 < nch) tmem_ld32_issue(taddr + (uint32_t)((c + 2) * 32), vb);
+                if (c + TC_EPI_SUB < nch) tmem_ld32_issue(taddr + (uint32_t)((c + TC_EPI_SUB) * 32), vb);
                 epi_chunk<MODE>(a, va, bias_s, c * 32, min(32, n_valid - c * 32), n0, m, tc.sp, run_max, run_sum, lse_l2, rs_m);
-                if (c + 2 < nch) {
+                if (c + TC_EPI_SUB < nch) {
                     tmem_wait_ld(vb);
-                    if (c + 4 < nch) tmem_ld32_issue(taddr + (uint32_t)((c + 4) * 32), va);
-                    epi_chunk<MODE>(a, vb, bias_s, (c + 2) * 32, min(32, n_valid - (c + 2) * 32), n0, m, tc.sp, run_max,
+                    if (c + 2 * TC_EPI_SUB < nch) tmem_ld32_issue(taddr + (uint32_t)((c + 2 * TC_EPI_SUB) * 32), va);
+                    epi_chunk<MODE>(a, vb, bias_s, (c + TC_EPI_SUB) * 32, min(32, n_valid - (c + TC_EPI_SUB) * 32), n0, m, tc.sp, run_max,
                                     run_sum, lse_l2, rs_m);
                 }
             }
             if (MODE == TC_EPI_LSE && m < a.M) {
-                const int64_t pi = (int64_t)(tc.n_idx * 2 + half) * a.M + m;
+                const int64_t pi = (int64_t)(tc.n_idx * TC_EPI_SUB + half) * a.M + m;
                 a.part_max[pi] = run_max;
                 a.part_sum[pi] = run_sum;
             }
@@ -607,7 +612,7 @@ static int pick_bn(int N, bool b_mn) {
     return (int)std::min<int64_t>(256, round_up(cdiv(N, tiles), g));
 }
 // number of (max, sum) partial rows the LSE epilogue writes per user: two warps per 256-item tile
-int tc_lse_tiles(int N) { return 2 * (int)cdiv(N, pick_bn(N, false)); }
+int tc_lse_tiles(int N) { return (tc_epi_warps(TC_EPI_LSE) / 4) * (int)cdiv(N, pick_bn(N, false)); }
 
 int tc_output_tiles(int M, int N, int b_mn) {
     return (int)(cdiv(M, use_cg2() ? 2 * TC_BM : TC_BM) * cdiv(N, pick_bn(N, b_mn != 0)));
@@ -623,7 +628,7 @@ static int launch_inst2(const CUtensorMap& tmA, const CUtensorMap& tmB, const Tc
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(tc_threads(MODE));
     cfg.dynamicSmemBytes = TC_SMEM;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
