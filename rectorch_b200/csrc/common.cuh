@@ -85,7 +85,7 @@ int launch_batch_scan(Ctx* c, const int64_t* indptr, const int32_t* row_ids, int
                       int64_t* bp, int32_t* sp, cudaStream_t s);
 int launch_batch_prep(Ctx* c, const BatchView& in, float p, uint64_t seed, uint64_t step,
                       int64_t row_offset, const uint8_t* keep_tape, bool train, float* xt, float* row_sum_out,
-                      cudaStream_t s);
+                      int32_t* mark, int32_t mark_step, cudaStream_t s);
 int launch_target_fixup(Ctx* c, const BatchView& tgt, float* PT, int64_t ldp, const float* rowscale, float inv_Bg,
                         float* loss_row, cudaStream_t s);
 int launch_spmm_zero(Ctx* c, const BatchView& v, const float* vals, int H, float* dWt, cudaStream_t s);
@@ -126,10 +126,26 @@ int launch_loss_final(Ctx* c, const float* loss_row, const float* kl_row, int B,
                       cudaStream_t s);
 int launch_tensor_norms(Ctx* c, const float* w, const int64_t* offs, const int64_t* lens,
                         int n_tensors, float* partial, float* norms, cudaStream_t s);
+// Row filter + launch footprint of one Adam launch.  Elements inside the re-zero window [z_lo, z_hi) (the
+// encoder-0 weight, rows of `row_len` floats) are filtered by the per-row step marks batch_prep wrote:
+//   ADAM_ROWS_ALL       every row (gradient read from g)
+//   ADAM_ROWS_MARKED    only rows with mark == mark_step (the rows this step's sparse scatter wrote)
+//   ADAM_ROWS_UNMARKED  only the other rows; their gradient is exactly zero, so g is neither read nor re-zeroed
+// ctas_per_sm x threads is the grid-stride footprint: the full-width default for a launch that owns the GPU,
+// a narrow one for launches that share it with the other stream's kernels.
+enum { ADAM_ROWS_ALL = 0, ADAM_ROWS_MARKED = 1, ADAM_ROWS_UNMARKED = 2 };
+struct AdamOpt {
+    const int32_t* mark = nullptr;
+    int32_t mark_step = 0;
+    int filter = ADAM_ROWS_ALL;
+    int row_len = 0;
+    int ctas_per_sm = 8;
+    int threads = 256;
+};
 int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float lr_over_bc1,
                 float beta1, float beta2, float bc2_sqrt, float eps, float wd, float lam,
                 const float* norm_ptr, float* shadow, int64_t sh_lo, int64_t sh_hi, int64_t z_lo, int64_t z_hi,
-                cudaStream_t s);
+                const AdamOpt& opt, cudaStream_t s);
 int launch_round_tf32(Ctx* c, const float* x, float* y, int64_t n, cudaStream_t s);
 int launch_tanh_grad(Ctx* c, float* d, const float* y, int64_t n, cudaStream_t s);
 int launch_axpy(Ctx* c, float* y, const float* x, float a, int64_t n, cudaStream_t s);

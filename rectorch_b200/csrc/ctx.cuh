@@ -82,6 +82,18 @@ struct Ctx {
     bool use_tc = true;
     bool tc_dec = false;              // decoder-last shapes are tcgen05-eligible
     cudaEvent_t ev_wd = nullptr;      // recorded when dW_d / db_d (tail of the gradient arena) are final
+
+    // Single-GPU fused step: Adam work that does not depend on the end of the backward pass runs on a second
+    // stream, in narrow launches that share the SMs with the small kernels of the main stream (engine.cu,
+    // train_step_fused).  `mark[j]` = last step whose batch read / wrote row j of the encoder-0 weight.
+    int32_t* mark = nullptr;          // [n_items]
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_mark = nullptr;    // marks of the current step are written
+    cudaEvent_t ev_side = nullptr;    // side-stream Adam of the current step is complete
+    int overlap = 3;                  // bit 0: decoder-output Adam beside the encoder backward; bit 1: untouched
+                                      // encoder-0 rows beside the forward pass (B200VAE_OVERLAP)
+    int side_ctas[2] = {2, 2};        // CTAs per SM of the two side launches (B200VAE_SIDE_CTAS="a,b")
+    int side_threads = 256;
 };
 
 // bookkeeping after every kernel launch: launch counter + (timing mode) an event named after the launcher

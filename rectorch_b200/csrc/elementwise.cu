@@ -1,4 +1,5 @@
 // elementwise.cu -- reparameterisation + KL, loss assembly, parameter norms and the fused Adam.
+#include <algorithm>
 #include "ctx.cuh"
 
 namespace b200 {
@@ -183,12 +184,15 @@ __device__ __forceinline__ void adam_one(float& w, float g, float& m, float& v, 
     w = __fadd_rn(w, __fdiv_rn(__fmul_rn(neg_step, m), denom));
 }
 
-template <bool EXTRAS>
+// FILTER (see AdamOpt): rows of the re-zero window [z_lo, z_hi) are selected by their step mark; elements outside
+// the window are always processed.  z_lo and row_len are multiples of 4 when FILTER != 0, so a float4 never
+// straddles two rows.
+template <bool EXTRAS, int FILTER>
 __global__ void __launch_bounds__(256)
 k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
        int64_t n, float neg_step, float b1c, float b2, float b2c, float bc2_sqrt, float eps, float wd,
        float lam, const float* __restrict__ norm_ptr, float* __restrict__ shadow, int64_t sh_lo, int64_t sh_hi,
-       int64_t z_lo, int64_t z_hi) {
+       int64_t z_lo, int64_t z_hi, const int32_t* __restrict__ mark, int32_t mark_step, int row_len) {
     float reg = 0.f;
     if (EXTRAS && norm_ptr) {
         float nrm = *norm_ptr;
@@ -201,7 +205,19 @@ k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, floa
     float4* m4 = reinterpret_cast<float4*>(m);
     float4* v4 = reinterpret_cast<float4*>(v);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        float4 ww = w4[i], gg = __ldcs(g4 + i), mm = m4[i], vv = v4[i];
+        const int64_t e0 = i << 2;
+        const bool in_z = e0 >= z_lo && e0 < z_hi;
+        bool zero_g = false;
+        if (FILTER != ADAM_ROWS_ALL && in_z) {
+            const bool marked = mark[(e0 - z_lo) / row_len] == mark_step;
+            if (FILTER == ADAM_ROWS_MARKED && !marked) continue;
+            if (FILTER == ADAM_ROWS_UNMARKED) {
+                if (marked) continue;
+                zero_g = true;          // no scatter reached this row: its gradient is +0 and stays in memory as such
+            }
+        }
+        float4 ww = w4[i], mm = m4[i], vv = v4[i];
+        float4 gg = zero_g ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcs(g4 + i);
         adam_one(ww.x, gg.x, mm.x, vv.x, neg_step, b1c, b2, b2c, bc2_sqrt, eps, EXTRAS ? wd : 0.f, reg);
         adam_one(ww.y, gg.y, mm.y, vv.y, neg_step, b1c, b2, b2c, bc2_sqrt, eps, EXTRAS ? wd : 0.f, reg);
         adam_one(ww.z, gg.z, mm.z, vv.z, neg_step, b1c, b2, b2c, bc2_sqrt, eps, EXTRAS ? wd : 0.f, reg);
@@ -209,10 +225,9 @@ k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, floa
         w4[i] = ww;
         m4[i] = mm;
         v4[i] = vv;
-        const int64_t e0 = i << 2;
         // the encoder-0 gradient is accumulated by sparse scatters into an all-zero buffer: restore the zeros
         // here, touching only the (few) rows that actually received a gradient
-        if (e0 >= z_lo && e0 < z_hi && (gg.x != 0.f || gg.y != 0.f || gg.z != 0.f || gg.w != 0.f))
+        if (in_z && !zero_g && (gg.x != 0.f || gg.y != 0.f || gg.z != 0.f || gg.w != 0.f))
             g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (shadow && e0 >= sh_lo && e0 < sh_hi)   // tf32 image of W_d for the tensor-core GEMMs
             *reinterpret_cast<float4*>(shadow + (e0 - sh_lo)) =
@@ -220,10 +235,20 @@ k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, floa
     }
     // tail (n not a multiple of 4)
     for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const bool in_z = i >= z_lo && i < z_hi;
+        bool zero_g = false;
+        if (FILTER != ADAM_ROWS_ALL && in_z) {
+            const bool marked = mark[(i - z_lo) / row_len] == mark_step;
+            if (FILTER == ADAM_ROWS_MARKED && !marked) continue;
+            if (FILTER == ADAM_ROWS_UNMARKED) {
+                if (marked) continue;
+                zero_g = true;
+            }
+        }
         float ww = w[i], mm = m[i], vv = v[i];
-        const float gi = g[i];
+        const float gi = zero_g ? 0.f : g[i];
         adam_one(ww, gi, mm, vv, neg_step, b1c, b2, b2c, bc2_sqrt, eps, EXTRAS ? wd : 0.f, reg);
-        if (i >= z_lo && i < z_hi && gi != 0.f) g[i] = 0.f;
+        if (in_z && gi != 0.f) g[i] = 0.f;
         w[i] = ww;
         m[i] = mm;
         v[i] = vv;
@@ -234,20 +259,35 @@ k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, floa
 int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float lr_over_bc1,
                 float beta1, float beta2, float bc2_sqrt, float eps, float wd, float lam,
                 const float* norm_ptr, float* shadow, int64_t sh_lo, int64_t sh_hi, int64_t z_lo, int64_t z_hi,
-                cudaStream_t s) {
+                const AdamOpt& opt, cudaStream_t s) {
     if (n == 0) return 0;
     B200_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(m) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0,
                  B200VAE_EINVAL, "adam: arenas must be 16-byte aligned");
-    // persistent-style grid: a multiple of the SM count, 8 CTAs of 256 threads per SM
-    int64_t want = cdiv(std::max<int64_t>(n >> 2, 1), 256);
-    int blocks = (int)std::min<int64_t>(want, (int64_t)c->num_sms * 8);
+    const int filter = (z_hi > z_lo) ? opt.filter : ADAM_ROWS_ALL;
+    if (filter != ADAM_ROWS_ALL)
+        B200_REQUIRE(opt.mark && opt.row_len > 0 && opt.row_len % 4 == 0 && z_lo % 4 == 0, B200VAE_EINVAL,
+                     "adam: the row filter needs step marks and 16-byte aligned rows");
+    // persistent-style grid: a multiple of the SM count (default 8 CTAs of 256 threads per SM)
+    const int threads = std::min(256, std::max(32, opt.threads & ~31));
+    int64_t want = cdiv(std::max<int64_t>(n >> 2, 1), threads);
+    int blocks = (int)std::min<int64_t>(want, (int64_t)c->num_sms * std::max(1, opt.ctas_per_sm));
     bool extras = (wd != 0.f) || (lam != 0.f && norm_ptr);
     float b1c = 1.f - beta1, b2c = 1.f - beta2;
-    if (extras)
-        k_adam<true><<<blocks, 256, 0, s>>>(w, g, m, v, n, -lr_over_bc1, b1c, beta2, b2c, bc2_sqrt, eps, wd, lam, norm_ptr, shadow, sh_lo, sh_hi, z_lo, z_hi);
-    else
-        k_adam<false><<<blocks, 256, 0, s>>>(w, g, m, v, n, -lr_over_bc1, b1c, beta2, b2c, bc2_sqrt, eps, 0.f, 0.f, nullptr, shadow, sh_lo, sh_hi, z_lo, z_hi);
+#define ADAM_LAUNCH(EX, FI)                                                                                               \
+    k_adam<EX, FI><<<blocks, threads, 0, s>>>(w, g, m, v, n, -lr_over_bc1, b1c, beta2, b2c, bc2_sqrt, eps, EX ? wd : 0.f, \
+                                              EX ? lam : 0.f, EX ? norm_ptr : nullptr, shadow, sh_lo, sh_hi, z_lo, z_hi,  \
+                                              opt.mark, opt.mark_step, opt.row_len)
+    if (extras) {
+        if (filter == ADAM_ROWS_MARKED) ADAM_LAUNCH(true, ADAM_ROWS_MARKED);
+        else if (filter == ADAM_ROWS_UNMARKED) ADAM_LAUNCH(true, ADAM_ROWS_UNMARKED);
+        else ADAM_LAUNCH(true, ADAM_ROWS_ALL);
+    } else {
+        if (filter == ADAM_ROWS_MARKED) ADAM_LAUNCH(false, ADAM_ROWS_MARKED);
+        else if (filter == ADAM_ROWS_UNMARKED) ADAM_LAUNCH(false, ADAM_ROWS_UNMARKED);
+        else ADAM_LAUNCH(false, ADAM_ROWS_ALL);
+    }
+#undef ADAM_LAUNCH
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -50,6 +50,10 @@ static void free_ctx(Ctx* c) {
         for (int j = 0; j < 2; ++j) cudaEventDestroy(c->ev[i][j]);
     for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
     if (c->ev_wd) cudaEventDestroy(c->ev_wd);
+    if (c->ev_mark) cudaEventDestroy(c->ev_mark);
+    if (c->ev_side) cudaEventDestroy(c->ev_side);
+    if (c->side) cudaStreamDestroy(c->side);
+    F(c->mark);
     delete c;
 }
 
@@ -105,11 +109,29 @@ struct FwdState {
 };
 
 // encoder + reparameterisation + hidden decoder layers.  Leaves z and h_last in the ctx.
+struct AdamHyper {
+    float lr, beta1, beta2, eps, wd, lam;
+    int64_t step;
+};
+static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo = 0, int64_t r_hi = -1,
+                     int w1_filter = ADAM_ROWS_ALL, int ctas_per_sm = 8);
+
+// `fused` (single-GPU fused step only): batch_prep stamps the encoder-0 rows this step touches, and the Adam
+// update of all the OTHER rows -- zero gradient, not read by this step's gather -- starts right away on the side
+// stream, in a narrow launch that shares the SMs with the forward pass.
 static int forward_hidden(Ctx* c, FwdState* st, int B, bool train, float p, uint64_t seed, uint64_t step,
                           int64_t row_offset, const uint8_t* keep_tape, const float* eps_tape,
-                          float* row_sum_out, cudaStream_t s) {
-    B200_CHECK(launch_batch_prep(c, st->in, p, seed, step, row_offset, keep_tape, train, c->xt, row_sum_out, s));
+                          float* row_sum_out, cudaStream_t s, const AdamHyper* fused = nullptr) {
+    const bool split_rows = fused && (c->overlap & 2);
+    B200_CHECK(launch_batch_prep(c, st->in, p, seed, step, row_offset, keep_tape, train, c->xt, row_sum_out,
+                                 split_rows ? c->mark : nullptr, split_rows ? (int32_t)fused->step : 0, s));
     const Layer& e0 = c->enc[0];
+    if (split_rows) {
+        B200_CUDA_OK(cudaEventRecord(c->ev_mark, s));
+        B200_CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_mark, 0));
+        B200_CHECK(adam_step(c, *fused, c->side, e0.w_off, e0.w_off + (int64_t)e0.in * e0.out, ADAM_ROWS_UNMARKED,
+                             c->side_ctas[1]));
+    }
     B200_CHECK(launch_spmm_gather(c, st->in, c->xt, c->w + e0.w_off, e0.out, c->w + e0.b_off,
                                   e0.tanh_act ? 1 : 0, c->act_enc[0], s));
     for (size_t i = 1; i < c->enc.size(); ++i)
@@ -203,13 +225,19 @@ static int dec_lse(Ctx* c, const float* h, int B, int H, int* n_tiles, bool for_
 static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int use_target, float beta,
                             float lam, float p, uint64_t seed, uint64_t step, int64_t row_offset,
                             const uint8_t* keep_tape, const float* eps_tape, float* loss_out,
-                            cudaStream_t s) {
+                            cudaStream_t s, const AdamHyper* fused = nullptr) {
     B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
     B200_REQUIRE(B >= 1 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
     B200_REQUIRE(Bg >= B, B200VAE_EINVAL, "B_global (%d) < B (%d)", Bg, B);
     const int I = c->n_items;
     const float inv_Bg = 1.0f / (float)Bg;
     if (c->timing) { c->tcount = 0; note(c, "step_start", s); c->launches--; }
+    const bool dae_reg = (!c->cfg.is_vae) && lam != 0.f;
+    if (dae_reg) {
+        // before anything of this step can move a weight (the side stream updates untouched rows early)
+        B200_CHECK(launch_tensor_norms(c, c->w, c->d_toff, c->d_tlen, c->n_tensors, c->norm_partial, c->norms, s));
+        c->norms_valid = true;      // the weights do not change before this step's Adam: it reuses them
+    }
     FwdState st;
     B200_CHECK(make_view(c, 0, row_ids, B, &st.in, s));
     if (use_target) {
@@ -220,7 +248,7 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
     // ---------------- forward ----------------
     if (use_target) B200_CHECK(launch_row_sums(c, st.tgt, c->T, s));
     B200_CHECK(forward_hidden(c, &st, B, true, p, seed, step, row_offset, keep_tape, eps_tape,
-                              use_target ? nullptr : c->T, s));
+                              use_target ? nullptr : c->T, s, fused));
     const Layer& DL = c->dec.back();
     const int H = st.H;
     const float* Wd = c->w + DL.w_off;
@@ -236,11 +264,6 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         B200_CHECK(launch_spmm_gather(c, st.tgt, nullptr, Wd, H, nullptr, 0, c->gvec, s));
         B200_CHECK(launch_row_loss(c, st.tgt, st.h_last, c->gvec, H, c->w + DL.b_off, c->part_max, c->part_sum, n_lse_tiles,
                                    c->lse, c->T, inv_Bg, c->loss_row, c->rowscale, s));
-    }
-    const bool dae_reg = (!c->cfg.is_vae) && lam != 0.f;
-    if (dae_reg) {
-        B200_CHECK(launch_tensor_norms(c, c->w, c->d_toff, c->d_tlen, c->n_tensors, c->norm_partial, c->norms, s));
-        c->norms_valid = true;      // the weights do not change before this step's Adam: it reuses them
     }
 
     // ---------------- backward: decoder output layer ----------------
@@ -348,16 +371,18 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
     return 0;
 }
 
-// Adam over the arena range [r_lo, r_hi) (whole arena: 0, n_elems).  Ranges must not cut a tensor.
-static int adam_step(Ctx* c, float lr, float beta1, float beta2, float eps, float wd, float lam,
-                     int64_t step, cudaStream_t s, int64_t r_lo = 0, int64_t r_hi = -1) {
+// Adam over the arena range [r_lo, r_hi) (whole arena: 0, n_elems).  Ranges must not cut a tensor; the ranges
+// of one step are issued tail first and the range that starts at 0 closes the step.  `w1_filter` selects rows
+// of the encoder-0 weight by their step mark (AdamOpt), `ctas_per_sm` the width of the launch.
+static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo, int64_t r_hi, int w1_filter,
+                     int ctas_per_sm) {
     if (r_hi < 0) r_hi = c->n_elems;
     B200_REQUIRE(r_lo >= 0 && r_lo < r_hi && r_hi <= c->n_elems && r_lo % 4 == 0, B200VAE_EINVAL, "bad Adam range");
     B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
-    B200_REQUIRE(step >= 1, B200VAE_EINVAL, "adam step must be >= 1");
-    double bc1 = 1.0 - std::pow((double)beta1, (double)step);
-    double bc2 = 1.0 - std::pow((double)beta2, (double)step);
-    float step_size = (float)((double)lr / bc1);
+    B200_REQUIRE(h.step >= 1, B200VAE_EINVAL, "adam step must be >= 1");
+    double bc1 = 1.0 - std::pow((double)h.beta1, (double)h.step);
+    double bc2 = 1.0 - std::pow((double)h.beta2, (double)h.step);
+    float step_size = (float)((double)h.lr / bc1);
     float bc2_sqrt = (float)std::sqrt(bc2);
     tick(c, 1, 0, s);
     const Layer& DL = c->dec.back();
@@ -366,27 +391,72 @@ static int adam_step(Ctx* c, float lr, float beta1, float beta2, float eps, floa
     // Adam re-zeroes the encoder-0 gradient rows it consumed (sparse writes), so forward_backward never memsets
     const Layer& E0 = c->enc[0];
     const int64_t z_lo = E0.w_off, z_hi = E0.w_off + (int64_t)E0.in * E0.out;
-    if (wd == 0.f && lam == 0.f) {
+    AdamOpt opt;
+    opt.mark = c->mark;
+    opt.mark_step = (int32_t)h.step;
+    opt.filter = w1_filter;
+    opt.row_len = E0.out;
+    opt.ctas_per_sm = ctas_per_sm;
+    opt.threads = (ctas_per_sm < 8) ? c->side_threads : 256;
+    if (h.wd == 0.f && h.lam == 0.f) {
         // kernel indices are relative to the pointers it gets: shift the shadow / re-zero windows by r_lo
         // (the shadow pointer is pre-offset so that shadow[(e - r_lo) - (sh_lo - r_lo)] addresses element e - sh_lo)
-        B200_CHECK(launch_adam(c, c->w + r_lo, c->g + r_lo, c->m + r_lo, c->v + r_lo, r_hi - r_lo, step_size, beta1, beta2,
-                               bc2_sqrt, eps, 0.f, 0.f, nullptr, shadow, sh_lo - r_lo, sh_hi - r_lo, z_lo - r_lo, z_hi - r_lo, s));
+        const int64_t zl = std::max(z_lo, r_lo) - r_lo, zh = std::min(z_hi, r_hi) - r_lo;
+        B200_REQUIRE(w1_filter == ADAM_ROWS_ALL || zh <= zl || z_lo >= r_lo, B200VAE_EINVAL,
+                     "a filtered Adam range must start at or before the encoder-0 weight");
+        B200_CHECK(launch_adam(c, c->w + r_lo, c->g + r_lo, c->m + r_lo, c->v + r_lo, r_hi - r_lo, step_size, h.beta1,
+                               h.beta2, bc2_sqrt, h.eps, 0.f, 0.f, nullptr, shadow, sh_lo - r_lo, sh_hi - r_lo,
+                               z_lo - r_lo, z_hi - r_lo, opt, s));
     } else {
-        if (lam != 0.f && !c->norms_valid)
+        if (h.lam != 0.f && !c->norms_valid)
             B200_CHECK(launch_tensor_norms(c, c->w, c->d_toff, c->d_tlen, c->n_tensors, c->norm_partial, c->norms, s));
         for (int t = 0; t < c->n_tensors; ++t) {
             int64_t o = c->toff[t];
             if (o < r_lo || o >= r_hi) continue;
             const bool is_wd = (o == DL.w_off);
-            B200_CHECK(launch_adam(c, c->w + o, c->g + o, c->m + o, c->v + o, c->tlen[t], step_size, beta1,
-                                   beta2, bc2_sqrt, eps, wd, lam, lam != 0.f ? c->norms + t : nullptr,
+            B200_CHECK(launch_adam(c, c->w + o, c->g + o, c->m + o, c->v + o, c->tlen[t], step_size, h.beta1,
+                                   h.beta2, bc2_sqrt, h.eps, h.wd, h.lam, h.lam != 0.f ? c->norms + t : nullptr,
                                    is_wd ? shadow : nullptr, 0, is_wd ? c->tlen[t] : 0,
-                                   0, (o == z_lo) ? c->tlen[t] : 0, s));
+                                   0, (o == z_lo) ? c->tlen[t] : 0, opt, s));
         }
     }
     tick(c, 1, 1, s);
-    if (r_hi >= c->n_elems) c->norms_valid = false;      // last (or only) range of the step: weights have moved
-    if (r_lo <= z_lo && r_hi >= z_hi) c->dw1_clean = true;
+    if (r_lo == 0) c->norms_valid = false;      // last (or only) range of the step: weights have moved
+    if (w1_filter != ADAM_ROWS_UNMARKED && r_lo <= z_lo && r_hi >= z_hi) c->dw1_clean = true;
+    return 0;
+}
+
+// One single-GPU optimisation step.  Timeline (main stream | side stream):
+//   batch scan, batch_prep (stamps the touched encoder-0 rows)  | -
+//   encoder, decoder, loss, decoder-output backward (tcgen05)   | Adam of the untouched encoder-0 rows
+//   hidden-layer backward, sparse scatter                       | Adam of W_d, b_d (+ tf32 image), once dW_d is final
+//   Adam of the touched encoder-0 rows and the small tensors    |
+// The side launches are narrow grid-stride kernels (side_ctas CTAs per SM) so the small kernels of the main stream
+// run beside them; the tcgen05 kernels need whole SMs and simply start when a side launch has drained.  Every
+// element sees exactly the arithmetic of the one-launch Adam (same adam_one, gradient +0 for untouched rows).
+static int train_step_fused(Ctx* c, const int32_t* row_ids, int B, int use_target, float beta, float p, uint64_t seed,
+                            const uint8_t* keep_tape, const float* eps_tape, const AdamHyper& h, float* loss_out,
+                            cudaStream_t s) {
+    const Layer& E0 = c->enc[0];
+    int ov = (c->timing || !c->side) ? 0 : c->overlap;
+    if (E0.out % 4 != 0 || E0.w_off % 4 != 0) ov &= ~2;
+    if (!ov) {
+        B200_CHECK(forward_backward(c, row_ids, B, B, use_target, beta, h.lam, p, seed, (uint64_t)h.step, 0, keep_tape,
+                                    eps_tape, loss_out, s));
+        return adam_step(c, h, s);
+    }
+    B200_CHECK(forward_backward(c, row_ids, B, B, use_target, beta, h.lam, p, seed, (uint64_t)h.step, 0, keep_tape,
+                                eps_tape, loss_out, s, &h));
+    const int64_t cut = c->dec.back().w_off;
+    int64_t head_hi = c->n_elems;
+    if (ov & 1) {
+        B200_CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_wd, 0));
+        B200_CHECK(adam_step(c, h, c->side, cut, c->n_elems, ADAM_ROWS_ALL, c->side_ctas[0]));
+        head_hi = cut;
+    }
+    B200_CUDA_OK(cudaEventRecord(c->ev_side, c->side));
+    B200_CHECK(adam_step(c, h, s, 0, head_hi, (ov & 2) ? ADAM_ROWS_MARKED : ADAM_ROWS_ALL, 8));
+    B200_CUDA_OK(cudaStreamWaitEvent(s, c->ev_side, 0));
     return 0;
 }
 
@@ -456,6 +526,20 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventCreate(&c->ev[i][j]);
     cudaEventCreateWithFlags(&c->ev_wd, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_mark, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) c->side = nullptr;
+    if (const char* e = getenv("B200VAE_OVERLAP")) c->overlap = atoi(e) & 3;
+    if (const char* e = getenv("B200VAE_SIDE_CTAS")) {
+        int a = 0, b = 0;
+        int n = sscanf(e, "%d,%d", &a, &b);
+        if (n >= 1 && a >= 1 && a <= 8) c->side_ctas[0] = c->side_ctas[1] = a;
+        if (n >= 2 && b >= 1 && b <= 8) c->side_ctas[1] = b;
+    }
+    if (const char* e = getenv("B200VAE_SIDE_THREADS")) {
+        int t = atoi(e);
+        if (t >= 32 && t <= 256) c->side_threads = t & ~31;
+    }
     if (cfg->dec_dims[cfg->n_dec] != c->n_items || cfg->enc_dims[cfg->n_enc] != c->latent) {
         set_error("enc_dims/dec_dims are inconsistent (n_items %d vs %d, latent %d vs %d)", c->n_items,
                   cfg->dec_dims[cfg->n_dec], cfg->enc_dims[cfg->n_enc], c->latent);
@@ -511,6 +595,7 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     A_(dmalloc(&c->d_specs, 128));
     A_(dmalloc(&c->spmm_acc, Bm * std::max(c->max_width, H)));
     A_(dmalloc(&c->spmm_ticket, Bm));
+    A_(dmalloc(&c->mark, I));
     A_(dmalloc(&c->dbuf[0], Bm * c->max_width)); A_(dmalloc(&c->dbuf[1], Bm * c->max_width));
     c->n_lse_tiles = (int)std::max<int64_t>(cdiv(I, 64), 1);
     A_(dmalloc(&c->part_max, (int64_t)c->n_lse_tiles * Bm)); A_(dmalloc(&c->part_sum, (int64_t)c->n_lse_tiles * Bm));
@@ -523,6 +608,7 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     if (!rc && cudaMemset(c->d_err, 0, sizeof(int)) != cudaSuccess) rc = B200VAE_ECUDA;
     if (!rc && cudaMemset(c->spmm_acc, 0, (size_t)Bm * std::max(c->max_width, H) * sizeof(float)) != cudaSuccess) rc = B200VAE_ECUDA;
     if (!rc && cudaMemset(c->spmm_ticket, 0, (size_t)Bm * sizeof(int)) != cudaSuccess) rc = B200VAE_ECUDA;
+    if (!rc && cudaMemset(c->mark, 0, (size_t)I * sizeof(int32_t)) != cudaSuccess) rc = B200VAE_ECUDA;   // steps start at 1
     if (rc) { free_ctx(c); return rc; }
     *out = reinterpret_cast<b200vae_ctx*>(c);
     return 0;
@@ -612,7 +698,8 @@ int b200vae_adam_step_range(b200vae_ctx* ctx, float lr, float beta1, float beta2
                             float lam, int64_t step, int64_t elem_lo, int64_t elem_hi, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     B200_REQUIRE(c, B200VAE_EINVAL, "null context");
-    return adam_step(c, lr, beta1, beta2, eps, weight_decay, lam, step, (cudaStream_t)stream, elem_lo, elem_hi);
+    const AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
+    return adam_step(c, h, (cudaStream_t)stream, elem_lo, elem_hi);
 }
 
 int b200vae_sync_weights(b200vae_ctx* ctx, void* stream) {
@@ -629,7 +716,8 @@ int b200vae_adam_step(b200vae_ctx* ctx, float lr, float beta1, float beta2, floa
                       float lam, int64_t step, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     B200_REQUIRE(c, B200VAE_EINVAL, "null context");
-    return adam_step(c, lr, beta1, beta2, eps, weight_decay, lam, step, (cudaStream_t)stream);
+    const AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
+    return adam_step(c, h, (cudaStream_t)stream);
 }
 
 int b200vae_train_step(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int use_target, float beta,
@@ -639,9 +727,9 @@ int b200vae_train_step(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int 
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     B200_REQUIRE(c && loss_out, B200VAE_EINVAL, "null argument");
     B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, B200VAE_EINVAL, "dropout_p must be in [0,1)");
-    B200_CHECK(forward_backward(c, row_ids, B, B, use_target, beta, lam, dropout_p, seed, (uint64_t)step, 0,
-                                keep_tape, eps_tape, loss_out, (cudaStream_t)stream));
-    return adam_step(c, lr, beta1, beta2, eps, weight_decay, lam, step, (cudaStream_t)stream);
+    const AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
+    return train_step_fused(c, row_ids, B, use_target, beta, dropout_p, seed, keep_tape, eps_tape, h, loss_out,
+                            (cudaStream_t)stream);
 }
 
 // ---- context-free helpers used by rectorch_b200.metrics / models.loss_function ---------------
@@ -717,8 +805,8 @@ int b200vae_train_step_host(b200vae_ctx* ctx, const int64_t* indptr_host, const 
     if (values_host)
         B200_CUDA_OK(cudaMemcpyAsync(S.int_values, values_host, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, s));
     S.int_has_values = values_host != nullptr;
-    B200_CHECK(forward_backward(c, nullptr, B, B, 0, beta, lam, dropout_p, seed, (uint64_t)step, 0, nullptr, nullptr, c->loss_dev, s));
-    B200_CHECK(adam_step(c, lr, 0.9f, 0.999f, 1e-8f, weight_decay, lam, step, s));
+    const AdamHyper h = {lr, 0.9f, 0.999f, 1e-8f, weight_decay, lam, step};
+    B200_CHECK(train_step_fused(c, nullptr, B, 0, beta, dropout_p, seed, nullptr, nullptr, h, c->loss_dev, s));
     B200_CUDA_OK(cudaMemcpyAsync(loss_host, c->loss_dev, 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
     return 0;

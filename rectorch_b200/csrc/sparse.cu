@@ -108,7 +108,8 @@ int launch_scan_i64(Ctx* c, const int64_t* lens, int n, int64_t cap, int64_t* ou
 // ------------------------------------------------------------------------------------------
 __global__ void k_batch_prep(BatchView v, float p, uint64_t seed, uint64_t step, int64_t row_offset,
                              const uint8_t* __restrict__ keep_tape, int train, int64_t cap,
-                             float* __restrict__ xt, float* __restrict__ row_sum_out) {
+                             float* __restrict__ xt, float* __restrict__ row_sum_out,
+                             int32_t* __restrict__ mark, int32_t mark_step) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= v.B) return;
@@ -148,17 +149,20 @@ __global__ void k_batch_prep(BatchView v, float p, uint64_t seed, uint64_t step,
             xn = keep ? xn * inv_keep : 0.f;
         }
         xt[o + (k - a)] = xn;
+        // item rows of encoder layer 0 that this step reads (gather) and whose gradient it writes (scatter):
+        // every other row has an exactly-zero gradient, which lets Adam update it off the critical path
+        if (mark && xn != 0.f) mark[v.indices[k]] = mark_step;
     }
 }
 
 int launch_batch_prep(Ctx* c, const BatchView& in, float p, uint64_t seed, uint64_t step,
                       int64_t row_offset, const uint8_t* keep_tape, bool train, float* xt, float* row_sum_out,
-                      cudaStream_t s) {
+                      int32_t* mark, int32_t mark_step, cudaStream_t s) {
     if (in.B == 0) return 0;
     int threads = 256;
     int blocks = (int)cdiv((int64_t)in.B * 32, threads);
     k_batch_prep<<<blocks, threads, 0, s>>>(in, p, seed, step, row_offset, keep_tape, train ? 1 : 0,
-                                            c->cfg.max_batch_nnz, xt, row_sum_out);
+                                            c->cfg.max_batch_nnz, xt, row_sum_out, mark, mark_step);
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -229,7 +229,8 @@ struct TcArgs {
     const float* rowscale;
     float* bias_grad;
     int vec_ok;             // C rows are 16 B aligned
-    int dbg;                // B200VAE_TC_DBG: 1 = no operand loads (MMA issue-rate probe, garbage results)
+    int dbg;                // B200VAE_TC_DBG bit mask (probes, garbage results): 1 = no operand loads,
+                            // 2 = epilogue only waits and releases the accumulator, 4 = no MMAs are issued
 };
 
 struct TileCoord { int m_idx, n_idx, sp; };
@@ -471,6 +472,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     for (int j = 0; j < TC_BK / 8; ++j) {
                         const uint64_t ad = A_MN ? make_sdesc(sa + j * 1024, 4096, 512, 1) : make_sdesc(sa + j * 32, 0, 1024, 2);
                         const uint64_t bd = B_MN ? make_sdesc(sb + j * 1024, 4096, 512, 1) : make_sdesc(sb + j * 32, 0, 1024, 2);
+                        if (a.dbg & 4) continue;
                         if (CG2) tcgen05_mma_tf32_cg2(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
                         else     tcgen05_mma_tf32(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
                     }
@@ -516,7 +518,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
             float run_max = -INFINITY, run_sum = 0.f;
             float va[32], vb[32];
-            int c = half;
+            int c = (a.dbg & 2) ? nch : half;
             if (c < nch) tmem_ld32_issue(taddr + (uint32_t)(c * 32), va);
             for (; c < nch; c += 2 * TC_EPI_SUB) {
                 tmem_wait_ld(va);
@@ -529,7 +531,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                     run_sum, lse_l2, rs_m);
                 }
             }
-            if (MODE == TC_EPI_LSE && m < a.M) {
+            if (MODE == TC_EPI_LSE && m < a.M && !(a.dbg & 2)) {
                 const int64_t pi = (int64_t)(tc.n_idx * TC_EPI_SUB + half) * a.M + m;
                 a.part_max[pi] = run_max;
                 a.part_sum[pi] = run_sum;
