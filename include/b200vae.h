@@ -140,6 +140,16 @@ int  b200vae_adam_step_range(b200vae_ctx* ctx, float lr, float beta1, float beta
                              float weight_decay, float lam, int64_t step, int64_t elem_lo, int64_t elem_hi,
                              void* stream);
 
+/* The Adam schedule of the fused single-GPU step, on gradients that are already in the gradient arena:
+ * rows of the encoder-0 weight NOT listed in touched_items have an exactly-zero gradient and are updated by a
+ * launch of their own on the context's side stream (overlap_bits & 2), the decoder-output tensors by another
+ * (overlap_bits & 1), the rest on `stream`; the call joins both streams before it returns control of `stream`.
+ * Every element gets the arithmetic of b200vae_adam_step bit for bit (tests/test_gpu_overlap.py).
+ * Replaces: torch.optim.Adam.step as configured in models.py:657-659, 768-770. */
+int  b200vae_adam_step_split(b200vae_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay,
+                             float lam, int64_t step, const int32_t* touched_items, int32_t n_touched,
+                             int overlap_bits, void* stream);
+
 /* forward_backward + adam_step in one call (single-GPU fast path). */
 int  b200vae_train_step(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int use_target,
                         float beta, float lam, float dropout_p, uint64_t seed, int64_t step,
@@ -212,7 +222,9 @@ int  b200vae_gemm_tf32(b200vae_ctx* ctx, const float* A, int64_t lda, int a_mn_m
 
 /* K4 standalone: lse[r] = log sum_j exp(h[r,:].W[j,:] + b[j]) for r < B without
  * materialising the [B x n_items] logits (F.log_softmax over the decoder output,
- * models.py:813 / nets.py:417).  h [B x H] row-major, W [n_items x H] row-major. */
+ * models.py:813 / nets.py:417).  h [B x H] row-major, W [n_items x H] row-major.
+ * lse == NULL launches only the fused GEMM + log-sum-exp kernel (the per-tile partials stay in
+ * the context's workspace): used to time that kernel back to back. */
 int  b200vae_dec_fwd_lse(b200vae_ctx* ctx, const float* h, const float* W, const float* bias,
                          int32_t B, int32_t n_items, int32_t H, float* lse, void* stream);
 
@@ -229,6 +241,24 @@ int  b200vae_set_timing(b200vae_ctx* ctx, int enable);
  * Returns the number of events. */
 int  b200vae_timing_report(b200vae_ctx* ctx, char* buf, int cap);
 float b200vae_kernel_ms(b200vae_ctx* ctx, int which);
+
+/* ---- data ingest (host side): pre-processed rating files -> canonical CSR ------------------------------
+ * Replaces pd.read_csv + scipy.sparse.csr_matrix((values, (rows, cols))) in DataReader._load_train_data /
+ * _load_train_test_data (data.py:363-409).  The file has a header line "uid,iid[,<value>,...]" and one
+ * rating per line; it is parsed by n_threads host threads (0 = all).  All pointers below are HOST pointers. */
+typedef struct b200vae_csv b200vae_csv;
+int  b200vae_csv_open(b200vae_csv** out, const char* path, char sep, int n_threads);
+/* record count, column count of the header, min / max of the uid column, max of the iid column */
+int  b200vae_csv_info(const b200vae_csv* csv, int64_t* n_records, int32_t* n_cols, int64_t* uid_min,
+                      int64_t* uid_max, int64_t* iid_max);
+/* name of the third column (the one DataReader takes the values from when cfg.topn is false, data.py:373) */
+const char* b200vae_csv_value_column(const b200vae_csv* csv);
+/* CSR of shape [n_rows x n_cols] with row = uid - uid_base: indices sorted inside a row, duplicate
+ * (row, col) records summed (scipy's canonical form).  use_values = 0 -> every record counts 1.0 (cfg.topn).
+ * indptr_host [n_rows+1]; indices_host / values_host sized for the record count; *nnz_out = entries written. */
+int  b200vae_csv_to_csr(const b200vae_csv* csv, int64_t uid_base, int64_t n_rows, int32_t n_cols, int use_values,
+                        int64_t* indptr_host, int32_t* indices_host, double* values_host, int64_t* nnz_out);
+int  b200vae_csv_close(b200vae_csv* csv);
 
 #ifdef __cplusplus
 }

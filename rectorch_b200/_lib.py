@@ -51,6 +51,8 @@ _SIGS = {
                                   c_int64, c_void_p]),
     "b200vae_adam_step_range": (c_int, [c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
                                         c_int64, c_int64, c_int64, c_void_p]),
+    "b200vae_adam_step_split": (c_int, [c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
+                                        c_int64, c_void_p, c_int32, c_int, c_void_p]),
     "b200vae_train_step": (c_int, [c_void_p, c_void_p, c_int32, c_int, c_float, c_float, c_float,
                                    c_uint64, c_int64, c_void_p, c_void_p, c_float, c_float, c_float,
                                    c_float, c_float, c_void_p, c_void_p]),
@@ -79,6 +81,13 @@ _SIGS = {
     "b200vae_set_timing": (c_int, [c_void_p, c_int]),
     "b200vae_kernel_ms": (c_float, [c_void_p, c_int]),
     "b200vae_timing_report": (c_int, [c_void_p, c_char_p, c_int]),
+    "b200vae_csv_open": (c_int, [POINTER(c_void_p), c_char_p, ctypes.c_char, c_int]),
+    "b200vae_csv_info": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int32), POINTER(c_int64),
+                                 POINTER(c_int64), POINTER(c_int64)]),
+    "b200vae_csv_value_column": (c_char_p, [c_void_p]),
+    "b200vae_csv_to_csr": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int, c_void_p, c_void_p, c_void_p,
+                                   POINTER(c_int64)]),
+    "b200vae_csv_close": (c_int, [c_void_p]),
 }
 
 EXPORTS = tuple(sorted(_SIGS))

@@ -175,7 +175,7 @@ bool tc_supported(int M, int N, int K, int64_t lda, int64_t ldb);
 int launch_tc_gemm(Ctx* c, int mode, const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb,
                    int b_mn, float* C, int64_t ldc, int M, int N, int K, const TcEpi& e,
                    cudaStream_t s);
-int tc_lse_tiles(int N);
+int tc_lse_tiles(int M, int N, int num_sms);   // (max, sum) partial rows per user the LSE epilogue writes
 int tc_output_tiles(int M, int N, int b_mn);   // output tiles of the current tiling (pair tiles in CTA-pair mode)
 int tc_parallel_tiles(int num_sms);            // tiles that run concurrently (SMs, or SM pairs)
 int launch_splitk_reduce(Ctx* c, const float* parts, int n_split, int64_t split_stride, float* out,

@@ -90,8 +90,10 @@ struct Ctx {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_mark = nullptr;    // marks of the current step are written
     cudaEvent_t ev_side = nullptr;    // side-stream Adam of the current step is complete
-    int overlap = 3;                  // bit 0: decoder-output Adam beside the encoder backward; bit 1: untouched
-                                      // encoder-0 rows beside the forward pass (B200VAE_OVERLAP)
+    int overlap = 1;                  // bit 0: decoder-output Adam beside the encoder backward (default);
+                                      // bit 1: untouched encoder-0 rows beside the forward pass -- measured slower
+                                      // (the tcgen05 kernels wait for the narrow launch), kept for experiments
+                                      // (B200VAE_OVERLAP)
     int side_ctas[2] = {2, 2};        // CTAs per SM of the two side launches (B200VAE_SIDE_CTAS="a,b")
     int side_threads = 256;
 };

@@ -112,6 +112,7 @@ struct FwdState {
 struct AdamHyper {
     float lr, beta1, beta2, eps, wd, lam;
     int64_t step;
+    int ov = 0;           // effective overlap bits of the fused step this update belongs to (0 = serial)
 };
 static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo = 0, int64_t r_hi = -1,
                      int w1_filter = ADAM_ROWS_ALL, int ctas_per_sm = 8);
@@ -122,7 +123,7 @@ static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo = 
 static int forward_hidden(Ctx* c, FwdState* st, int B, bool train, float p, uint64_t seed, uint64_t step,
                           int64_t row_offset, const uint8_t* keep_tape, const float* eps_tape,
                           float* row_sum_out, cudaStream_t s, const AdamHyper* fused = nullptr) {
-    const bool split_rows = fused && (c->overlap & 2);
+    const bool split_rows = fused && (fused->ov & 2);
     B200_CHECK(launch_batch_prep(c, st->in, p, seed, step, row_offset, keep_tape, train, c->xt, row_sum_out,
                                  split_rows ? c->mark : nullptr, split_rows ? (int32_t)fused->step : 0, s));
     const Layer& e0 = c->enc[0];
@@ -209,14 +210,18 @@ static int dec_lse(Ctx* c, const float* h, int B, int H, int* n_tiles, bool for_
         e.bias = b;
         e.part_max = c->part_max;
         e.part_sum = c->part_sum;
+        tick(c, 0, 0, s);      // K4 proper: the tcgen05 GEMM + log-sum-exp kernel alone (operand prep is outside)
         B200_CHECK(launch_tc_gemm(c, TC_EPI_LSE, c->h_r, H, 0, c->wd_shadow, H, 0, nullptr, 0, B, I, H, e, s));
-        *n_tiles = tc_lse_tiles(I);
+        tick(c, 0, 1, s);
+        *n_tiles = tc_lse_tiles(B, I, c->num_sms);
     } else {
         GemmEpi e;
         e.bias = b;
         e.part_max = c->part_max;
         e.part_sum = c->part_sum;
+        tick(c, 0, 0, s);
         B200_CHECK(launch_simt_gemm(c, EPI_LSE, h, H, 1, W, 1, H, nullptr, 0, B, I, H, e, s));
+        tick(c, 0, 1, s);
         *n_tiles = (int)cdiv(I, 64);
     }
     return 0;
@@ -253,9 +258,7 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
     const int H = st.H;
     const float* Wd = c->w + DL.w_off;
     int n_lse_tiles = 0;
-    tick(c, 0, 0, s);
     B200_CHECK(dec_lse(c, st.h_last, B, H, &n_lse_tiles, true, s));
-    tick(c, 0, 1, s);
     if (c->tc_dec) {
         // merge the LSE partials, T/B; the sparse loss term is taken from P^T after the recompute kernel (target_fixup)
         B200_CHECK(launch_row_loss(c, st.tgt, st.h_last, nullptr, H, c->w + DL.b_off, c->part_max, c->part_sum, n_lse_tiles,
@@ -421,7 +424,10 @@ static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo, i
         }
     }
     tick(c, 1, 1, s);
-    if (r_lo == 0) c->norms_valid = false;      // last (or only) range of the step: weights have moved
+    // the range that starts at 0 and reads gradients is the last (or only) one of a step: the weights have moved.
+    // (The untouched-row launch also starts at 0 but runs first; invalidating there would make the closing launch
+    // recompute the norms from half-updated weights.)
+    if (r_lo == 0 && w1_filter != ADAM_ROWS_UNMARKED) c->norms_valid = false;
     if (w1_filter != ADAM_ROWS_UNMARKED && r_lo <= z_lo && r_hi >= z_hi) c->dw1_clean = true;
     return 0;
 }
@@ -434,19 +440,16 @@ static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo, i
 // The side launches are narrow grid-stride kernels (side_ctas CTAs per SM) so the small kernels of the main stream
 // run beside them; the tcgen05 kernels need whole SMs and simply start when a side launch has drained.  Every
 // element sees exactly the arithmetic of the one-launch Adam (same adam_one, gradient +0 for untouched rows).
-static int train_step_fused(Ctx* c, const int32_t* row_ids, int B, int use_target, float beta, float p, uint64_t seed,
-                            const uint8_t* keep_tape, const float* eps_tape, const AdamHyper& h, float* loss_out,
-                            cudaStream_t s) {
+static int effective_overlap(const Ctx* c) {
     const Layer& E0 = c->enc[0];
     int ov = (c->timing || !c->side) ? 0 : c->overlap;
-    if (E0.out % 4 != 0 || E0.w_off % 4 != 0) ov &= ~2;
-    if (!ov) {
-        B200_CHECK(forward_backward(c, row_ids, B, B, use_target, beta, h.lam, p, seed, (uint64_t)h.step, 0, keep_tape,
-                                    eps_tape, loss_out, s));
-        return adam_step(c, h, s);
-    }
-    B200_CHECK(forward_backward(c, row_ids, B, B, use_target, beta, h.lam, p, seed, (uint64_t)h.step, 0, keep_tape,
-                                eps_tape, loss_out, s, &h));
+    if (E0.out % 4 != 0 || E0.w_off % 4 != 0) ov &= ~2;      // the row filter works on whole float4s
+    return ov;
+}
+
+// Adam part of the fused step (`ov` != 0).  Expects: marks of step h.step written before ev_mark (bit 1; the
+// untouched-row launch was already issued by forward_hidden), ev_wd recorded once dW_d / db_d are final.
+static int fused_adam_finish(Ctx* c, const AdamHyper& h, int ov, cudaStream_t s) {
     const int64_t cut = c->dec.back().w_off;
     int64_t head_hi = c->n_elems;
     if (ov & 1) {
@@ -458,6 +461,25 @@ static int train_step_fused(Ctx* c, const int32_t* row_ids, int B, int use_targe
     B200_CHECK(adam_step(c, h, s, 0, head_hi, (ov & 2) ? ADAM_ROWS_MARKED : ADAM_ROWS_ALL, 8));
     B200_CUDA_OK(cudaStreamWaitEvent(s, c->ev_side, 0));
     return 0;
+}
+
+static int train_step_fused(Ctx* c, const int32_t* row_ids, int B, int use_target, float beta, float p, uint64_t seed,
+                            const uint8_t* keep_tape, const float* eps_tape, AdamHyper h, float* loss_out,
+                            cudaStream_t s) {
+    h.ov = effective_overlap(c);
+    if (!h.ov) {
+        B200_CHECK(forward_backward(c, row_ids, B, B, use_target, beta, h.lam, p, seed, (uint64_t)h.step, 0, keep_tape,
+                                    eps_tape, loss_out, s));
+        return adam_step(c, h, s);
+    }
+    B200_CHECK(forward_backward(c, row_ids, B, B, use_target, beta, h.lam, p, seed, (uint64_t)h.step, 0, keep_tape,
+                                eps_tape, loss_out, s, &h));
+    return fused_adam_finish(c, h, h.ov, s);
+}
+
+__global__ void k_stamp_rows(const int32_t* __restrict__ items, int n, int n_items, int32_t* __restrict__ mark, int32_t step) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && items[i] >= 0 && items[i] < n_items) mark[items[i]] = step;
 }
 
 static int predict(Ctx* c, const int32_t* row_ids, int B, int remove_train, int train_mode, float p,
@@ -530,6 +552,10 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming);
     if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) c->side = nullptr;
     if (const char* e = getenv("B200VAE_OVERLAP")) c->overlap = atoi(e) & 3;
+    // width of the decoder-output Adam on the side stream: narrow when there are hidden-layer kernels to share
+    // the SMs with (cfg2: 2 CTAs/SM = 743 us/step vs 778 at 8), full width when the backward tail is only the
+    // sparse scatter (cfg3, one hidden layer: 386 us at 8 vs 392 at 2)            [B200, profiles/r1_overlap_sweep.txt]
+    c->side_ctas[0] = (cfg->n_enc + cfg->n_dec > 2) ? 2 : 8;
     if (const char* e = getenv("B200VAE_SIDE_CTAS")) {
         int a = 0, b = 0;
         int n = sscanf(e, "%d,%d", &a, &b);
@@ -698,7 +724,7 @@ int b200vae_adam_step_range(b200vae_ctx* ctx, float lr, float beta1, float beta2
                             float lam, int64_t step, int64_t elem_lo, int64_t elem_hi, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     B200_REQUIRE(c, B200VAE_EINVAL, "null context");
-    const AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
+    AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
     return adam_step(c, h, (cudaStream_t)stream, elem_lo, elem_hi);
 }
 
@@ -716,8 +742,42 @@ int b200vae_adam_step(b200vae_ctx* ctx, float lr, float beta1, float beta2, floa
                       float lam, int64_t step, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     B200_REQUIRE(c, B200VAE_EINVAL, "null context");
-    const AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
+    AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
     return adam_step(c, h, (cudaStream_t)stream);
+}
+
+int b200vae_adam_step_split(b200vae_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay,
+                            float lam, int64_t step, const int32_t* touched_items, int32_t n_touched, int overlap_bits,
+                            void* stream) {
+    // The Adam schedule of the fused step on caller-provided gradients: rows of the encoder-0 weight listed in
+    // `touched_items` are the only ones whose gradient may be non-zero.
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    cudaStream_t s = (cudaStream_t)stream;
+    B200_REQUIRE(c && (touched_items || n_touched == 0) && n_touched >= 0, B200VAE_EINVAL, "bad argument");
+    B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
+    AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
+    const int saved = c->overlap;
+    c->overlap = overlap_bits & 3;
+    h.ov = effective_overlap(c);
+    c->overlap = saved;
+    if (!h.ov) return adam_step(c, h, s);
+    if (lam != 0.f) {
+        B200_CHECK(launch_tensor_norms(c, c->w, c->d_toff, c->d_tlen, c->n_tensors, c->norm_partial, c->norms, s));
+        c->norms_valid = true;
+    }
+    if (h.ov & 2) {
+        if (n_touched > 0) {
+            k_stamp_rows<<<(int)cdiv(n_touched, 256), 256, 0, s>>>(touched_items, n_touched, c->n_items, c->mark, (int32_t)step);
+            note(c, "stamp_rows", s);
+        }
+        B200_CUDA_OK(cudaEventRecord(c->ev_mark, s));
+        B200_CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_mark, 0));
+        const Layer& e0 = c->enc[0];
+        B200_CHECK(adam_step(c, h, c->side, e0.w_off, e0.w_off + (int64_t)e0.in * e0.out, ADAM_ROWS_UNMARKED,
+                             c->side_ctas[1]));
+    }
+    B200_CUDA_OK(cudaEventRecord(c->ev_wd, s));
+    return fused_adam_finish(c, h, h.ov, s);
 }
 
 int b200vae_train_step(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int use_target, float beta,
@@ -727,7 +787,7 @@ int b200vae_train_step(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int 
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     B200_REQUIRE(c && loss_out, B200VAE_EINVAL, "null argument");
     B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, B200VAE_EINVAL, "dropout_p must be in [0,1)");
-    const AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
+    AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
     return train_step_fused(c, row_ids, B, use_target, beta, dropout_p, seed, keep_tape, eps_tape, h, loss_out,
                             (cudaStream_t)stream);
 }
@@ -805,7 +865,7 @@ int b200vae_train_step_host(b200vae_ctx* ctx, const int64_t* indptr_host, const 
     if (values_host)
         B200_CUDA_OK(cudaMemcpyAsync(S.int_values, values_host, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, s));
     S.int_has_values = values_host != nullptr;
-    const AdamHyper h = {lr, 0.9f, 0.999f, 1e-8f, weight_decay, lam, step};
+    AdamHyper h = {lr, 0.9f, 0.999f, 1e-8f, weight_decay, lam, step};
     B200_CHECK(train_step_fused(c, nullptr, B, 0, beta, dropout_p, seed, nullptr, nullptr, h, c->loss_dev, s));
     B200_CUDA_OK(cudaMemcpyAsync(loss_host, c->loss_dev, 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
@@ -876,7 +936,7 @@ int b200vae_dec_fwd_lse(b200vae_ctx* ctx, const float* h, const float* W, const 
                         int32_t n_items, int32_t H, float* lse, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     cudaStream_t s = (cudaStream_t)stream;
-    B200_REQUIRE(c && h && W && lse, B200VAE_EINVAL, "null argument");
+    B200_REQUIRE(c && h && W, B200VAE_EINVAL, "null argument");
     B200_REQUIRE(B <= c->cfg.max_batch && n_items <= c->n_items, B200VAE_ECAPACITY, "exceeds context capacity");
     B200_REQUIRE(tc_supported(B, n_items, H, H, H), B200VAE_EINVAL, "shape not supported by the tcgen05 path (H %% 4 != 0?)");
     TcEpi e;
@@ -885,8 +945,9 @@ int b200vae_dec_fwd_lse(b200vae_ctx* ctx, const float* h, const float* W, const 
     e.part_sum = c->part_sum;
     tick(c, 0, 0, s);
     B200_CHECK(launch_tc_gemm(c, TC_EPI_LSE, h, H, 0, W, H, 0, nullptr, 0, B, n_items, H, e, s));
-    B200_CHECK(launch_lse_merge(c, c->part_max, c->part_sum, tc_lse_tiles(n_items), B, lse, s));
     tick(c, 0, 1, s);
+    if (lse)   // lse == NULL: only the fused GEMM + log-sum-exp kernel (per-tile partials stay in the workspace)
+        B200_CHECK(launch_lse_merge(c, c->part_max, c->part_sum, tc_lse_tiles(B, n_items, c->num_sms), B, lse, s));
     return 0;
 }
 

@@ -613,8 +613,28 @@ static int pick_bn(int N, bool b_mn) {
     const int64_t tiles = cdiv(N, 256);                 // fewest tiles, then the smallest tile that covers N
     return (int)std::min<int64_t>(256, round_up(cdiv(N, tiles), g));
 }
-// number of (max, sum) partial rows the LSE epilogue writes per user: two warps per 256-item tile
-int tc_lse_tiles(int N) { return (tc_epi_warps(TC_EPI_LSE) / 4) * (int)cdiv(N, pick_bn(N, false)); }
+// N tile of the item-sized K-major GEMMs with a per-row epilogue (LSE / PROB: N = n_items, no split-K).  All tiles
+// of a launch have the same shape and the persistent CTAs (pairs) walk them round-robin, so the launch takes
+// ceil(tiles / parallel) waves of one tile each: pick the tile that minimises waves x (BN + fixed cost) instead of
+// always the widest one -- 50 000 items on 74 CTA pairs: 196 x 256 = 3 waves of 256, 209 x 240 = 3 waves of 240.
+// A pair tile needs N % 16 == 0 (each CTA stages N/2 rows, a multiple of the 8-row swizzle atom).
+static int pick_bn_items(int M, int N, int num_sms) {
+    const bool cg2 = use_cg2();
+    const int g = 16;
+    if (N <= 256) return (int)std::min<int64_t>(256, round_up(N, cg2 ? 32 : 16));
+    const int64_t tiles_m = cdiv(M, cg2 ? 2 * TC_BM : TC_BM);
+    const int64_t parallel = cg2 ? std::max(1, num_sms / 2) : num_sms;
+    int best = 256;
+    int64_t best_cost = INT64_MAX;
+    for (int bn = 256; bn >= 128; bn -= g) {
+        const int64_t waves = cdiv(cdiv(N, bn) * tiles_m, parallel);
+        const int64_t cost = waves * (bn + 24);        // ~24 columns' worth of per-tile fixed cost (ring refill, epilogue tail)
+        if (cost < best_cost) { best_cost = cost; best = bn; }
+    }
+    return best;
+}
+// number of (max, sum) partial rows the LSE epilogue writes per user: two warps per item tile
+int tc_lse_tiles(int M, int N, int num_sms) { return (tc_epi_warps(TC_EPI_LSE) / 4) * (int)cdiv(N, pick_bn_items(M, N, num_sms)); }
 
 int tc_output_tiles(int M, int N, int b_mn) {
     return (int)(cdiv(M, use_cg2() ? 2 * TC_BM : TC_BM) * cdiv(N, pick_bn(N, b_mn != 0)));
@@ -656,7 +676,7 @@ int launch_tc_gemm(Ctx* c, int mode, const float* A, int64_t lda, int a_mn, cons
     B200_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, B200VAE_EINVAL, "tc_gemm: operands must be 16-byte aligned");
     TcArgs a;
     a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
-    a.BN = pick_bn(N, b_mn != 0);
+    a.BN = (mode == TC_EPI_LSE || mode == TC_EPI_PROB) ? pick_bn_items(M, N, c->num_sms) : pick_bn(N, b_mn != 0);
     const bool cg2 = use_cg2();
     a.tiles_m = (int)cdiv(M, cg2 ? 2 * TC_BM : TC_BM);
     a.tiles_n = (int)cdiv(N, a.BN);

@@ -1,0 +1,152 @@
+"""CPU: rectorch_b200.data.DataReader / DatasetManager (CSV -> CSR ingest of libb200vae.so, host side) against
+  (a) the known answers of the reference's own tests (tests/test_data.py:104-190 topn, :352-359 rated), and
+  (b) fixtures produced by the unmodified reference DataReader (oracle/make_golden_data.py).
+No GPU is needed: the ingest is host code; the matrices it returns are what DataSampler uploads.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy import sparse
+
+from rectorch_b200._lib import B200VaeError
+from rectorch_b200.configuration import DataConfig
+from rectorch_b200.data import DataReader, DatasetManager, read_csv_csr
+
+NAMES = ['train.csv', 'unique_iid.txt', 'unique_uid.txt', 'validation_tr.csv', 'validation_te.csv',
+         'test_tr.csv', 'test_te.csv']
+
+
+def _folder(tmp_path, files, cfg_extra):
+    for n, f in zip(NAMES, files):
+        with open(os.path.join(tmp_path, n), "w", newline="") as fh:
+            fh.write(f)
+    cfg = {"data_path": "NOT USED", "proc_path": str(tmp_path), "seed": 42, "threshold": 2.5, "separator": " ",
+           "u_min": 1, "i_min": 1, "heldout": 1, "test_prop": 0.5}
+    cfg.update(cfg_extra)
+    p = os.path.join(tmp_path, "cfg.json")
+    json.dump(cfg, open(p, "w"))
+    return p
+
+
+def test_datareader_reference_known_answers_topn(tmp_path):
+    files = ['uid,iid\n0,0\n0,1\n1,2\n1,1\n', '2\n5\n3\n', '2\n4\n1\n3\n', 'uid,iid\n2,0\n', 'uid,iid\n2,1\n',
+             'uid,iid\n3,0\n', 'uid,iid\n3,1\n']
+    cfgp = _folder(tmp_path, files, {"topn": 1})
+    with pytest.raises(TypeError):
+        DataReader(1)
+    reader = DataReader(cfgp)
+    reader2 = DataReader(DataConfig(cfgp))
+    assert reader.n_items == 3
+    assert reader.cfg == reader2.cfg
+    with pytest.raises(ValueError):
+        reader.load_data("training")
+    sp_data = reader.load_data("full")
+    sp_train = reader.load_data("train")
+    sp_vtr, sp_vte = reader.load_data("validation")
+    sp_ttr, sp_tte = reader.load_data("test")
+    assert sp_data.dtype == np.float64 and sparse.isspmatrix_csr(sp_train)
+    assert np.all(sp_data.data == np.ones(8))
+    r, c = sp_data.nonzero()
+    assert np.all(r == np.array([0, 0, 1, 1, 2, 2, 3, 3]))
+    assert np.all(c == np.array([0, 1, 1, 2, 0, 1, 0, 1]))
+    assert np.all(sp_train.data == np.ones(4))
+    r, c = sp_train.nonzero()
+    assert np.all(r == np.array([0, 0, 1, 1])) and np.all(c == np.array([0, 1, 1, 2]))
+    for m, col in ((sp_vtr, 0), (sp_vte, 1), (sp_ttr, 0), (sp_tte, 1)):
+        assert np.all(m.data == np.array([1.]))
+        r, c = m.nonzero()
+        assert np.all(r == np.array([0])) and np.all(c == np.array([col]))
+    # DatasetManager (data.py:522-560)
+    man = DatasetManager(cfgp)
+    assert man.n_items == 3 and man.training_set[1] is None
+    tr, te = man.get_train_and_test()
+    assert tr.shape == (4, 3) and te.shape == (4, 3)
+    assert np.array_equal(tr.toarray(), np.array([[1, 1, 0], [0, 1, 1], [1, 1, 0], [1, 0, 0]], dtype=float))
+    assert np.array_equal(te.toarray(), np.array([[0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 1, 0]], dtype=float))
+
+
+def test_datareader_reference_known_answers_rated(tmp_path):
+    files = ['uid,iid,2\n0,0,3\n0,1,4\n1,2,4\n1,1,4\n', '2\n5\n3\n', '2\n4\n1\n3\n', 'uid,iid,2\n2,0,5\n',
+             'uid,iid,2\n2,1,4\n', 'uid,iid,2\n3,0,5\n', 'uid,iid,2\n3,1,4\n']
+    cfgp = _folder(tmp_path, files, {})          # no "topn" key: DefaultMunch -> None -> values from column 3
+    sp_data = DataReader(cfgp).load_data("full")
+    assert np.all(sp_data.data == np.array([3., 4., 4., 4., 5., 4., 5., 4.]))
+    r, c = sp_data.nonzero()
+    assert np.all(r == np.array([0, 0, 1, 1, 2, 2, 3, 3]))
+    assert np.all(c == np.array([0, 1, 1, 2, 0, 1, 0, 1]))
+
+
+def _same(m, g, key):
+    m = m.tocsr()
+    m.sum_duplicates()
+    m.sort_indices()
+    assert tuple(m.shape) == tuple(g[key + "/shape"]), key
+    assert np.array_equal(m.indptr, g[key + "/indptr"]), key
+    assert np.array_equal(m.indices, g[key + "/indices"]), key
+    assert np.array_equal(m.data, g[key + "/data"]), key
+
+
+@pytest.mark.parametrize("name", ["topn", "rated_dups", "crlf", "no_final_newline"])
+def test_datareader_matches_reference_fixture(name, tmp_path, golden_dir):
+    g = np.load(os.path.join(golden_dir, "datareader_%s.npz" % name))
+    files = [str(g["file/" + n]) for n in NAMES]
+    cfgp = _folder(tmp_path, files, {"topn": int(g["topn"])})
+    reader = DataReader(cfgp)
+    assert reader.n_items == int(g["n_items"])
+    tr = reader.load_data("train")
+    assert tr.has_canonical_format
+    _same(tr, g, "train")
+    a, b = reader.load_data("validation")
+    _same(a, g, "validation_tr")
+    _same(b, g, "validation_te")
+    a, b = reader.load_data("test")
+    _same(a, g, "test_tr")
+    _same(b, g, "test_te")
+    _same(reader.load_data("full"), g, "full")
+
+
+def test_ingest_large_file_parallel_chunks(tmp_path):
+    """A file large enough to be cut into several per-thread chunks parses to the same matrix as numpy."""
+    rng = np.random.default_rng(0)
+    n, n_users, n_items = 400_000, 20_000, 3_000
+    u = rng.integers(0, n_users, n)
+    i = rng.integers(0, n_items, n)
+    v = rng.integers(1, 11, n) / 2.0
+    p = os.path.join(tmp_path, "big.csv")
+    with open(p, "w") as fh:
+        fh.write("uid,iid,rating\n")
+        fh.write("\n".join("%d,%d,%r" % t for t in zip(u.tolist(), i.tolist(), v.tolist())))
+        fh.write("\n")
+    assert os.path.getsize(p) > 4 << 20
+    m = read_csv_csr(p, n_items, topn=False, n_rows=n_users)
+    ref = sparse.csr_matrix((v, (u, i)), shape=(n_users, n_items), dtype=np.float64)
+    ref.sum_duplicates()
+    ref.sort_indices()
+    assert np.array_equal(m.indptr, ref.indptr) and np.array_equal(m.indices, ref.indices)
+    assert np.allclose(m.data, ref.data, rtol=0, atol=1e-12)
+    ones = read_csv_csr(p, n_items, topn=True, n_rows=n_users)
+    assert np.array_equal(ones.indptr, ref.indptr) and ones.data.sum() == n
+
+
+def test_ingest_errors(tmp_path):
+    p = os.path.join(tmp_path, "bad.csv")
+    with open(p, "w") as fh:
+        fh.write("uid,iid\n0,1\n1,x\n")
+    with pytest.raises(B200VaeError, match="malformed record near data line 3"):
+        read_csv_csr(p, 5)
+    with pytest.raises(B200VaeError, match="cannot open"):
+        read_csv_csr(os.path.join(tmp_path, "missing.csv"), 5)
+    with open(p, "w") as fh:
+        fh.write("uid,iid\n0,7\n")
+    with pytest.raises(B200VaeError, match="column index 7"):
+        read_csv_csr(p, 5)
+    with open(p, "w") as fh:
+        fh.write("uid,iid\n0,1\n")
+    with pytest.raises(B200VaeError, match="no value column"):
+        read_csv_csr(p, 5, topn=False)
+    with open(p, "w") as fh:
+        fh.write("uid,iid\n")
+    m = read_csv_csr(p, 5)
+    assert m.shape == (0, 5) and m.nnz == 0
