@@ -211,12 +211,20 @@ def run_b200(args):
     B, K, W = CFG["batch"], args.steps, args.warmup
     n_users = min(CFG["n_users"], max(B * (K + W), B * 8))
     n_users = CFG["n_users"] if args.full_matrix else n_users
-    csr = synth.make_matrix(n_users, CFG["n_items"], seed=synth.DEFAULT_SEED + rank)
     torch.manual_seed(0)
     net = MultiVAE_net(list(CFG["dec_dims"]), None, CFG["dropout"]).cuda(dev)
     model = MultiVAE(net, beta=CFG["beta"], anneal_steps=CFG["anneal_steps"], learning_rate=CFG["lr"])
     eng = model._engine
-    sampler = DataSampler(csr, None, batch_size=B, shuffle=False, device=dev)
+    if world == 1:
+        csr = synth.make_matrix(n_users, CFG["n_items"], seed=synth.DEFAULT_SEED + rank)
+        sampler = DataSampler(csr, None, batch_size=B, shuffle=False, device=dev)
+    else:
+        # one global matrix of n_users x world rows, users sharded row-wise: rank r trains on rows
+        # [r * n_users, (r + 1) * n_users), the global batch is B * world.  "factors": every GPU holds the whole CSR
+        # and the encoder-0 gradient is exchanged as factors; "allreduce": sharded CSR, whole arena all-reduced
+        csr = synth.make_matrix(n_users * world, CFG["n_items"], seed=synth.DEFAULT_SEED)
+        sampler = DataSampler(csr, None, batch_size=B * world, shuffle=False, device=dev, rank=rank, world_size=world,
+                              replicate=(args.dp == "factors"))
     batches = list(sampler.iter_rows(dev))
     model.network.train()
     slots = model._loss_hist
@@ -405,7 +413,7 @@ def run_b200(args):
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 (tf32 tensor-core operands, fp32 accumulate)", "data": "synthetic",
                 "config": {"workload": "cfg2: MultiVAE [50000-600-200], %d users x 50000 items per GPU, batch %d per GPU"
-                                       % (n_users, B), "global_batch": B * world, "parallelism": "dp%d row-sharded, 1 allreduce/step" % world,
+                                       % (n_users, B), "global_batch": B * world, "parallelism": ("dp1" if world == 1 else "dp%d row-sharded; %s" % (world, "all-reduce of the decoder-output half of the gradient arena + all-gather of the encoder-0 gradient factors" if args.dp == "factors" else "1 all-reduce of the gradient arena per step")),
                            "schedule": "decoder-output Adam on a second stream beside the encoder backward (B200VAE_OVERLAP=1)" if world == 1 else "gradient all-reduce in two buckets overlapped with backward / Adam",
                            "l2": "no flush: per-step working set (4 x 242 MB arenas) exceeds the 126 MB L2"},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
@@ -426,6 +434,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--full-matrix", action="store_true", help="generate all 200K users per GPU even for short runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dp", default="factors", choices=["factors", "allreduce"],
+                    help="N > 1: how the encoder-0 gradient is summed over ranks")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

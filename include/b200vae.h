@@ -114,12 +114,23 @@ int  b200vae_expand_batch(b200vae_ctx* ctx, int slot, const int32_t* row_ids, in
  *   keep_tape    optional uint8 per non-zero of the batch (1 = kept): parity mode, replaces Philox
  *   eps_tape     optional [B x latent] N(0,1) draws: parity mode
  *   loss_out     device float[4]: {loss, nll(BCE term), kld, reg}
+ *   enc0_delta_out  NULL, or device [B x H1]: receives d(loss)/d(pre-activation of encoder layer 0) and the
+ *                gradient of that layer (weight + bias) is NOT written -- a data-parallel caller gathers the
+ *                deltas of all ranks and calls b200vae_enc0_grad instead of all-reducing the dense matrix
  */
 int  b200vae_forward_backward(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int32_t B_global,
                               int use_target, float beta, float lam, float dropout_p,
                               uint64_t seed, uint64_t step, int64_t row_offset,
                               const uint8_t* keep_tape, const float* eps_tape,
-                              float* loss_out, void* stream);
+                              float* loss_out, float* enc0_delta_out, void* stream);
+
+/* Encoder-0 gradient of a GLOBAL batch from its factors: dW1[j,:] = sum_u xt[u,j] * delta[u,:], db1 = colsum(delta)
+ * over the B_total rows `row_ids` of CSR slot 0 (which must hold the rows of every rank); xt is recomputed
+ * from the CSR with the Philox keys (seed, step, row + row_offset, item) the owning rank's forward pass used.
+ * Replaces the all-reduce of the dense [n_items x H1] gradient that loss.backward() + DistributedDataParallel
+ * style training would need (models.py:832; SURVEY.md section 8f N1 "sparse-aware encoder-gradient exchange"). */
+int  b200vae_enc0_grad(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B_total, const float* delta,
+                       float dropout_p, uint64_t seed, uint64_t step, int64_t row_offset, void* stream);
 
 /* Make `stream` wait until the most recent b200vae_forward_backward has finished writing the
  * gradients of the decoder output layer (the arena range starting at that layer's w_off, i.e. the

@@ -46,7 +46,9 @@ _SIGS = {
     "b200vae_expand_batch": (c_int, [c_void_p, c_int, c_void_p, c_int32, c_void_p, c_void_p]),
     "b200vae_forward_backward": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int, c_float, c_float,
                                          c_float, c_uint64, c_uint64, c_int64, c_void_p, c_void_p,
-                                         c_void_p, c_void_p]),
+                                         c_void_p, c_void_p, c_void_p]),
+    "b200vae_enc0_grad": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_float, c_uint64, c_uint64, c_int64,
+                                  c_void_p]),
     "b200vae_adam_step": (c_int, [c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
                                   c_int64, c_void_p]),
     "b200vae_adam_step_range": (c_int, [c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,

@@ -94,6 +94,11 @@ struct Ctx {
                                       // bit 1: untouched encoder-0 rows beside the forward pass -- measured slower
                                       // (the tcgen05 kernels wait for the narrow launch), kept for experiments
                                       // (B200VAE_OVERLAP)
+    // scratch of b200vae_enc0_grad (a GLOBAL batch: rows of every data-parallel rank), grown on demand
+    int64_t* gl_bp = nullptr;
+    int32_t* gl_sp = nullptr;
+    float*   gl_xt = nullptr;
+    int64_t  gl_rows = 0, gl_nnz = 0;
     int side_ctas[2] = {2, 2};        // CTAs per SM of the two side launches (B200VAE_SIDE_CTAS="a,b")
     int side_threads = 256;
 };

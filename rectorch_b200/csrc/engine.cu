@@ -53,7 +53,7 @@ static void free_ctx(Ctx* c) {
     if (c->ev_mark) cudaEventDestroy(c->ev_mark);
     if (c->ev_side) cudaEventDestroy(c->ev_side);
     if (c->side) cudaStreamDestroy(c->side);
-    F(c->mark);
+    F(c->mark); F(c->gl_bp); F(c->gl_sp); F(c->gl_xt);
     delete c;
 }
 
@@ -227,10 +227,24 @@ static int dec_lse(Ctx* c, const float* h, int B, int H, int* n_tiles, bool for_
     return 0;
 }
 
+// gradients of encoder layer 0 from its factors: dW1[j,:] += sum_u xt[u,j] * delta[u,:] (sparse scatter into the
+// all-zero gradient rows), db1 = colsum(delta)
+static int enc0_grad(Ctx* c, const BatchView& v, const float* xt, const float* delta, int B, cudaStream_t s) {
+    const Layer& e0 = c->enc[0];
+    if (!c->dw1_clean) {
+        B200_CUDA_OK(cudaMemsetAsync(c->g + e0.w_off, 0, (size_t)c->n_items * e0.out * sizeof(float), s));
+        if (c->timing) { note(c, "memset_dW1", s); c->launches--; }
+    }
+    c->dw1_clean = false;
+    B200_CHECK(launch_spmm_scatter(c, v, xt, 1.0f, delta, e0.out, c->g + e0.w_off, s));
+    B200_CHECK(launch_colsum(c, delta, e0.out, B, e0.out, c->g + e0.b_off, s));
+    return 0;
+}
+
 static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int use_target, float beta,
                             float lam, float p, uint64_t seed, uint64_t step, int64_t row_offset,
                             const uint8_t* keep_tape, const float* eps_tape, float* loss_out,
-                            cudaStream_t s, const AdamHyper* fused = nullptr) {
+                            cudaStream_t s, const AdamHyper* fused = nullptr, float* enc0_delta_out = nullptr) {
     B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
     B200_REQUIRE(B >= 1 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
     B200_REQUIRE(Bg >= B, B200VAE_EINVAL, "B_global (%d) < B (%d)", Bg, B);
@@ -364,14 +378,13 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         std::swap(cur, nxt);
     }
     const Layer& e0 = c->enc[0];
-    if (!c->dw1_clean) {
-        B200_CUDA_OK(cudaMemsetAsync(c->g + e0.w_off, 0, (size_t)I * e0.out * sizeof(float), s));
-        if (c->timing) { note(c, "memset_dW1", s); c->launches--; }
+    if (enc0_delta_out) {
+        // data-parallel caller: the encoder-0 gradient is assembled from the factors of ALL ranks
+        // (b200vae_enc0_grad) instead of being reduced as a dense [n_items x H1] matrix
+        B200_CUDA_OK(cudaMemcpyAsync(enc0_delta_out, cur, (size_t)B * e0.out * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        return 0;
     }
-    c->dw1_clean = false;
-    B200_CHECK(launch_spmm_scatter(c, st.in, c->xt, 1.0f, cur, e0.out, c->g + e0.w_off, s));
-    B200_CHECK(launch_colsum(c, cur, e0.out, B, e0.out, c->g + e0.b_off, s));
-    return 0;
+    return enc0_grad(c, st.in, c->xt, cur, B, s);
 }
 
 // Adam over the arena range [r_lo, r_hi) (whole arena: 0, n_elems).  Ranges must not cut a tensor; the ranges
@@ -712,12 +725,52 @@ int b200vae_expand_batch(b200vae_ctx* ctx, int slot, const int32_t* row_ids, int
 int b200vae_forward_backward(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int32_t B_global,
                              int use_target, float beta, float lam, float dropout_p, uint64_t seed,
                              uint64_t step, int64_t row_offset, const uint8_t* keep_tape,
-                             const float* eps_tape, float* loss_out, void* stream) {
+                             const float* eps_tape, float* loss_out, float* enc0_delta_out, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     B200_REQUIRE(c && loss_out, B200VAE_EINVAL, "null argument");
     B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, B200VAE_EINVAL, "dropout_p must be in [0,1)");
     return forward_backward(c, row_ids, B, B_global, use_target, beta, lam, dropout_p, seed, step, row_offset,
-                            keep_tape, eps_tape, loss_out, (cudaStream_t)stream);
+                            keep_tape, eps_tape, loss_out, (cudaStream_t)stream, nullptr, enc0_delta_out);
+}
+
+int b200vae_enc0_grad(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B_total, const float* delta, float dropout_p,
+                      uint64_t seed, uint64_t step, int64_t row_offset, void* stream) {
+    // Encoder-0 gradient of a GLOBAL batch from its factors (data parallelism without the dense all-reduce of
+    // the [n_items x H1] gradient): the rows of every rank's batch are looked up in the CSR bound to slot 0
+    // (which must therefore hold all of them), their normalised / dropped-out input values are recomputed
+    // (same Philox keys as the forward pass of the rank that owns them) and scattered against the gathered
+    // delta rows.  delta [B_total x H1] already carries the 1/B_global factor.
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    cudaStream_t s = (cudaStream_t)stream;
+    B200_REQUIRE(c && row_ids && delta && B_total >= 1, B200VAE_EINVAL, "bad argument");
+    B200_REQUIRE(c->params_bound && c->slot[0].indptr, B200VAE_ESTATE, "parameters / CSR slot 0 are not bound");
+    B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, B200VAE_EINVAL, "dropout_p must be in [0,1)");
+    const int64_t parts = cdiv(B_total, c->cfg.max_batch);
+    const int64_t cap = parts * c->cfg.max_batch_nnz;
+    if (B_total > c->gl_rows || cap > c->gl_nnz) {
+        B200_CUDA_OK(cudaStreamSynchronize(s));
+        if (c->gl_bp) cudaFree(c->gl_bp);
+        if (c->gl_sp) cudaFree(c->gl_sp);
+        if (c->gl_xt) cudaFree(c->gl_xt);
+        c->gl_bp = nullptr; c->gl_sp = nullptr; c->gl_xt = nullptr;
+        c->gl_rows = 0; c->gl_nnz = 0;
+        B200_CHECK(dmalloc(&c->gl_bp, (int64_t)B_total + 1));
+        B200_CHECK(dmalloc(&c->gl_sp, (int64_t)B_total + 1));
+        B200_CHECK(dmalloc(&c->gl_xt, cap));
+        c->gl_rows = B_total;
+        c->gl_nnz = cap;
+    }
+    const CsrSlot& S = c->slot[0];
+    BatchView v;
+    v.B = B_total; v.row_ids = row_ids; v.indptr = S.indptr; v.indices = S.indices; v.values = S.values;
+    v.bp = c->gl_bp; v.sp = c->gl_sp;
+    const int64_t saved_cap = c->cfg.max_batch_nnz;       // the launchers size their grids / bounds from the context
+    c->cfg.max_batch_nnz = cap;
+    int rc = launch_batch_scan(c, v.indptr, row_ids, B_total, cap, c->gl_bp, c->gl_sp, s);
+    if (!rc) rc = launch_batch_prep(c, v, dropout_p, seed, step, row_offset, nullptr, true, c->gl_xt, nullptr, nullptr, 0, s);
+    if (!rc) rc = enc0_grad(c, v, c->gl_xt, delta, B_total, s);
+    c->cfg.max_batch_nnz = saved_cap;
+    return rc;
 }
 
 int b200vae_adam_step_range(b200vae_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay,

@@ -224,8 +224,9 @@ class Engine:
     # ---- compute entry points ------------------------------------------------------------------------
     def forward_backward(self, rows=None, dense=None, dense_target=None, use_target=False, B_global=None,
                          beta=1.0, lam=0.0, dropout_p=0.5, seed=0, step=0, row_offset=0, keep_tape=None,
-                         eps_tape=None):
-        """Gradients into ``self.g``; loss components into ``self.loss_buf`` (device)."""
+                         eps_tape=None, enc0_delta_out=None):
+        """Gradients into ``self.g``; loss components into ``self.loss_buf`` (device).  With
+        ``enc0_delta_out`` ([B x H1] device tensor) the encoder-0 gradient is left to :meth:`enc0_grad`."""
         if dense is not None:
             B = dense.shape[0]
             self._prepare(None, dense, B, self._nnz_cap_dense(B), 0)
@@ -240,8 +241,15 @@ class Engine:
         check(_lib.lib().b200vae_forward_backward(
             self._ctx, ptr(rid), B, B if B_global is None else int(B_global), 1 if use_target else 0,
             float(beta), float(lam), float(dropout_p), int(seed) & (2 ** 64 - 1), int(step), int(row_offset),
-            ptr(keep_tape), ptr(eps_tape), ptr(self.loss_buf), stream_ptr()))
+            ptr(keep_tape), ptr(eps_tape), ptr(self.loss_buf), ptr(enc0_delta_out), stream_ptr()))
         return self.loss_buf
+
+    def enc0_grad(self, all_rows, delta_all, dropout_p, seed, step, row_offset=0):
+        """Encoder-0 weight / bias gradient of the GLOBAL batch ``all_rows`` (rows of CSR slot 0) from the
+        gathered ``delta_all`` [len(all_rows) x H1]."""
+        check(_lib.lib().b200vae_enc0_grad(self._ctx, ptr(all_rows), int(all_rows.numel()), ptr(delta_all),
+                                           float(dropout_p), int(seed) & (2 ** 64 - 1), int(step), int(row_offset),
+                                           stream_ptr()))
 
     def adam(self, lr, betas, eps, weight_decay, lam):
         self.adam_steps += 1

@@ -10,9 +10,10 @@ checkpoint -- ``lam`` / ``beta``, ``anneal_steps``, ``annealing``, ``gradient_up
 
 One ``train_batch`` = one call into libb200vae.so: sparse input layer, small dense layers,
 fused decoder GEMM + log-softmax + loss, backward, fused Adam.  With ``torch.distributed``
-initialised (one process per GPU) users are sharded row-wise by the sampler, gradients are
-summed with ONE ``all_reduce`` of the flat gradient arena per step, and every rank applies
-the identical Adam update.
+initialised (one process per GPU) users are sharded row-wise by the sampler and every rank applies
+the identical Adam update to gradients summed over ranks: the decoder-output half of the gradient
+arena by an ``all_reduce`` that overlaps the rest of the step, the encoder-0 half by exchanging its
+small factors (``_step_dp_factors``; plain samplers fall back to all-reducing the whole arena).
 """
 import ctypes
 import logging
@@ -119,6 +120,14 @@ class AETrainer(TorchNNTrainer):
         self._make_optimizer(learning_rate)
         self._loss_hist = torch.zeros(4 * 4096, dtype=torch.float32, device=self.device)
         self._comm_stream = torch.cuda.Stream(device=self.device)
+        # data parallelism: a second communicator for the small collectives of a step, so that they do not
+        # queue behind the all-reduce of the decoder-output gradient (new_group is collective: every rank
+        # builds its trainers in the same order)
+        self._pg_small = None
+        self._dp_seed = None
+        self._delta_bufs = None
+        if _dist_world()[1] > 1:
+            self._pg_small = dist.new_group()
 
     # ---- optimizer <-> arena coupling --------------------------------------------------------------
     def _make_optimizer(self, lr):
@@ -169,8 +178,18 @@ class AETrainer(TorchNNTrainer):
         net = self.network
         lr, betas, eps, wd = self._hyper()
         p = float(net.dropout.p)
-        seed = draw_seed()
         rank, world = _dist_world()
+        replicated = isinstance(tr_batch, RowBatch) and tr_batch.all_rows is not None
+        if world > 1 and replicated and self._dp_seed is None:
+            # every rank has to reproduce the dropout draws of every other rank's users: one base seed for the
+            # run, drawn on rank 0 from torch's generator, and a per-step seed derived from it
+            t = torch.tensor([draw_seed()], dtype=torch.int64, device=self.device)
+            dist.broadcast(t, src=0)
+            self._dp_seed = int(t.item())
+        if self._dp_seed is not None:
+            seed = (self._dp_seed + 0x9E3779B97F4A7C15 * (eng.adam_steps + 1)) % (1 << 63)
+        else:
+            seed = draw_seed()
         kw = dict(beta=beta, lam=lam, dropout_p=p, seed=seed)
         if rng_tape is not None:
             keep, eps_t = rng_tape
@@ -191,6 +210,8 @@ class AETrainer(TorchNNTrainer):
         eng.loss_buf = loss_slot
         if world == 1:
             eng.train_step(lr=lr, betas=betas, eps=eps, weight_decay=wd, **kw)
+        elif replicated:
+            self._step_dp_factors(tr_batch, B_local, world, rank, lr, betas, eps, wd, lam, loss_slot, kw)
         else:
             # row-sharded data parallelism: local gradients are already scaled by 1/B_global
             eng.forward_backward(B_global=B_local * world, step=eng.adam_steps + 1, row_offset=row_offset, **kw)
@@ -211,6 +232,42 @@ class AETrainer(TorchNNTrainer):
             eng.adam_range(lr, betas, eps, wd, lam, 0, cut, first=False)
             w_loss.wait()
         self._step_tensor += 1.0
+
+    def _step_dp_factors(self, rb, B_local, world, rank, lr, betas, eps, wd, lam, loss_slot, kw):
+        """Data-parallel step on a replicated sampler.  The decoder-output gradient (half of the arena) is
+        all-reduced while the rest of the step runs; the other item-sized gradient -- encoder layer 0,
+        dW1 = sum_u x~_u (x) delta_u -- is NOT reduced as a dense [n_items x H1] matrix: the ranks all-gather
+        their delta rows (B_local x H1 floats each) and every rank scatters the global batch itself
+        (b200vae_enc0_grad; the CSR rows and the Philox dropout bits of the other ranks' users are recomputed
+        locally).  Only the small hidden-layer tensors are all-reduced.  Per step and rank: 4*P/2 bytes of
+        all-reduce instead of 4*P, plus ~B_global*H1*4 bytes of all-gather."""
+        eng = self._engine
+        H1 = eng.shapes[0][0]
+        n_rows = int(rb.all_rows.numel())
+        if n_rows != B_local * world:
+            raise RuntimeError("replicated RowBatch: %d global rows for %d ranks x %d local rows" % (n_rows, world, B_local))
+        step = eng.adam_steps + 1
+        if self._delta_bufs is None or self._delta_bufs[0].shape[0] != B_local or self._delta_bufs[1].shape[0] != n_rows:
+            self._delta_bufs = (torch.empty((B_local, H1), dtype=torch.float32, device=self.device),
+                                torch.empty((n_rows, H1), dtype=torch.float32, device=self.device))
+        mine, everyone = self._delta_bufs
+        eng.forward_backward(B_global=n_rows, step=step, row_offset=0, enc0_delta_out=mine, **kw)
+        cut = eng.w_off[-1]
+        side = self._comm_stream
+        check(_lib.lib().b200vae_wait_wd_ready(eng._ctx, ctypes.c_void_p(side.cuda_stream)))
+        with torch.cuda.stream(side):
+            w_tail = dist.all_reduce(eng.g[cut:], op=dist.ReduceOp.SUM, async_op=True)
+        small = self._pg_small
+        dist.all_gather_into_tensor(everyone, mine, group=small)
+        eng.enc0_grad(rb.all_rows, everyone, kw["dropout_p"], kw["seed"], step, 0)
+        lo = eng.w_off[1] if len(eng.w_off) > 1 else cut
+        if lo < cut:
+            dist.all_reduce(eng.g[lo:cut], op=dist.ReduceOp.SUM, group=small)
+        dist.all_reduce(loss_slot, op=dist.ReduceOp.SUM, group=small)
+        # encoder half first (its inputs are complete long before the big all-reduce is), decoder half after
+        eng.adam_range(lr, betas, eps, wd, lam, 0, cut, first=True)
+        w_tail.wait()
+        eng.adam_range(lr, betas, eps, wd, lam, cut, eng.n_elems, first=False)
 
     def _loss_from(self, comps, beta, lam):
         """Python float loss from the 4 device components (sum over ranks already applied)."""

@@ -12,9 +12,12 @@ is uploaded to HBM once; a batch is just a slice of a (shuffled) device row-id v
   on the training / evaluation hot path.
 
 Row-sharded data parallelism (one process per GPU): ``DataSampler(..., rank=r, world_size=N)``
-keeps only users ``[r*U//N, (r+1)*U//N)`` on rank r's GPU; ``batch_size`` stays the GLOBAL
-batch size and every rank draws ``batch_size // N`` of its own users per step, so all ranks
-run the same number of equally sized steps (``shard_plan``).
+assigns users ``[r*U//N, (r+1)*U//N)`` to rank r; ``batch_size`` stays the GLOBAL batch size and
+every rank draws ``batch_size // N`` of its own users per step, so all ranks run the same number
+of equally sized steps (``shard_plan``).  With ``replicate=True`` (default for N > 1) every GPU
+holds the whole CSR matrix (a few hundred MB even for 1M users) and every rank knows the rows
+of the whole global batch (``RowBatch.all_rows``): the trainers then exchange the small factors
+of the encoder-0 gradient instead of all-reducing the dense [n_items x H1] matrix.
 """
 import numpy as np
 import torch
@@ -62,12 +65,13 @@ class Sampler():
 class RowBatch:
     """A batch as row ids into the sampler's device CSR matrices."""
 
-    __slots__ = ("sampler", "rows", "has_te")
+    __slots__ = ("sampler", "rows", "has_te", "all_rows")
 
-    def __init__(self, sampler, rows, has_te):
+    def __init__(self, sampler, rows, has_te, all_rows=None):
         self.sampler = sampler
-        self.rows = rows            # int32 CUDA tensor [B], local to the sampler's shard
+        self.rows = rows            # int32 CUDA tensor [B]: rows of the sampler's device CSR
         self.has_te = has_te
+        self.all_rows = all_rows    # replicated samplers: rows of the GLOBAL batch, rank-major [N * B]
 
     @property
     def shape(self):
@@ -84,7 +88,7 @@ class DataSampler(Sampler):
     """
 
     def __init__(self, sparse_data_tr, sparse_data_te=None, batch_size=1, shuffle=True, device=None,
-                 rank=0, world_size=1):
+                 rank=0, world_size=1, replicate=None):
         super(DataSampler, self).__init__()
         self.sparse_data_tr = sparse_data_tr
         self.sparse_data_te = sparse_data_te
@@ -94,7 +98,10 @@ class DataSampler(Sampler):
         self.rank = rank
         self.world_size = world_size
         lo, hi, lb, nb, used = shard_plan(int(sparse_data_tr.shape[0]), batch_size, rank, world_size)
-        self.row_offset, self._hi, self.local_batch, self._n_batches, self._rows_used = lo, hi, lb, nb, used
+        self._lo, self._hi, self.local_batch, self._n_batches, self._rows_used = lo, hi, lb, nb, used
+        self.replicate = bool(world_size > 1 if replicate is None else (replicate and world_size > 1))
+        # offset added to a device-CSR row id to get the global user id (keys the Philox streams)
+        self.row_offset = 0 if self.replicate else lo
         self._dev = None
 
     @property
@@ -117,7 +124,7 @@ class DataSampler(Sampler):
             if not torch.cuda.is_available():
                 raise RuntimeError("rectorch_b200.samplers.DataSampler needs a CUDA device (no CPU path)")
             dev = torch.device(device or self.device or ("cuda:%d" % torch.cuda.current_device()))
-            lo, hi = self.row_offset, self._hi
+            lo, hi = (0, self.n_users) if self.replicate else (self._lo, self._hi)
             tr = DeviceCSR(_row_slice(self.sparse_data_tr, lo, hi), dev)
             te = None
             if self.sparse_data_te is not None:
@@ -126,19 +133,50 @@ class DataSampler(Sampler):
         return self._dev
 
     def _permutation(self):
-        n = self._hi - self.row_offset
+        n = self._hi - self._lo
         idx = np.arange(n, dtype=np.int32)
         if self.shuffle:
             np.random.shuffle(idx)
         return idx[:self._rows_used] if self.world_size > 1 else idx
 
+    def global_plan(self):
+        """Replicated mode: int32 ``[world_size x rows_used]`` of GLOBAL user ids, row r = the users rank r
+        visits this epoch, in order.  Every rank must hold the same plan: without shuffling it is pure
+        arithmetic; with shuffling rank 0 draws the per-shard permutations (``np.random``, like the
+        reference's sampler) and broadcasts them through ``torch.distributed``."""
+        n, N, used = self.n_users, self.world_size, self._rows_used
+        plan = np.empty((N, used), dtype=np.int32)
+        for r in range(N):
+            lo, hi = r * n // N, (r + 1) * n // N
+            idx = np.arange(lo, hi, dtype=np.int32)
+            if self.shuffle:
+                np.random.shuffle(idx)
+            plan[r] = idx[:used]
+        if self.shuffle:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                on_dev = dist.get_backend() == "nccl"
+                t = torch.from_numpy(plan)
+                t = t.cuda() if on_dev else t
+                dist.broadcast(t, src=0)
+                plan = t.cpu().numpy()
+        return plan
+
     def iter_rows(self, device=None):
         """Yield :class:`RowBatch` objects (no densification)."""
         tr, te = self.device_csr(device)
+        lb = self.local_batch
+        if self.replicate:
+            plan = torch.from_numpy(np.ascontiguousarray(self.global_plan())).to(tr.device)
+            used = int(plan.shape[1])
+            for start in range(0, used, lb):
+                blk = plan[:, start:min(start + lb, used)]
+                yield RowBatch(self, blk[self.rank].contiguous(), te is not None, blk.reshape(-1).contiguous())
+            return
         perm = torch.from_numpy(np.ascontiguousarray(self._permutation())).to(tr.device)
         n = int(perm.numel())
-        for start in range(0, n, self.local_batch):
-            yield RowBatch(self, perm[start:min(start + self.local_batch, n)], te is not None)
+        for start in range(0, n, lb):
+            yield RowBatch(self, perm[start:min(start + lb, n)], te is not None)
 
     def __iter__(self):
         from ._expand import expand_rows

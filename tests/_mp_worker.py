@@ -31,15 +31,22 @@ csr = synth.make_matrix(N_USERS, N_ITEMS, seed=3, mu=3.0, sigma=0.7, min_len=3, 
 torch.manual_seed(0)
 net = MultiVAE_net([32, 96, N_ITEMS]).cuda()
 model = MultiVAE(net, beta=0.3, anneal_steps=10)
-torch.manual_seed(123)          # identical draw_seed() stream on every rank
+mode = sys.argv[3] if len(sys.argv) > 3 else "factors"   # "factors": replicated CSR, encoder-0 gradient from
+                                                          # gathered factors; "allreduce": sharded CSR, dense all-reduce
+torch.manual_seed(123 + (rank if mode == "factors" else 0))   # factors mode must not depend on per-rank generators
 losses = []
 if world > 1:
-    sampler = DataSampler(csr, None, batch_size=GB, shuffle=False, rank=rank, world_size=world)
+    sampler = DataSampler(csr, None, batch_size=GB, shuffle=False, rank=rank, world_size=world,
+                          replicate=(mode == "factors"))
     for i, rb in enumerate(sampler.iter_rows()):
         if i >= STEPS:
             break
+        assert (rb.all_rows is not None) == (mode == "factors")
         losses.append(model.train_batch(rb))
 else:
+    from rectorch_b200.engine import draw_seed
+    if mode == "factors":
+        model._dp_seed = draw_seed()     # what rank 0 draws and broadcasts in the multi-process run
     sampler = DataSampler(csr, None, batch_size=GB, shuffle=False)
     sampler.device_csr()
     lb = GB // ref_world

@@ -1,8 +1,10 @@
 """GPU (>= 2 devices): row-sharded data parallelism == single process on the same global batches.
 
 Rank r owns users [r*U/N, (r+1)*U/N); every step each rank runs forward/backward on its local
-rows with the loss scaled by 1/B_global, ONE all_reduce(SUM) over the flat gradient arena, and the
-identical fused Adam.  Dropout / eps come from Philox keyed by the GLOBAL user row, so the result
+rows with the loss scaled by 1/B_global and applies the identical fused Adam to the summed gradient.
+"allreduce": sharded CSR, the whole gradient arena is all-reduced.  "factors" (default with a replicated
+sampler): only the decoder-output half is all-reduced, the encoder-0 gradient is rebuilt on every rank from
+the all-gathered delta rows (AETrainer._step_dp_factors).  Dropout / eps come from Philox keyed by the GLOBAL user row, so the result
 must equal the 1-process run up to fp32 summation order.
 """
 import os
@@ -24,18 +26,19 @@ def _free_port():
         return s.getsockname()[1]
 
 
+@pytest.mark.parametrize("mode", ["factors", "allreduce"])
 @pytest.mark.parametrize("world", [2])
-def test_sharded_training_matches_single_process(tmp_path, world):
+def test_sharded_training_matches_single_process(tmp_path, world, mode):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     worker = os.path.join(ROOT, "tests", "_mp_worker.py")
     multi, single = str(tmp_path / "multi.npz"), str(tmp_path / "single.npz")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-                        "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), worker, multi, str(world)],
+                        "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), worker, multi, str(world), mode],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     env = dict(os.environ, WORLD_SIZE="1", RANK="0", LOCAL_RANK="0")
-    r = subprocess.run([sys.executable, worker, single, str(world)], capture_output=True, text=True, timeout=600, env=env)
+    r = subprocess.run([sys.executable, worker, single, str(world), mode], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     a, b = np.load(multi), np.load(single)
     rel = np.abs(a["losses"] - b["losses"]) / np.abs(b["losses"])

@@ -96,7 +96,7 @@ def test_sampler_host_side():
     s = DataSampler(m, batch_size=10, shuffle=False)
     assert len(s) == 11 and s.n_users == 103 and s.n_items == 50
     s2 = DataSampler(m, batch_size=10, shuffle=True, rank=1, world_size=2)
-    assert len(s2) == int(np.ceil((103 // 2) / 5)) and s2.row_offset == 51
+    assert len(s2) == int(np.ceil((103 // 2) / 5)) and s2.row_offset == 0 and s2._lo == 51 and s2.replicate
     np.random.seed(5)
     a = s._permutation()
     assert np.array_equal(a, np.arange(103))
@@ -157,6 +157,28 @@ ref = per_user[all_rows].sum(0) / bg
 assert np.allclose(g.numpy(), ref, atol=1e-5), "allreduced gradient != single-process gradient"
 assert abs(loss[0].item() - per_user[all_rows, 0].sum() / bg) < 1e-4
 assert abs(loss[3].item() / world - 3.0) < 1e-6          # replicated term is divided by world
+# replicated sampler: with shuffling, rank 0's per-shard permutations reach every rank (broadcast), so all ranks
+# agree on the rows of the whole global batch (RowBatch.all_rows) although their numpy generators differ
+from rectorch_b200 import synth
+from rectorch_b200.samplers import DataSampler
+np.random.seed(100 + rank)
+m = synth.make_matrix(n_users, 50, seed=2, density=0.2)
+s = DataSampler(m, None, batch_size=bg, shuffle=True, rank=rank, world_size=world)
+assert s.replicate and s.row_offset == 0 and len(s) == nb
+plan = s.global_plan()
+assert plan.shape == (world, used) and plan.dtype == np.int32
+for r in range(world):
+    l, h = shard_plan(n_users, bg, r, world)[:2]
+    assert plan[r].min() >= l and plan[r].max() < h and len(set(plan[r].tolist())) == used
+mine = torch.from_numpy(plan.astype(np.int64).copy())
+lst = [torch.empty_like(mine) for _ in range(world)]
+dist.all_gather(lst, mine)
+assert all(torch.equal(lst[0], t) for t in lst), "ranks disagree on the global plan"
+s0 = DataSampler(m, None, batch_size=bg, shuffle=False, rank=rank, world_size=world)
+p0 = s0.global_plan()
+assert np.array_equal(p0[1], np.arange(*shard_plan(n_users, bg, 1, world)[:2])[:used])
+s1 = DataSampler(m, None, batch_size=bg, shuffle=False, rank=rank, world_size=world, replicate=False)
+assert not s1.replicate and s1.row_offset == lo
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 """
