@@ -41,7 +41,7 @@ typedef struct b200vae_ctx b200vae_ctx;
 
 /* Network description == constructor arguments of
  * MultiVAE_net(dec_dims, enc_dims, dropout) / MultiDAE_net(...)  (nets.py:208, 390).
- * enc_dims[0] == dec_dims[n_dec] == n_items.  For is_vae the LAST encoder layer
+ * dec_dims[n_dec] == n_items, enc_dims[0] == n_items + cond_dim.  For is_vae the LAST encoder layer
  * has 2*enc_dims[n_enc] outputs (nets.py:264). */
 typedef struct {
     int32_t device;                          /* CUDA ordinal                                  */
@@ -54,6 +54,10 @@ typedef struct {
     int64_t max_batch_nnz;                   /* non-zeros per batch, capacity (input+target)  */
     int32_t use_tensor_cores;                /* 1 = tcgen05 path for the item-sized GEMMs when
                                                 shapes allow (default), 0 = fp32 SIMT kernels */
+    int32_t cond_dim;                        /* CMultiVAE_net(cond_dim, ...) (nets.py:455-480): the encoder input is
+                                                [n_items ratings | cond_dim condition flags], enc_dims[0] ==
+                                                n_items + cond_dim; the condition columns bypass F.normalize and
+                                                nn.Dropout.  0 for MultiVAE_net / MultiDAE_net */
 } b200vae_config;
 
 const char* b200vae_last_error(void);
@@ -252,6 +256,16 @@ int  b200vae_set_timing(b200vae_ctx* ctx, int enable);
  * Returns the number of events. */
 int  b200vae_timing_report(b200vae_ctx* ctx, char* buf, int cap);
 float b200vae_kernel_ms(b200vae_ctx* ctx, int which);
+
+/* Conditioned batch builder (ConditionedDataSampler.__iter__, samplers.py:187-232) on the device: for example i
+ * = (row ex_rows[i] of the bound CSRs, condition ex_conds[i] or -1) the internal batch of slot 0 becomes
+ * [CSR-0 row | one-hot(cond)] (the condition as column n_items + cond) and the internal batch of slot 1 the
+ * CSR-1 row restricted to the items that satisfy the condition (any condition when -1).  item_cond_mask[j] has
+ * bit c set iff item j satisfies condition c (n_cond <= 64).  Afterwards row_ids == NULL in the step functions
+ * means these batches.  Examples whose filtered target is empty must have been dropped by the caller
+ * (samplers.py:227-229 drops them after the fact). */
+int  b200vae_build_cond_batch(b200vae_ctx* ctx, const int32_t* ex_rows, const int32_t* ex_conds, int32_t B,
+                              const uint64_t* item_cond_mask, void* stream);
 
 /* ---- data ingest (host side): pre-processed rating files -> canonical CSR ------------------------------
  * Replaces pd.read_csv + scipy.sparse.csr_matrix((values, (rows, cols))) in DataReader._load_train_data /

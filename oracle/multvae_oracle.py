@@ -24,6 +24,8 @@ a usable specification for the kernels.
 
 Reference citations (file:line under /root/reference/rectorch):
   forward DAE     nets.py:219-233        forward VAE    nets.py:394-417
+  forward CVAE    nets.py:455-480 (condition columns bypass normalize / dropout), predict models.py:947-956
+  cond. sampler   samplers.py:176-232
   reparameterise  nets.py:317-320, 407-411
   VAE loss        models.py:813-815      DAE loss       models.py:701-706
   train step      models.py:424-447 (DAE), 817-835 (VAE, beta annealing)
@@ -39,7 +41,7 @@ import numpy as np
 import torch
 
 __all__ = ["Net", "AdamState", "forward", "loss_value", "backward", "adam_update",
-           "train_step", "predict", "batches", "recall_at_k", "ndcg_at_k", "hit_at_k",
+           "train_step", "predict", "batches", "conditioned_batches", "recall_at_k", "ndcg_at_k", "hit_at_k",
            "mrr_at_k", "compute_metrics", "evaluate", "replay_rng_tape", "beta_schedule"]
 
 
@@ -54,19 +56,20 @@ class Net:
     nets.py:222-225).
     """
 
-    def __init__(self, enc, dec, vae, dropout):
+    def __init__(self, enc, dec, vae, dropout, cond_dim=0):
         self.enc = [(w.clone().float(), b.clone().float()) for w, b in enc]
         self.dec = [(w.clone().float(), b.clone().float()) for w, b in dec]
         self.vae = bool(vae)
         self.dropout = float(dropout)
+        self.cond_dim = int(cond_dim)     # CMultiVAE_net: trailing condition columns of the input (nets.py:455-470)
 
     @staticmethod
-    def from_state_dict(sd, vae, dropout):
+    def from_state_dict(sd, vae, dropout, cond_dim=0):
         n_enc = len({k.split(".")[1] for k in sd if k.startswith("enc_layers.")})
         n_dec = len({k.split(".")[1] for k in sd if k.startswith("dec_layers.")})
         enc = [(sd["enc_layers.%d.weight" % i], sd["enc_layers.%d.bias" % i]) for i in range(n_enc)]
         dec = [(sd["dec_layers.%d.weight" % i], sd["dec_layers.%d.bias" % i]) for i in range(n_dec)]
-        return Net(enc, dec, vae, dropout)
+        return Net(enc, dec, vae, dropout, cond_dim)
 
     def state_dict(self):
         sd = {}
@@ -114,11 +117,15 @@ def forward(net, x, train, drop_scale=None, eps=None):
     Returns a cache dict with every intermediate the backward pass needs.
     """
     c = {"x": x, "train": train}
+    C = net.cond_dim
+    xi = x[:, :-C] if C else x                    # CMultiVAE_net.encode: x[:, :-cond_dim] (nets.py:466)
     # F.normalize(x): x / max(||x||_2, 1e-12), row-wise (nets.py:220, 395)
-    nrm = torch.sqrt((x * x).sum(dim=1, keepdim=True)).clamp_min(1e-12)
-    h = x / nrm
+    nrm = torch.sqrt((xi * xi).sum(dim=1, keepdim=True)).clamp_min(1e-12)
+    h = xi / nrm
     if train and net.dropout > 0.0:
-        h = h * drop_scale
+        h = h * drop_scale                        # drop_scale [B, n_items]: the condition columns are not dropped
+    if C:
+        h = torch.cat((h, x[:, -C:]), 1)          # nets.py:469
     c["x_in"] = h
     acts = []
     n_enc = len(net.enc)
@@ -263,7 +270,8 @@ def predict(net, x, remove_train=True):
     c = forward(net, x, False)
     out = c["logits"].clone()
     if remove_train:
-        out[x != 0] = -np.inf
+        xi = x[:, :-net.cond_dim] if net.cond_dim else x      # models.py:953-954
+        out[xi != 0] = -np.inf
     if net.vae:
         return out, c["mu"], c["logvar"]
     return (out,)
@@ -296,6 +304,44 @@ def batches(csr_tr, csr_te=None, batch_size=1, perm=None):
         if csr_te is not None:
             te = torch.from_numpy(np.asarray(csr_te[rows].toarray(), dtype=np.float32))
         yield tr, te
+
+
+def conditioned_batches(iid2cids, n_cond, csr_tr, csr_te=None, batch_size=1, perm=None):
+    """ConditionedDataSampler (samplers.py:158-232), written with explicit loops: examples are (user, -1) for
+    every user followed by (user, c) for every condition c known by one of the user's training items (ascending
+    c); a batch is a slice of (optionally permuted) examples; input = [training row | one-hot(c)], target = test
+    row restricted to the items that satisfy c (any condition for -1); examples with an empty target are dropped.
+    Yields (tr [B, I + n_cond], te [B, I], kept example array [B, 2])."""
+    if csr_te is None:
+        csr_te = csr_tr
+    n_users, n_items = csr_tr.shape
+    item_conds = [set(iid2cids.get(j, [])) for j in range(n_items)]
+    examples = [(r, -1) for r in range(n_users)]
+    for r in range(n_users):
+        cols = csr_tr[r].nonzero()[1]
+        for c in sorted(set().union(*[item_conds[j] for j in cols])):
+            examples.append((r, c))
+    examples = np.array(examples)
+    idx = np.arange(len(examples)) if perm is None else np.asarray(perm)
+    for s in range(0, len(examples), batch_size):
+        ex = examples[idx[s:min(s + batch_size, len(examples))]]
+        tr_rows, te_rows, kept = [], [], []
+        for r, c in ex:
+            x = np.zeros(n_items + n_cond, dtype=np.float32)
+            x[:n_items] = np.asarray(csr_tr[r].toarray(), dtype=np.float32)[0]
+            if c >= 0:
+                x[n_items + c] = 1.0
+            t = np.asarray(csr_te[r].toarray(), dtype=np.float32)[0].copy()
+            for j in range(n_items):
+                ok = (c in item_conds[j]) if c >= 0 else (len(item_conds[j]) > 0)
+                if not ok:
+                    t[j] = 0.0
+            if t.any():
+                tr_rows.append(x)
+                te_rows.append(t)
+                kept.append((r, c))
+        if kept:
+            yield torch.from_numpy(np.stack(tr_rows)), torch.from_numpy(np.stack(te_rows)), np.array(kept)
 
 
 # ----------------------------------------------------------------------------------------

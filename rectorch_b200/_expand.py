@@ -5,13 +5,15 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 
-def expand_rows(csr, rows):
-    """Dense float32 [B x n_items] CUDA tensor of the given rows of a DeviceCSR."""
+def expand_rows(csr, rows, width=None):
+    """Dense float32 [B x width] CUDA tensor of the given rows of a DeviceCSR (width defaults to the matrix's
+    column count; a larger one leaves zero columns on the right, e.g. for condition flags)."""
     B = int(rows.numel())
-    out = torch.empty((B, csr.shape[1]), dtype=torch.float32, device=csr.device)
+    width = csr.shape[1] if width is None else int(width)
+    out = torch.empty((B, width), dtype=torch.float32, device=csr.device)
     with torch.cuda.device(csr.device):
         check(_lib.lib().b200vae_expand_rows_raw(ptr(csr.indptr), ptr(csr.indices), ptr(csr.values), ptr(rows),
-                                                 B, csr.shape[1], ptr(out), stream_ptr()))
+                                                 B, width, ptr(out), stream_ptr()))
     return out
 
 

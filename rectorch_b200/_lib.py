@@ -26,7 +26,8 @@ class B200VaeError(RuntimeError):
 class Config(Structure):
     _fields_ = [("device", c_int32), ("is_vae", c_int32), ("n_enc", c_int32), ("n_dec", c_int32),
                 ("enc_dims", c_int32 * (MAX_LAYERS + 1)), ("dec_dims", c_int32 * (MAX_LAYERS + 1)),
-                ("max_batch", c_int32), ("max_batch_nnz", c_int64), ("use_tensor_cores", c_int32)]
+                ("max_batch", c_int32), ("max_batch_nnz", c_int64), ("use_tensor_cores", c_int32),
+                ("cond_dim", c_int32)]
 
 
 _lib = None
@@ -83,6 +84,7 @@ _SIGS = {
     "b200vae_set_timing": (c_int, [c_void_p, c_int]),
     "b200vae_kernel_ms": (c_float, [c_void_p, c_int]),
     "b200vae_timing_report": (c_int, [c_void_p, c_char_p, c_int]),
+    "b200vae_build_cond_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "b200vae_csv_open": (c_int, [POINTER(c_void_p), c_char_p, ctypes.c_char, c_int]),
     "b200vae_csv_info": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int32), POINTER(c_int64),
                                  POINTER(c_int64), POINTER(c_int64)]),

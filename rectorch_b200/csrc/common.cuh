@@ -86,6 +86,8 @@ int launch_batch_scan(Ctx* c, const int64_t* indptr, const int32_t* row_ids, int
 int launch_batch_prep(Ctx* c, const BatchView& in, float p, uint64_t seed, uint64_t step,
                       int64_t row_offset, const uint8_t* keep_tape, bool train, float* xt, float* row_sum_out,
                       int32_t* mark, int32_t mark_step, cudaStream_t s);
+int launch_build_cond_batch(Ctx* c, const int32_t* ex_rows, const int32_t* ex_conds, int B,
+                            const uint64_t* item_cond_mask, cudaStream_t s);
 int launch_target_fixup(Ctx* c, const BatchView& tgt, float* PT, int64_t ldp, const float* rowscale, float inv_Bg,
                         float* loss_row, cudaStream_t s);
 int launch_spmm_zero(Ctx* c, const BatchView& v, const float* vals, int H, float* dWt, cudaStream_t s);

@@ -23,7 +23,8 @@ struct Ctx {
     b200vae_config cfg;
     int num_sms = 0;
     int64_t launches = 0;
-    int n_items = 0, latent = 0;
+    int n_items = 0, latent = 0;      // decoder outputs (items), latent width
+    int enc_in = 0;                   // encoder input width = n_items + cond_dim
     std::vector<Layer> enc, dec;      // forward order
     int n_tensors = 0;                // 2 * (n_enc + n_dec)
     int max_width = 0;                // widest hidden activation
@@ -70,6 +71,7 @@ struct Ctx {
     float* loss_dev = nullptr;        // [4] scratch for train_step_host
     int*   d_err = nullptr;           // device error flag (capacity overflow)
     int64_t* lens_tmp = nullptr;      // [max_batch+1]
+    int64_t* lens_tmp2 = nullptr;     // [max_batch+1]
 
     // timing instrumentation
     std::vector<cudaEvent_t> tev;     // one event after every launch of the current step (timing mode)

@@ -44,7 +44,7 @@ static void free_ctx(Ctx* c) {
     for (float* p : c->act_dec) F(p);
     F(c->z); F(c->eps); F(c->gvec); F(c->P); F(c->hT); F(c->dbuf[0]); F(c->dbuf[1]);
     F(c->part_max); F(c->part_sum); F(c->splitk); F(c->norms); F(c->norm_partial);
-    F(c->d_toff); F(c->d_tlen); F(c->loss_dev); F(c->d_err); F(c->lens_tmp);
+    F(c->d_toff); F(c->d_tlen); F(c->loss_dev); F(c->d_err); F(c->lens_tmp); F(c->lens_tmp2);
     F(c->h_r); F(c->wd_shadow); F(c->d_specs); F(c->spmm_acc); F(c->spmm_ticket);
     for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventDestroy(c->ev[i][j]);
@@ -232,7 +232,7 @@ static int dec_lse(Ctx* c, const float* h, int B, int H, int* n_tiles, bool for_
 static int enc0_grad(Ctx* c, const BatchView& v, const float* xt, const float* delta, int B, cudaStream_t s) {
     const Layer& e0 = c->enc[0];
     if (!c->dw1_clean) {
-        B200_CUDA_OK(cudaMemsetAsync(c->g + e0.w_off, 0, (size_t)c->n_items * e0.out * sizeof(float), s));
+        B200_CUDA_OK(cudaMemsetAsync(c->g + e0.w_off, 0, (size_t)e0.in * e0.out * sizeof(float), s));
         if (c->timing) { note(c, "memset_dW1", s); c->launches--; }
     }
     c->dw1_clean = false;
@@ -555,7 +555,8 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     B200_REQUIRE(c, B200VAE_ECUDA, "out of host memory");
     c->cfg = *cfg;
     c->num_sms = prop.multiProcessorCount;
-    c->n_items = cfg->enc_dims[0];
+    c->n_items = cfg->dec_dims[cfg->n_dec];
+    c->enc_in = cfg->enc_dims[0];
     c->latent = cfg->dec_dims[0];
     c->use_tc = cfg->use_tensor_cores != 0;
     for (int i = 0; i < 5; ++i)
@@ -579,9 +580,9 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
         int t = atoi(e);
         if (t >= 32 && t <= 256) c->side_threads = t & ~31;
     }
-    if (cfg->dec_dims[cfg->n_dec] != c->n_items || cfg->enc_dims[cfg->n_enc] != c->latent) {
-        set_error("enc_dims/dec_dims are inconsistent (n_items %d vs %d, latent %d vs %d)", c->n_items,
-                  cfg->dec_dims[cfg->n_dec], cfg->enc_dims[cfg->n_enc], c->latent);
+    if (cfg->cond_dim < 0 || cfg->cond_dim > 64 || c->enc_in != c->n_items + cfg->cond_dim || cfg->enc_dims[cfg->n_enc] != c->latent) {
+        set_error("enc_dims/dec_dims are inconsistent (encoder input %d vs n_items %d + cond_dim %d, latent %d vs %d)", c->enc_in,
+                  c->n_items, cfg->cond_dim, cfg->enc_dims[cfg->n_enc], c->latent);
         free_ctx(c);
         return B200VAE_EINVAL;
     }
@@ -634,7 +635,7 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     A_(dmalloc(&c->d_specs, 128));
     A_(dmalloc(&c->spmm_acc, Bm * std::max(c->max_width, H)));
     A_(dmalloc(&c->spmm_ticket, Bm));
-    A_(dmalloc(&c->mark, I));
+    A_(dmalloc(&c->mark, c->enc_in));
     A_(dmalloc(&c->dbuf[0], Bm * c->max_width)); A_(dmalloc(&c->dbuf[1], Bm * c->max_width));
     c->n_lse_tiles = (int)std::max<int64_t>(cdiv(I, 64), 1);
     A_(dmalloc(&c->part_max, (int64_t)c->n_lse_tiles * Bm)); A_(dmalloc(&c->part_sum, (int64_t)c->n_lse_tiles * Bm));
@@ -642,12 +643,12 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     A_(dmalloc(&c->splitk, c->splitk_elems));
     A_(dmalloc(&c->norms, c->n_tensors)); A_(dmalloc(&c->norm_partial, (int64_t)c->n_tensors * NORM_PARTS));
     A_(dmalloc(&c->d_toff, c->n_tensors)); A_(dmalloc(&c->d_tlen, c->n_tensors));
-    A_(dmalloc(&c->loss_dev, 4)); A_(dmalloc(&c->d_err, 1)); A_(dmalloc(&c->lens_tmp, Bm + 1));
+    A_(dmalloc(&c->loss_dev, 4)); A_(dmalloc(&c->d_err, 1)); A_(dmalloc(&c->lens_tmp, Bm + 1)); A_(dmalloc(&c->lens_tmp2, Bm + 1));
 #undef A_
     if (!rc && cudaMemset(c->d_err, 0, sizeof(int)) != cudaSuccess) rc = B200VAE_ECUDA;
     if (!rc && cudaMemset(c->spmm_acc, 0, (size_t)Bm * std::max(c->max_width, H) * sizeof(float)) != cudaSuccess) rc = B200VAE_ECUDA;
     if (!rc && cudaMemset(c->spmm_ticket, 0, (size_t)Bm * sizeof(int)) != cudaSuccess) rc = B200VAE_ECUDA;
-    if (!rc && cudaMemset(c->mark, 0, (size_t)I * sizeof(int32_t)) != cudaSuccess) rc = B200VAE_ECUDA;   // steps start at 1
+    if (!rc && cudaMemset(c->mark, 0, (size_t)c->enc_in * sizeof(int32_t)) != cudaSuccess) rc = B200VAE_ECUDA;   // steps start at 1
     if (rc) { free_ctx(c); return rc; }
     *out = reinterpret_cast<b200vae_ctx*>(c);
     return 0;
@@ -704,11 +705,22 @@ int b200vae_dense_to_csr(b200vae_ctx* ctx, int slot, const float* dense, int32_t
     B200_REQUIRE(c && dense && (slot == 0 || slot == 1), B200VAE_EINVAL, "bad argument");
     B200_REQUIRE(B >= 1 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
     CsrSlot& S = c->slot[slot];
-    B200_CHECK(launch_dense_count(c, dense, B, c->n_items, c->lens_tmp, s));
+    const int width = slot == 0 ? c->enc_in : c->n_items;     // slot 0 = network input (items + condition flags)
+    B200_CHECK(launch_dense_count(c, dense, B, width, c->lens_tmp, s));
     B200_CHECK(launch_scan_i64(c, c->lens_tmp, B, c->cfg.max_batch_nnz, S.int_indptr, s));
-    B200_CHECK(launch_dense_fill(c, dense, B, c->n_items, S.int_indptr, S.int_indices, S.int_values, s));
+    B200_CHECK(launch_dense_fill(c, dense, B, width, S.int_indptr, S.int_indices, S.int_values, s));
     S.int_has_values = true;
     return 0;
+}
+
+int b200vae_build_cond_batch(b200vae_ctx* ctx, const int32_t* ex_rows, const int32_t* ex_conds, int32_t B,
+                             const uint64_t* item_cond_mask, void* stream) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    B200_REQUIRE(c && ex_rows && ex_conds && item_cond_mask, B200VAE_EINVAL, "null argument");
+    B200_REQUIRE(B >= 1 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
+    B200_REQUIRE(c->cfg.cond_dim >= 1, B200VAE_ESTATE, "the network has no condition inputs (cond_dim == 0)");
+    B200_REQUIRE(c->slot[0].indptr && c->slot[1].indptr, B200VAE_ESTATE, "both CSR slots must be bound");
+    return launch_build_cond_batch(c, ex_rows, ex_conds, B, item_cond_mask, (cudaStream_t)stream);
 }
 
 int b200vae_expand_batch(b200vae_ctx* ctx, int slot, const int32_t* row_ids, int32_t B, float* out, void* stream) {
@@ -719,7 +731,7 @@ int b200vae_expand_batch(b200vae_ctx* ctx, int slot, const int32_t* row_ids, int
     if (B == 0) return 0;
     BatchView v;
     B200_CHECK(make_view(c, slot, row_ids, B, &v, s));
-    return launch_expand(c, v, c->n_items, out, s);
+    return launch_expand(c, v, slot == 0 ? c->enc_in : c->n_items, out, s);
 }
 
 int b200vae_forward_backward(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int32_t B_global,
@@ -820,7 +832,7 @@ int b200vae_adam_step_split(b200vae_ctx* ctx, float lr, float beta1, float beta2
     }
     if (h.ov & 2) {
         if (n_touched > 0) {
-            k_stamp_rows<<<(int)cdiv(n_touched, 256), 256, 0, s>>>(touched_items, n_touched, c->n_items, c->mark, (int32_t)step);
+            k_stamp_rows<<<(int)cdiv(n_touched, 256), 256, 0, s>>>(touched_items, n_touched, c->enc_in, c->mark, (int32_t)step);
             note(c, "stamp_rows", s);
         }
         B200_CUDA_OK(cudaEventRecord(c->ev_mark, s));

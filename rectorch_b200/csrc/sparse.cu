@@ -109,7 +109,7 @@ int launch_scan_i64(Ctx* c, const int64_t* lens, int n, int64_t cap, int64_t* ou
 __global__ void k_batch_prep(BatchView v, float p, uint64_t seed, uint64_t step, int64_t row_offset,
                              const uint8_t* __restrict__ keep_tape, int train, int64_t cap,
                              float* __restrict__ xt, float* __restrict__ row_sum_out,
-                             int32_t* __restrict__ mark, int32_t mark_step) {
+                             int32_t* __restrict__ mark, int32_t mark_step, int n_items) {
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= v.B) return;
@@ -118,7 +118,10 @@ __global__ void k_batch_prep(BatchView v, float p, uint64_t seed, uint64_t step,
     int64_t o = v.bp[warp];
     if (o + (b - a) > cap) return;   // capacity overflow flagged by the scan
     float ss = 0.f, sx = 0.f;
+    // columns >= n_items are condition flags (CMultiVAE_net.encode, nets.py:466-470): concatenated AFTER
+    // F.normalize / nn.Dropout, so they take no part in the norm and are passed through unchanged
     for (int64_t k = a + lane; k < b; k += 32) {
+        if (v.indices[k] >= n_items) continue;
         float x = v.values ? v.values[k] : 1.f;
         ss += x * x;
         sx += x;
@@ -133,8 +136,9 @@ __global__ void k_batch_prep(BatchView v, float p, uint64_t seed, uint64_t step,
     float inv_keep = 1.0f / (1.0f - p);
     for (int64_t k = a + lane; k < b; k += 32) {
         float x = v.values ? v.values[k] : 1.f;
-        float xn = x / denom;
-        if (drop) {
+        const bool cond_col = v.indices[k] >= n_items;
+        float xn = cond_col ? x : x / denom;
+        if (drop && !cond_col) {
             bool keep;
             if (keep_tape) {
                 keep = keep_tape[o + (k - a)] != 0;
@@ -162,7 +166,8 @@ int launch_batch_prep(Ctx* c, const BatchView& in, float p, uint64_t seed, uint6
     int threads = 256;
     int blocks = (int)cdiv((int64_t)in.B * 32, threads);
     k_batch_prep<<<blocks, threads, 0, s>>>(in, p, seed, step, row_offset, keep_tape, train ? 1 : 0,
-                                            c->cfg.max_batch_nnz, xt, row_sum_out, mark, mark_step);
+                                            c->cfg.max_batch_nnz, xt, row_sum_out, mark, mark_step,
+                                            c->n_items > 0 ? c->n_items : INT32_MAX);
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -524,7 +529,7 @@ __global__ void k_mask_seen(BatchView v, int I, float* __restrict__ scores) {
     int64_t a = v.indptr[gr], b = v.indptr[gr + 1];
     for (int64_t k = a + lane; k < b; k += 32) {
         float x = v.values ? v.values[k] : 1.f;
-        if (x != 0.f) scores[(int64_t)warp * I + v.indices[k]] = -INFINITY;
+        if (x != 0.f && v.indices[k] < I) scores[(int64_t)warp * I + v.indices[k]] = -INFINITY;   // cond columns are not items
     }
 }
 
@@ -534,6 +539,93 @@ int launch_mask_seen(Ctx* c, const BatchView& v, int I, float* scores, cudaStrea
     k_mask_seen<<<(int)cdiv((int64_t)v.B * 32, threads), threads, 0, s>>>(v, I, scores);
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// conditioned batches (ConditionedDataSampler.__iter__, samplers.py:187-232): example = (row, cond)
+//   slot 0 internal batch: CSR-0 row + the condition as column n_items + cond (value 1)
+//   slot 1 internal batch: CSR-1 row restricted to the items whose condition mask has bit `cond` (any bit if cond < 0)
+// one warp per example; count -> scan -> fill
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool cond_pass(uint64_t m, int cond) {
+    return cond < 0 ? (m != 0ull) : ((m >> cond) & 1ull) != 0ull;
+}
+__global__ void k_cond_count(const int64_t* __restrict__ ip0, const int64_t* __restrict__ ip1,
+                             const int32_t* __restrict__ ix1, const int32_t* __restrict__ rows,
+                             const int32_t* __restrict__ conds, int B, const uint64_t* __restrict__ mask,
+                             int64_t* __restrict__ len0, int64_t* __restrict__ len1) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const int64_t r = rows[warp];
+    const int cond = conds[warp];
+    int cnt = 0;
+    for (int64_t k = ip1[r] + lane; k < ip1[r + 1]; k += 32) cnt += cond_pass(mask[ix1[k]], cond) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) {
+        len0[warp] = ip0[r + 1] - ip0[r] + (cond >= 0 ? 1 : 0);
+        len1[warp] = cnt;
+    }
+}
+__global__ void k_cond_fill(const int64_t* __restrict__ ip0, const int32_t* __restrict__ ix0, const float* __restrict__ v0,
+                            const int64_t* __restrict__ ip1, const int32_t* __restrict__ ix1, const float* __restrict__ v1,
+                            const int32_t* __restrict__ rows, const int32_t* __restrict__ conds, int B,
+                            const uint64_t* __restrict__ mask, int n_items, int64_t cap,
+                            const int64_t* __restrict__ op0, int32_t* __restrict__ ox0, float* __restrict__ ov0,
+                            const int64_t* __restrict__ op1, int32_t* __restrict__ ox1, float* __restrict__ ov1) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    if (op0[B] > cap || op1[B] > cap) return;          // capacity overflow flagged by the scans
+    const int64_t r = rows[warp];
+    const int cond = conds[warp];
+    const int64_t a0 = ip0[r], n0 = ip0[r + 1] - a0, o0 = op0[warp];
+    for (int64_t k = lane; k < n0; k += 32) {
+        ox0[o0 + k] = ix0[a0 + k];
+        ov0[o0 + k] = v0 ? v0[a0 + k] : 1.f;
+    }
+    if (cond >= 0 && lane == 0) {                      // columns stay sorted: every item id < n_items + cond
+        ox0[o0 + n0] = n_items + cond;
+        ov0[o0 + n0] = 1.f;
+    }
+    // filtered target row, order preserved: warp-wide compaction 32 entries at a time
+    const int64_t a1 = ip1[r], n1 = ip1[r + 1] - a1;
+    int64_t w = op1[warp];
+    for (int64_t k0 = 0; k0 < n1; k0 += 32) {
+        const int64_t k = k0 + lane;
+        bool keep = false;
+        int32_t col = 0;
+        if (k < n1) { col = ix1[a1 + k]; keep = cond_pass(mask[col], cond); }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int64_t pos = w + __popc(bal & ((1u << lane) - 1u));
+            ox1[pos] = col;
+            ov1[pos] = v1 ? v1[a1 + k] : 1.f;
+        }
+        w += __popc(bal);
+    }
+}
+
+int launch_build_cond_batch(Ctx* c, const int32_t* ex_rows, const int32_t* ex_conds, int B,
+                            const uint64_t* item_cond_mask, cudaStream_t s) {
+    CsrSlot& S0 = c->slot[0];
+    CsrSlot& S1 = c->slot[1];
+    const int threads = 256;
+    const int blocks = (int)cdiv((int64_t)B * 32, threads);
+    int64_t* len0 = c->lens_tmp;
+    int64_t* len1 = c->lens_tmp2;
+    k_cond_count<<<blocks, threads, 0, s>>>(S0.indptr, S1.indptr, S1.indices, ex_rows, ex_conds, B, item_cond_mask, len0, len1);
+    note(c, "cond_count", s);
+    B200_CHECK(launch_scan_i64(c, len0, B, c->cfg.max_batch_nnz, S0.int_indptr, s));
+    B200_CHECK(launch_scan_i64(c, len1, B, c->cfg.max_batch_nnz, S1.int_indptr, s));
+    k_cond_fill<<<blocks, threads, 0, s>>>(S0.indptr, S0.indices, S0.values, S1.indptr, S1.indices, S1.values, ex_rows,
+                                           ex_conds, B, item_cond_mask, c->n_items, c->cfg.max_batch_nnz,
+                                           S0.int_indptr, S0.int_indices, S0.int_values,
+                                           S1.int_indptr, S1.int_indices, S1.int_values);
+    note(c, "cond_fill", s);
+    B200_CUDA_OK(cudaGetLastError());
+    S0.int_has_values = true;
+    S1.int_has_values = true;
     return 0;
 }
 

@@ -68,7 +68,11 @@ class Engine:
         if self.is_vae:
             self.enc_dims[-1] //= 2
         self.dec_dims = [int(net.dec_layers[0].in_features)] + [int(l.out_features) for l in net.dec_layers]
-        self.n_items = self.enc_dims[0]
+        self.cond_dim = int(getattr(net, "cond_dim", 0) or 0)      # CMultiVAE_net: condition flags after the items
+        self.enc_in = self.enc_dims[0]                             # encoder input width = n_items + cond_dim
+        self.n_items = self.dec_dims[-1]
+        if self.enc_in != self.n_items + self.cond_dim:
+            raise ValueError("encoder input width %d != n_items %d + cond_dim %d" % (self.enc_in, self.n_items, self.cond_dim))
         self.latent = self.dec_dims[0]
         if self.n_enc > _lib.MAX_LAYERS or self.n_dec > _lib.MAX_LAYERS:
             raise ValueError("at most %d layers per side are supported" % _lib.MAX_LAYERS)
@@ -151,6 +155,7 @@ class Engine:
         cfg.max_batch = cap_b
         cfg.max_batch_nnz = cap_n
         cfg.use_tensor_cores = 1 if self.use_tc else 0
+        cfg.cond_dim = self.cond_dim
         h = ctypes.c_void_p()
         torch.cuda.synchronize(self.device)
         check(_lib.lib().b200vae_ctx_create(ctypes.byref(h), ctypes.byref(cfg)))
@@ -209,7 +214,7 @@ class Engine:
         return x
 
     def _nnz_cap_dense(self, B):
-        return min(B * self.n_items, max(B * 4096, 1 << 20))
+        return min(B * self.enc_in, max(B * 4096, 1 << 20))
 
     def _nnz_cap_rows(self, B):
         cap = 0
@@ -264,11 +269,22 @@ class Engine:
                                                  float(weight_decay), float(lam), self.adam_steps, int(lo), int(hi),
                                                  stream_ptr()))
 
+    def build_cond_batch(self, rows, conds, item_mask):
+        """Conditioned examples (row, cond) -> the context's internal batches: slot 0 = [tr row | one-hot(cond)],
+        slot 1 = te row restricted to the items satisfying the condition (ConditionedDataSampler.__iter__)."""
+        B = int(rows.numel())
+        self._prepare(rows, None, B, self._nnz_cap_rows(B) + B)
+        check(_lib.lib().b200vae_build_cond_batch(self._ctx, ptr(rows), ptr(conds), B, ptr(item_mask), stream_ptr()))
+        return B
+
     def train_step(self, rows=None, dense=None, dense_target=None, use_target=False, beta=1.0, lam=0.0,
                    dropout_p=0.5, seed=0, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
-                   keep_tape=None, eps_tape=None):
+                   keep_tape=None, eps_tape=None, cond=None):
         """Fused single-GPU step: one C call for forward, backward and Adam."""
-        if dense is not None:
+        if cond is not None:
+            B = self.build_cond_batch(rows, *cond)
+            use_target, rid = True, None
+        elif dense is not None:
             B = dense.shape[0]
             self._prepare(None, dense, B, self._nnz_cap_dense(B), 0)
             if dense_target is not None:
@@ -288,8 +304,11 @@ class Engine:
         return self.loss_buf
 
     def predict(self, rows=None, dense=None, remove_train=True, train_mode=False, dropout_p=0.0, seed=0,
-                want_scores=True, want_latent=True):
-        if dense is not None:
+                want_scores=True, want_latent=True, cond=None):
+        if cond is not None:
+            B = self.build_cond_batch(rows, *cond)
+            rid = None
+        elif dense is not None:
             B = dense.shape[0]
             self._prepare(None, dense, B, self._nnz_cap_dense(B), 0)
             rid = None
@@ -320,7 +339,7 @@ class Engine:
     def expand(self, slot, rows):
         B = rows.numel()
         self._ensure_ctx(B, self._nnz_cap_rows(B))
-        out = torch.empty((B, self.n_items), dtype=torch.float32, device=self.device)
+        out = torch.empty((B, self.enc_in if slot == 0 else self.n_items), dtype=torch.float32, device=self.device)
         check(_lib.lib().b200vae_expand_batch(self._ctx, slot, ptr(rows), B, ptr(out), stream_ptr()))
         return out
 
@@ -331,6 +350,7 @@ class Engine:
         kinds = (ctypes.c_int32 * n)(*[s[0] for s in specs])
         ks = (ctypes.c_int32 * n)(*[s[1] for s in specs])
         out = torch.empty((n, B), dtype=torch.float32, device=self.device)
+        # gt_rows None = the context's internal slot-1 batch (conditioned examples: the filtered held-out rows)
         check(_lib.lib().b200vae_topk_metrics(self._ctx, ptr(scores), ptr(gt_rows), B, kinds, ks, n, ptr(out), None,
                                               stream_ptr()))
         return out

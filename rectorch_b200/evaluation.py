@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from .metrics import KINDS, Metrics, parse_metric
-from .samplers import DataSampler
+from .samplers import CondRowBatch, DataSampler
 
 __all__ = ['ValidFunc', 'evaluate']
 
@@ -65,8 +65,14 @@ def _evaluate_device(model, test_loader, metric_list):
     model.network.eval()
     parts = []
     for rb in test_loader.iter_rows(eng.device):
-        scores, _, _ = eng.predict(rows=rb.rows, remove_train=True, want_latent=False)
-        parts.append(eng.topk_metrics(scores, rb.rows, specs))
+        if isinstance(rb, CondRowBatch):
+            # conditioned examples: input = [tr row | one-hot(cond)], ground truth = the filtered held-out row; both
+            # live in the context's internal batches after predict built them
+            scores, _, _ = eng.predict(rows=rb.rows, remove_train=True, want_latent=False, cond=rb.cond)
+            parts.append(eng.topk_metrics(scores, None, specs))
+        else:
+            scores, _, _ = eng.predict(rows=rb.rows, remove_train=True, want_latent=False)
+            parts.append(eng.topk_metrics(scores, rb.rows, specs))
     eng.check_overflow()
     allres = torch.cat(parts, dim=1).cpu().numpy().astype(np.float64)
     for i, name in enumerate(names):

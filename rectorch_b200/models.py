@@ -27,11 +27,11 @@ from torch import optim
 
 from .engine import Engine, draw_seed, param_norm_sum
 from .evaluation import ValidFunc, evaluate
-from .samplers import DataSampler, RowBatch
+from .samplers import CondRowBatch, DataSampler, RowBatch
 from . import _lib
 from ._lib import check, ptr, stream_ptr
 
-__all__ = ['RecSysModel', 'TorchNNTrainer', 'AETrainer', 'MultiDAE', 'MultiVAE']
+__all__ = ['RecSysModel', 'TorchNNTrainer', 'AETrainer', 'MultiDAE', 'MultiVAE', 'CMultiVAE']
 
 logger = logging.getLogger(__name__)
 
@@ -199,6 +199,10 @@ class AETrainer(TorchNNTrainer):
             self._bind_sampler(tr_batch.sampler)
             kw["rows"] = tr_batch.rows
             kw["use_target"] = bool(self._is_vae and tr_batch.has_te and te_batch is not None)
+            if isinstance(tr_batch, CondRowBatch):
+                if world > 1:
+                    raise NotImplementedError("conditioned batches are single-GPU for now")
+                kw["cond"] = tr_batch.cond
             row_offset = tr_batch.sampler.row_offset
             B_local = int(tr_batch.rows.numel())
         else:
@@ -368,7 +372,8 @@ class AETrainer(TorchNNTrainer):
         eng = self._engine
         if isinstance(x, RowBatch):
             self._bind_sampler(x.sampler)
-            scores, mu, logvar = eng.predict(rows=x.rows, remove_train=remove_train)
+            scores, mu, logvar = eng.predict(rows=x.rows, remove_train=remove_train,
+                                             cond=x.cond if isinstance(x, CondRowBatch) else None)
         else:
             scores, mu, logvar = eng.predict(dense=Engine._as_dense(x, self.device), remove_train=remove_train)
         if self._is_vae:
@@ -494,3 +499,14 @@ class MultiVAE(AETrainer):
         checkpoint = super().load_model(filepath)
         self.gradient_updates = checkpoint['gradient_updates']
         return checkpoint
+
+
+class CMultiVAE(MultiVAE):
+    """Conditioned variational auto-encoder trainer (rectorch/models.py:911-956): MultiVAE's loss, annealing,
+    optimizer and checkpoints on a :class:`rectorch_b200.nets.CMultiVAE_net`; the samplers are the conditioned
+    ones (:class:`ConditionedDataSampler`, :class:`EmptyConditionedDataSampler`), whose training batches carry
+    ``cond_dim`` condition columns after the items.  ``predict`` masks only the item part of the input
+    (models.py:953-954) -- the seen-item kernel ignores the condition columns."""
+
+    def __init__(self, cmvae_net, beta=1., anneal_steps=0, learning_rate=1e-3):
+        super(CMultiVAE, self).__init__(cmvae_net, beta=beta, anneal_steps=anneal_steps, learning_rate=learning_rate)

@@ -18,7 +18,7 @@ from torch.nn.init import xavier_uniform_ as xavier_init
 
 from .engine import Engine, draw_seed
 
-__all__ = ['AE_net', 'MultiDAE_net', 'MultiVAE_net']
+__all__ = ['AE_net', 'MultiDAE_net', 'MultiVAE_net', 'CMultiVAE_net']
 
 logger = logging.getLogger(__name__)
 
@@ -145,3 +145,27 @@ class MultiVAE_net(_EngineNet):
                                          dropout_p=self.dropout.p if self.training else 0.0,
                                          seed=draw_seed() if self.training else 0)
         return scores, mu, logvar
+
+
+class CMultiVAE_net(MultiVAE_net):
+    """Conditioned variational auto-encoder (rectorch/nets.py:420-480).
+
+    ``CMultiVAE_net(cond_dim, dec_dims, enc_dims=None, dropout=0.5)``: the encoder input is
+    ``[n_items ratings | cond_dim condition flags]``; only the rating part goes through F.normalize and
+    nn.Dropout, the condition flags are concatenated afterwards (nets.py:466-470).  The first encoder layer
+    therefore has ``n_items + cond_dim`` inputs; the decoder still emits ``n_items`` scores.  Like the
+    reference, the MultiVAE_net layers are built (and initialised) first and then replaced, so a given
+    ``torch.manual_seed`` produces bit-identical initial weights.
+    """
+
+    def __init__(self, cond_dim, dec_dims, enc_dims=None, dropout=0.5):
+        super(CMultiVAE_net, self).__init__(dec_dims, enc_dims, dropout)
+        self.cond_dim = cond_dim
+        temp_dims = list(self.enc_dims[:-1]) + [self.enc_dims[-1] * 2]
+        temp_dims[0] += self.cond_dim
+        self.__dict__.pop("_engine", None)
+        self.enc_layers = nn.ModuleList(
+            [nn.Linear(d_in, d_out) for d_in, d_out in zip(temp_dims[:-1], temp_dims[1:])])
+        self.dec_layers = nn.ModuleList(
+            [nn.Linear(d_in, d_out) for d_in, d_out in zip(self.dec_dims[:-1], self.dec_dims[1:])])
+        self.init_weights()

@@ -24,7 +24,8 @@ import torch
 
 from .engine import DeviceCSR
 
-__all__ = ['Sampler', 'DataSampler', 'RowBatch', 'shard_plan']
+__all__ = ['Sampler', 'DataSampler', 'RowBatch', 'CondRowBatch', 'shard_plan', 'EmptyConditionedDataSampler',
+           'ConditionedDataSampler', 'BalancedConditionedDataSampler']
 
 
 def shard_plan(n_users, batch_size, rank, world_size):
@@ -185,6 +186,172 @@ class DataSampler(Sampler):
             data_tr = expand_rows(tr, rb.rows)
             data_te = expand_rows(te, rb.rows) if te is not None else None
             yield data_tr, data_te
+
+
+class CondRowBatch(RowBatch):
+    """A batch of conditioned examples: row ``rows[i]`` of the sampler's CSR matrices under condition
+    ``conds[i]`` (-1 = unconditioned).  The engine turns it into [tr row | one-hot(cond)] / filtered te row."""
+
+    __slots__ = ("conds",)
+
+    def __init__(self, sampler, rows, conds):
+        super(CondRowBatch, self).__init__(sampler, rows, True)
+        self.conds = conds          # int32 CUDA tensor [B]
+
+    @property
+    def cond(self):
+        return self.conds, self.sampler.item_mask(self.rows.device)
+
+
+class EmptyConditionedDataSampler(DataSampler):
+    """``EmptyConditionedDataSampler(cond_size, sparse_data_tr, sparse_data_te=None, batch_size=1,
+    shuffle=True)`` (rectorch/samplers.py:341-419): :class:`DataSampler` whose training batches carry
+    ``cond_size`` all-zero condition columns, for evaluating / training a CMultiVAE without conditions.
+    The test matrix defaults to the training matrix (samplers.py:412-413)."""
+
+    def __init__(self, cond_size, sparse_data_tr, sparse_data_te=None, batch_size=1, shuffle=True, device=None):
+        super(EmptyConditionedDataSampler, self).__init__(
+            sparse_data_tr, sparse_data_tr if sparse_data_te is None else sparse_data_te, batch_size, shuffle, device)
+        self.cond_size = cond_size
+
+    def __iter__(self):
+        from ._expand import expand_rows
+        tr, te = self.device_csr()
+        for rb in self.iter_rows():
+            yield expand_rows(tr, rb.rows, width=tr.shape[1] + self.cond_size), expand_rows(te, rb.rows)
+
+
+class ConditionedDataSampler(DataSampler):
+    """``ConditionedDataSampler(iid2cids, n_cond, sparse_data_tr, sparse_data_te=None, batch_size=1,
+    shuffle=True)`` (rectorch/samplers.py:108-232).
+
+    Training examples are (user, condition) pairs: every user once unconditioned (-1) and once per condition
+    that at least one of the user's training items satisfies.  An example's input is the user's training row
+    with the condition one-hot appended, its target the user's test row restricted to the items that satisfy the
+    condition (to items with any condition when unconditioned); examples whose target is empty are dropped from
+    their batch (samplers.py:227-229).  The reference rebuilds these matrices with scipy for every batch; here the
+    example list, an item -> condition bit mask and the validity of every example are computed once (vectorised),
+    the CSR matrices stay in HBM and a batch is a pair of small int32 vectors handed to the engine's conditioned
+    batch builder.  Conditions of a user are enumerated in ascending order.
+    """
+
+    def __init__(self, iid2cids, n_cond, sparse_data_tr, sparse_data_te=None, batch_size=1, shuffle=True, device=None):
+        if n_cond > 64:
+            raise ValueError("at most 64 conditions are supported (item -> condition bit mask)")
+        super(ConditionedDataSampler, self).__init__(
+            sparse_data_tr, sparse_data_tr if sparse_data_te is None else sparse_data_te, batch_size, shuffle, device)
+        self.iid2cids = iid2cids
+        self.n_cond = n_cond
+        self._mask_dev = None
+        self._compute_conditions()
+
+    # -- host precomputation -------------------------------------------------------------------------
+    def _item_cond_matrix(self):
+        from scipy.sparse import csr_matrix
+        rows = [m for m in self.iid2cids for _ in range(len(self.iid2cids[m]))]
+        cols = [g for m in self.iid2cids for g in self.iid2cids[m]]
+        return csr_matrix((np.ones(len(rows)), (rows, cols)), shape=(len(self.iid2cids), self.n_cond))
+
+    @staticmethod
+    def _scipy(m):
+        return m.to_scipy() if hasattr(m, "to_scipy") else m.tocsr()
+
+    def _user_conditions(self):
+        """bool [n_users x n_cond]: the conditions known by each user (union over the training items)."""
+        tr = self._scipy(self.sparse_data_tr)
+        M = self.M
+        if M.shape[0] < tr.shape[1]:          # items missing from iid2cids satisfy no condition
+            from scipy.sparse import vstack, csr_matrix
+            M = vstack([M, csr_matrix((tr.shape[1] - M.shape[0], self.n_cond))], format="csr")
+        self._M_full = M
+        return np.asarray(((tr != 0).astype(np.float64) @ M).todense()) > 0
+
+    def _compute_conditions(self):
+        self.M = self._item_cond_matrix()
+        known = self._user_conditions()
+        n = known.shape[0]
+        r_idx, c_idx = np.nonzero(known)      # row-major: users ascending, conditions ascending
+        self.examples = np.concatenate([np.stack([np.arange(n), np.full(n, -1)], 1),
+                                        np.stack([r_idx, c_idx], 1)]).astype(np.int64)
+        self._finish_examples()
+
+    def _finish_examples(self):
+        te = self._scipy(self.sparse_data_te)
+        cnt = np.asarray(((te != 0).astype(np.float64) @ self._M_full).todense())      # [n_users x n_cond]
+        r, c = self.examples[:, 0], self.examples[:, 1]
+        self._valid = np.where(c >= 0, cnt[r, np.maximum(c, 0)] > 0, cnt[r].sum(1) > 0)
+        mask = np.zeros(self._M_full.shape[0], dtype=np.uint64)
+        coo = self._M_full.tocoo()
+        np.bitwise_or.at(mask, coo.row, np.left_shift(np.uint64(1), coo.col.astype(np.uint64)))
+        self._mask_host = mask
+
+    def item_mask(self, device):
+        if self._mask_dev is None or self._mask_dev.device != torch.device(device):
+            self._mask_dev = torch.from_numpy(self._mask_host.view(np.int64)).to(device)
+        return self._mask_dev
+
+    def __len__(self):
+        return int(np.ceil(len(self.examples) / self.batch_size))
+
+    # -- iteration -------------------------------------------------------------------------------------------
+    def iter_rows(self, device=None):
+        tr, _ = self.device_csr(device)
+        n = len(self.examples)
+        idxlist = list(range(n))
+        if self.shuffle:
+            np.random.shuffle(idxlist)
+        idx = np.asarray(idxlist, dtype=np.int64)
+        for start in range(0, n, self.batch_size):
+            sel = idx[start:min(start + self.batch_size, n)]
+            sel = sel[self._valid[sel]]
+            if sel.size == 0:
+                continue
+            ex = torch.from_numpy(self.examples[sel].astype(np.int32)).to(tr.device)
+            yield CondRowBatch(self, ex[:, 0].contiguous(), ex[:, 1].contiguous())
+
+    def __iter__(self):
+        from ._expand import expand_rows
+        tr, te = self.device_csr()
+        n_items = tr.shape[1]
+        for rb in self.iter_rows():
+            data_tr = expand_rows(tr, rb.rows, width=n_items + self.n_cond)
+            has = rb.conds >= 0
+            rws = torch.nonzero(has).flatten()
+            data_tr[rws, n_items + rb.conds[has].long()] = 1.0
+            mask = self.item_mask(tr.device)
+            shift = rb.conds.clamp(min=0).long()[:, None]
+            bit = torch.bitwise_and(torch.bitwise_right_shift(mask[None, :], shift), 1) != 0
+            filt = torch.where(has[:, None], bit, (mask != 0)[None, :])
+            yield data_tr, expand_rows(te, rb.rows) * filt.to(torch.float32)
+
+
+class BalancedConditionedDataSampler(ConditionedDataSampler):
+    """Sub-sampled :class:`ConditionedDataSampler` (rectorch/samplers.py:235-338): every user unconditioned, plus for
+    each condition ``m = int(n_conditioned_examples * subsample / n_cond)`` users drawn with replacement
+    (``np.random.choice``) among those who know it."""
+
+    def __init__(self, iid2cids, n_cond, sparse_data_tr, sparse_data_te=None, batch_size=1, subsample=.2, device=None):
+        self.subsample = subsample
+        super(BalancedConditionedDataSampler, self).__init__(iid2cids, n_cond, sparse_data_tr, sparse_data_te,
+                                                             batch_size, True, device)
+
+    def _compute_conditions(self):
+        self.M = self._item_cond_matrix()
+        known = self._user_conditions()
+        n = known.shape[0]
+        self.num_cond_examples = int(known.sum())
+        m = int(self.num_cond_examples * self.subsample / self.n_cond)
+        data = [np.stack([np.arange(n), np.full(n, -1)], 1)]
+        for c in range(self.n_cond):
+            users = np.nonzero(known[:, c])[0]
+            if users.size and m > 0:
+                data.append(np.stack([np.random.choice(users, m), np.full(m, c)], 1))
+        self.examples = np.concatenate(data).astype(np.int64)
+        self._finish_examples()
+
+    def __len__(self):
+        m = int(self.num_cond_examples * self.subsample) + self.n_users
+        return int(np.ceil(m / self.batch_size))
 
 
 def _row_slice(m, lo, hi):
