@@ -150,10 +150,12 @@ int  b200vae_adam_step(b200vae_ctx* ctx, float lr, float beta1, float beta2, flo
 
 /* Same update restricted to the arena elements [elem_lo, elem_hi) (tensor boundaries).  Lets a data-parallel
  * caller update the half of the parameters whose gradient all-reduce has finished while the other half's
- * all-reduce is still in flight.  All ranges of one optimisation step use the same `step`. */
+ * all-reduce is still in flight.  All ranges of one optimisation step use the same `step`; the range that
+ * starts at element 0 must be issued last.  narrow != 0 launches a grid of only a few CTAs per SM, for a
+ * range that runs on a second stream beside other kernels (see b200vae_adam_step_split). */
 int  b200vae_adam_step_range(b200vae_ctx* ctx, float lr, float beta1, float beta2, float eps,
                              float weight_decay, float lam, int64_t step, int64_t elem_lo, int64_t elem_hi,
-                             void* stream);
+                             int narrow, void* stream);
 
 /* The Adam schedule of the fused single-GPU step, on gradients that are already in the gradient arena:
  * rows of the encoder-0 weight NOT listed in touched_items have an exactly-zero gradient and are updated by a

@@ -53,7 +53,7 @@ _SIGS = {
     "b200vae_adam_step": (c_int, [c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
                                   c_int64, c_void_p]),
     "b200vae_adam_step_range": (c_int, [c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
-                                        c_int64, c_int64, c_int64, c_void_p]),
+                                        c_int64, c_int64, c_int64, c_int, c_void_p]),
     "b200vae_adam_step_split": (c_int, [c_void_p, c_float, c_float, c_float, c_float, c_float, c_float,
                                         c_int64, c_void_p, c_int32, c_int, c_void_p]),
     "b200vae_train_step": (c_int, [c_void_p, c_void_p, c_int32, c_int, c_float, c_float, c_float,

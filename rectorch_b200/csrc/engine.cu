@@ -786,11 +786,11 @@ int b200vae_enc0_grad(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B_total,
 }
 
 int b200vae_adam_step_range(b200vae_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay,
-                            float lam, int64_t step, int64_t elem_lo, int64_t elem_hi, void* stream) {
+                            float lam, int64_t step, int64_t elem_lo, int64_t elem_hi, int narrow, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     B200_REQUIRE(c, B200VAE_EINVAL, "null context");
     AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
-    return adam_step(c, h, (cudaStream_t)stream, elem_lo, elem_hi);
+    return adam_step(c, h, (cudaStream_t)stream, elem_lo, elem_hi, ADAM_ROWS_ALL, narrow ? c->side_ctas[0] : 8);
 }
 
 int b200vae_sync_weights(b200vae_ctx* ctx, void* stream) {

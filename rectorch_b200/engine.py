@@ -261,13 +261,14 @@ class Engine:
         check(_lib.lib().b200vae_adam_step(self._ctx, float(lr), float(betas[0]), float(betas[1]), float(eps),
                                            float(weight_decay), float(lam), self.adam_steps, stream_ptr()))
 
-    def adam_range(self, lr, betas, eps, weight_decay, lam, lo, hi, first):
-        """Adam on arena elements [lo, hi); ``first`` advances the step counter (one step = all its ranges)."""
+    def adam_range(self, lr, betas, eps, weight_decay, lam, lo, hi, first, narrow=False):
+        """Adam on arena elements [lo, hi) on the current stream; ``first`` advances the step counter (one step = all
+        its ranges, the one starting at 0 last); ``narrow``: a few CTAs per SM, for a range that shares the GPU."""
         if first:
             self.adam_steps += 1
         check(_lib.lib().b200vae_adam_step_range(self._ctx, float(lr), float(betas[0]), float(betas[1]), float(eps),
                                                  float(weight_decay), float(lam), self.adam_steps, int(lo), int(hi),
-                                                 stream_ptr()))
+                                                 1 if narrow else 0, stream_ptr()))
 
     def build_cond_batch(self, rows, conds, item_mask):
         """Conditioned examples (row, cond) -> the context's internal batches: slot 0 = [tr row | one-hot(cond)],
