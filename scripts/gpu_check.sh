@@ -24,6 +24,8 @@ if [ "$1" == "rest" ] || [ -z "$1" ]; then
   run api 600 tests/test_gpu_api.py tests/test_gpu_multi.py
   run parity_fixture 600 tests/test_gpu_parity.py -k "fixture"
   run parity_oracle 900 tests/test_gpu_parity.py -k "not fixture"
+  run overlap 300 tests/test_gpu_overlap.py
+  run cond 300 tests/test_gpu_cond.py
   timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
   echo "smoke exit $?" >> gpurun_out/summary.txt
   tail -n 2 gpurun_out/smoke.log >> gpurun_out/summary.txt

@@ -55,6 +55,8 @@ for i in range(args.reps):
         tot += ms
     totals.append(tot)
 eng.set_timing(False)
+print("# instrumented steps run the SERIAL schedule (one stream); the production step overlaps the decoder-output Adam")
+print("# with the encoder backward on a second stream (profiles/r1_overlap_sweep.txt)")
 print("batch %d  items %d  %s: %.1f us per step (sum of launch intervals, %d launches)" % (
     B, args.items, "MultiDAE" if args.dae else "MultiVAE", 1e3 * np.mean(totals), len(agg)))
 rows = [(k, 1e3 * float(np.mean(v))) for k, v in agg.items()]
