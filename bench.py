@@ -266,6 +266,14 @@ def run_b200(args):
     ms_step = ms_total / K
     value = world * B / (ms_step / 1e3)
 
+    # ---- host cost of issuing one step (python + ctypes + ~26 launches), GPU idle at the start, no sync inside ----
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(20):
+        step(W + K + i)
+    host_us = (time.perf_counter() - t0) / 20 * 1e6
+    barrier()
+
     # ---- e2e: host (pinned) CSR batches through the C ABI, H2D + step + D2H loss every step ----
     from rectorch_b200 import _lib
     from rectorch_b200._lib import check
@@ -416,7 +424,7 @@ def run_b200(args):
                                        % (n_users, B), "global_batch": B * world, "parallelism": ("dp1" if world == 1 else "dp%d row-sharded; %s" % (world, "all-reduce of the decoder-output half of the gradient arena + all-gather of the encoder-0 gradient factors" if args.dp == "factors" else "1 all-reduce of the gradient arena per step")),
                            "schedule": "decoder-output Adam on a second stream beside the encoder backward (B200VAE_OVERLAP=1)" if world == 1 else "gradient all-reduce in two buckets overlapped with backward / Adam",
                            "l2": "no flush: per-step working set (4 x 242 MB arenas) exceeds the 126 MB L2"},
-                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "host_issue_us_per_step": host_us,
                 "roofline": roof_dom, "roofline_k4": roof_k4,
                 "kernel_ms": {n: float(v) for n, v in zip(names, kms)},
                 "cpu_baseline": cpu, "last_loss": last_loss}

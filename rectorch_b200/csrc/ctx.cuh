@@ -101,6 +101,7 @@ struct Ctx {
     int32_t* gl_sp = nullptr;
     float*   gl_xt = nullptr;
     int64_t  gl_rows = 0, gl_nnz = 0;
+    int overlap_host = 3;             // schedule of the host-synchronous entry point (B200VAE_HOST_OVERLAP)
     int side_ctas[2] = {2, 2};        // CTAs per SM of the two side launches (B200VAE_SIDE_CTAS="a,b")
     int side_threads = 256;
 };

@@ -353,6 +353,14 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
     // the decoder-output gradients (the tail of the gradient arena) are final from here on: a data-parallel
     // caller can start reducing them while the rest of the backward pass runs (b200vae_wait_wd_ready)
     B200_CUDA_OK(cudaEventRecord(c->ev_wd, s));
+    if (fused && (fused->ov & 1)) {
+        // fused single-GPU step: hand the decoder-output Adam to the side stream NOW, before the launches of the
+        // encoder backward are issued -- a caller that synchronises every step (b200vae_train_step_host) is
+        // host-bound here, and a side launch issued after them would start too late to overlap anything
+        // (measured: 869 us/step end to end vs 740 us when the host runs ahead)
+        B200_CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_wd, 0));
+        B200_CHECK(adam_step(c, *fused, c->side, c->dec.back().w_off, c->n_elems, ADAM_ROWS_ALL, c->side_ctas[0]));
+    }
 
     // ---------------- backward: hidden decoder layers ----------------
     // invariant: `cur` holds d(loss)/d(pre-activation of the layer below the one being processed)
@@ -461,13 +469,16 @@ static int effective_overlap(const Ctx* c) {
 }
 
 // Adam part of the fused step (`ov` != 0).  Expects: marks of step h.step written before ev_mark (bit 1; the
-// untouched-row launch was already issued by forward_hidden), ev_wd recorded once dW_d / db_d are final.
-static int fused_adam_finish(Ctx* c, const AdamHyper& h, int ov, cudaStream_t s) {
+// untouched-row launch was already issued by forward_hidden), ev_wd recorded once dW_d / db_d are final;
+// tail_issued: forward_backward already put the decoder-output launch on the side stream.
+static int fused_adam_finish(Ctx* c, const AdamHyper& h, int ov, cudaStream_t s, bool tail_issued = false) {
     const int64_t cut = c->dec.back().w_off;
     int64_t head_hi = c->n_elems;
     if (ov & 1) {
-        B200_CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_wd, 0));
-        B200_CHECK(adam_step(c, h, c->side, cut, c->n_elems, ADAM_ROWS_ALL, c->side_ctas[0]));
+        if (!tail_issued) {
+            B200_CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_wd, 0));
+            B200_CHECK(adam_step(c, h, c->side, cut, c->n_elems, ADAM_ROWS_ALL, c->side_ctas[0]));
+        }
         head_hi = cut;
     }
     B200_CUDA_OK(cudaEventRecord(c->ev_side, c->side));
@@ -478,8 +489,16 @@ static int fused_adam_finish(Ctx* c, const AdamHyper& h, int ov, cudaStream_t s)
 
 static int train_step_fused(Ctx* c, const int32_t* row_ids, int B, int use_target, float beta, float p, uint64_t seed,
                             const uint8_t* keep_tape, const float* eps_tape, AdamHyper h, float* loss_out,
-                            cudaStream_t s) {
+                            cudaStream_t s, bool host_sync = false) {
+    // host_sync: the caller synchronises with the host after every step (b200vae_train_step_host), so the GPU
+    // starts each step idle.  Measured [B200, cfg2]: schedule 1 (decoder-output Adam beside the encoder backward)
+    // is the fastest when the host runs ahead (735 us/step; 781 for schedule 3) but the slowest when it does not
+    // (866 us; 826 serial; 794 for schedule 3, whose side stream already has work early in the step; issuing the
+    // side launch earlier in host order or a warm-up no-op on the side stream change nothing: host issue is 124 us).
+    const int saved = c->overlap;
+    if (host_sync) c->overlap = c->overlap_host;
     h.ov = effective_overlap(c);
+    c->overlap = saved;
     if (!h.ov) {
         B200_CHECK(forward_backward(c, row_ids, B, B, use_target, beta, h.lam, p, seed, (uint64_t)h.step, 0, keep_tape,
                                     eps_tape, loss_out, s));
@@ -487,7 +506,7 @@ static int train_step_fused(Ctx* c, const int32_t* row_ids, int B, int use_targe
     }
     B200_CHECK(forward_backward(c, row_ids, B, B, use_target, beta, h.lam, p, seed, (uint64_t)h.step, 0, keep_tape,
                                 eps_tape, loss_out, s, &h));
-    return fused_adam_finish(c, h, h.ov, s);
+    return fused_adam_finish(c, h, h.ov, s, true);
 }
 
 __global__ void k_stamp_rows(const int32_t* __restrict__ items, int n, int n_items, int32_t* __restrict__ mark, int32_t step) {
@@ -565,7 +584,8 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     cudaEventCreateWithFlags(&c->ev_mark, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming);
     if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) c->side = nullptr;
-    if (const char* e = getenv("B200VAE_OVERLAP")) c->overlap = atoi(e) & 3;
+    if (const char* e = getenv("B200VAE_OVERLAP")) c->overlap = c->overlap_host = atoi(e) & 3;
+    if (const char* e = getenv("B200VAE_HOST_OVERLAP")) c->overlap_host = atoi(e) & 3;
     // width of the decoder-output Adam on the side stream: narrow when there are hidden-layer kernels to share
     // the SMs with (cfg2: 2 CTAs/SM = 743 us/step vs 778 at 8), full width when the backward tail is only the
     // sparse scatter (cfg3, one hidden layer: 386 us at 8 vs 392 at 2)            [B200, profiles/r1_overlap_sweep.txt]
@@ -931,7 +951,7 @@ int b200vae_train_step_host(b200vae_ctx* ctx, const int64_t* indptr_host, const 
         B200_CUDA_OK(cudaMemcpyAsync(S.int_values, values_host, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, s));
     S.int_has_values = values_host != nullptr;
     AdamHyper h = {lr, 0.9f, 0.999f, 1e-8f, weight_decay, lam, step};
-    B200_CHECK(train_step_fused(c, nullptr, B, 0, beta, dropout_p, seed, nullptr, nullptr, h, c->loss_dev, s));
+    B200_CHECK(train_step_fused(c, nullptr, B, 0, beta, dropout_p, seed, nullptr, nullptr, h, c->loss_dev, s, true));
     B200_CUDA_OK(cudaMemcpyAsync(loss_host, c->loss_dev, 4 * sizeof(float), cudaMemcpyDeviceToHost, s));
     B200_CUDA_OK(cudaStreamSynchronize(s));
     return 0;

@@ -576,9 +576,36 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// 2-D fp32 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, row pitch ld floats
+// 2-D fp32 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, row pitch ld floats.
+// A training step issues the same eight descriptors every time (same buffers, same shapes), and encoding one
+// costs a few microseconds of host time on a path that is host-bound when the caller synchronises per step:
+// descriptors are cached by their full key.
+struct TmapKey {
+    const float* base; int64_t inner, outer, ld; int box_inner, box_outer; bool mn_major;
+    bool operator==(const TmapKey& o) const {
+        return base == o.base && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
+               box_outer == o.box_outer && mn_major == o.mn_major;
+    }
+};
+static int make_tmap_uncached(CUtensorMap* tm, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                              int box_outer, bool mn_major);
 static int make_tmap(CUtensorMap* tm, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
                      int box_outer, bool mn_major) {
+    constexpr int CAP = 32;
+    static thread_local TmapKey keys[CAP];
+    static thread_local CUtensorMap maps[CAP];
+    static thread_local int used = 0, next = 0;
+    const TmapKey k = {base, inner, outer, ld, box_inner, box_outer, mn_major};
+    for (int i = 0; i < used; ++i)
+        if (keys[i] == k) { *tm = maps[i]; return 0; }
+    B200_CHECK(make_tmap_uncached(tm, base, inner, outer, ld, box_inner, box_outer, mn_major));
+    const int slot = used < CAP ? used++ : (next++ % CAP);
+    keys[slot] = k;
+    maps[slot] = *tm;
+    return 0;
+}
+static int make_tmap_uncached(CUtensorMap* tm, const float* base, int64_t inner, int64_t outer, int64_t ld, int box_inner,
+                              int box_outer, bool mn_major) {
     EncodeTiledFn enc = get_encode();
     B200_REQUIRE(enc, B200VAE_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
