@@ -150,3 +150,37 @@ def test_ingest_errors(tmp_path):
         fh.write("uid,iid\n")
     m = read_csv_csr(p, 5)
     assert m.shape == (0, 5) and m.nnz == 0
+
+
+def test_ingest_random_files_match_scipy(tmp_path):
+    """Property check: random small files (duplicates, unsorted records, blank lines, '3.0'-style ids, spaces)
+    parse to exactly what scipy builds from the same triples."""
+    rng = np.random.default_rng(7)
+    for case in range(25):
+        n_users, n_items = int(rng.integers(1, 12)), int(rng.integers(1, 9))
+        n = int(rng.integers(0, 40))
+        u = rng.integers(0, n_users, n)
+        i = rng.integers(0, n_items, n)
+        v = rng.integers(-4, 9, n) / 4.0
+        rated = bool(case % 2)
+        lines = []
+        for a, b, c in zip(u.tolist(), i.tolist(), v.tolist()):
+            ua = ("%d.0" % a) if case % 5 == 0 else ("%d" % a)
+            rec = "%s, %d" % (ua, b) if case % 7 == 0 else "%s,%d" % (ua, b)
+            lines.append(rec + ((",%r" % c) if rated else ""))
+            if case % 3 == 0 and rng.random() < 0.2:
+                lines.append("")
+        p = os.path.join(tmp_path, "f%d.csv" % case)
+        with open(p, "w") as fh:
+            fh.write("uid,iid,rating\n" if rated else "uid,iid\n")
+            fh.write("\n".join(lines))
+            if case % 4:
+                fh.write("\n")
+        m = read_csv_csr(p, n_items, topn=not rated, n_rows=n_users)
+        vals = v if rated else np.ones(n)
+        ref = sparse.csr_matrix((vals, (u, i)), shape=(n_users, n_items), dtype=np.float64)
+        ref.sum_duplicates()
+        ref.sort_indices()
+        assert m.shape == ref.shape
+        assert np.array_equal(m.indptr, ref.indptr) and np.array_equal(m.indices, ref.indices), case
+        assert np.allclose(m.data, ref.data, rtol=0, atol=1e-12), case
