@@ -461,9 +461,10 @@ static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo, i
 // The side launches are narrow grid-stride kernels (side_ctas CTAs per SM) so the small kernels of the main stream
 // run beside them; the tcgen05 kernels need whole SMs and simply start when a side launch has drained.  Every
 // element sees exactly the arithmetic of the one-launch Adam (same adam_one, gradient +0 for untouched rows).
-static int effective_overlap(const Ctx* c) {
+// schedule bits that can actually be used out of the requested ones (B200VAE_OVERLAP semantics)
+static int effective_overlap(const Ctx* c, int requested) {
     const Layer& E0 = c->enc[0];
-    int ov = (c->timing || !c->side) ? 0 : c->overlap;
+    int ov = (c->timing || !c->side) ? 0 : (requested & 3);
     if (E0.out % 4 != 0 || E0.w_off % 4 != 0) ov &= ~2;      // the row filter works on whole float4s
     return ov;
 }
@@ -495,10 +496,7 @@ static int train_step_fused(Ctx* c, const int32_t* row_ids, int B, int use_targe
     // is the fastest when the host runs ahead (735 us/step; 781 for schedule 3) but the slowest when it does not
     // (866 us; 826 serial; 794 for schedule 3, whose side stream already has work early in the step; issuing the
     // side launch earlier in host order or a warm-up no-op on the side stream change nothing: host issue is 124 us).
-    const int saved = c->overlap;
-    if (host_sync) c->overlap = c->overlap_host;
-    h.ov = effective_overlap(c);
-    c->overlap = saved;
+    h.ov = effective_overlap(c, host_sync ? c->overlap_host : c->overlap);
     if (!h.ov) {
         B200_CHECK(forward_backward(c, row_ids, B, B, use_target, beta, h.lam, p, seed, (uint64_t)h.step, 0, keep_tape,
                                     eps_tape, loss_out, s));
@@ -841,10 +839,7 @@ int b200vae_adam_step_split(b200vae_ctx* ctx, float lr, float beta1, float beta2
     B200_REQUIRE(c && (touched_items || n_touched == 0) && n_touched >= 0, B200VAE_EINVAL, "bad argument");
     B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
     AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
-    const int saved = c->overlap;
-    c->overlap = overlap_bits & 3;
-    h.ov = effective_overlap(c);
-    c->overlap = saved;
+    h.ov = effective_overlap(c, overlap_bits);
     if (!h.ov) return adam_step(c, h, s);
     if (lam != 0.f) {
         B200_CHECK(launch_tensor_norms(c, c->w, c->d_toff, c->d_tlen, c->n_tensors, c->norm_partial, c->norms, s));
