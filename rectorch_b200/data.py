@@ -6,9 +6,15 @@ CSV files are parsed and turned into CSR by the multi-threaded host ingest of li
 (``b200vae_csv_*``, csrc/ingest.cu) instead of ``pd.read_csv`` + ``csr_matrix((values, (rows, cols)))``.
 The matrices go straight into :class:`rectorch_b200.samplers.DataSampler`, which uploads them to HBM once.
 
-Not mirrored (host-side ETL outside the training path): ``DataProcessing`` (raw csv ->
-pre-processed files) and ``DataReader.load_data_as_dict`` (sequence view used by SVAE only).
+``DataProcessing(data_config).process()`` (data.py:46-325) is restated with numpy only: the reference's version
+depends on pandas group-by semantics that current pandas releases no longer have (``groupby(..., as_index=False)
+.size()`` returning a Series), so it cannot run in this environment; the restatement follows its steps and its
+``numpy.random`` call sequence one by one and is pinned by the exact file contents the reference's own tests expect
+(tests/test_data.py:14-101, 280-350).
+
+Not mirrored: ``DataReader.load_data_as_dict`` (sequence view used by SVAE only).
 """
+import logging
 import ctypes
 import os
 
@@ -19,7 +25,9 @@ from . import _lib
 from ._lib import check
 from .configuration import DataConfig
 
-__all__ = ['DataReader', 'DatasetManager', 'read_csv_csr']
+__all__ = ['DataProcessing', 'DataReader', 'DatasetManager', 'read_csv_csr']
+
+logger = logging.getLogger(__name__)
 
 
 class _Csv:
@@ -72,6 +80,180 @@ def read_csv_csr(path, n_items, topn=True, uid_base=None, n_rows=None, sep=","):
         return f.to_csr(base, max(rows, 0), n_items, not topn)
     finally:
         f.close()
+
+
+def _as_column(values):
+    """pandas-style inference of one raw column: int64 if every field is an integer literal, else float64 if every
+    field parses as a float, else the strings themselves."""
+    try:
+        return np.array([int(v) for v in values], dtype=np.int64)
+    except ValueError:
+        pass
+    try:
+        return np.array([float(v) for v in values], dtype=np.float64)
+    except ValueError:
+        return np.array(values, dtype=object)
+
+
+def _fmt(v):
+    """Field formatting of DataFrame.to_csv / '%s' for the inferred column types."""
+    if isinstance(v, (np.floating, float)):
+        return repr(float(v))
+    return str(v)
+
+
+class DataProcessing:
+    """Pre-processing of a raw rating file into the ``proc_path`` folder (rectorch/data.py:46-325).
+
+    ``DataProcessing(data_config)`` takes a :class:`DataConfig` or the path of its JSON file (anything else raises
+    :class:`TypeError`); :meth:`process` runs the reference's pipeline: read the csv, keep ratings above
+    ``threshold``, drop items / users with fewer than ``i_min`` / ``u_min`` ratings, permute the users
+    (``np.random.permutation`` under ``seed``) and split them into training / validation / test users
+    (``heldout`` each for the last two), restrict validation / test ratings to training items, drop held-out users
+    with fewer than two ratings, split each held-out user's ratings into a training and a test part
+    (``test_prop``, at least one test item, ``np.random.choice`` under a re-seeded generator), build the id maps
+    (``u2id`` / ``i2id``) and write ``train.csv``, ``validation_{tr,te}.csv``, ``test_{tr,te}.csv``,
+    ``unique_uid.txt`` and ``unique_iid.txt``.
+    """
+
+    def __init__(self, data_config):
+        if isinstance(data_config, DataConfig):
+            self.cfg = data_config
+        elif isinstance(data_config, str):
+            self.cfg = DataConfig(data_config)
+        else:
+            raise TypeError("'data_config' must be of type 'DataConfig' or 'str'.")
+        self.i2id = {}
+        self.u2id = {}
+
+    # -- raw file ------------------------------------------------------------------------------------------
+    def _read_raw(self):
+        sep = self.cfg.separator if self.cfg.separator else ','
+        with open(self.cfg.data_path, "r") as fh:
+            lines = [ln.rstrip("\r\n") for ln in fh if ln.strip()]
+        names = None
+        if self.cfg.header is not None:              # pandas: header=<row number of the column names>
+            h = int(self.cfg.header)
+            names = lines[h].split(sep)
+            lines = lines[h + 1:]
+        fields = [ln.split(sep) for ln in lines]
+        n_cols = len(fields[0]) if fields else 0
+        cols = [_as_column([f[c].strip() for f in fields]) for c in range(n_cols)]
+        if names is None:
+            names = list(range(n_cols))             # header=None: pandas names the columns 0, 1, 2, ...
+        return names, cols
+
+    @staticmethod
+    def _counts(keys):
+        """group-by size: (sorted unique keys, count of each)."""
+        return np.unique(keys, return_counts=True)
+
+    def _split_train_test(self, uid, rows):
+        """data.py:290-312 on row indices: per held-out user (ascending id) mark max(int(test_prop * n), 1) of the
+        n ratings as test items with np.random.choice (generator re-seeded with cfg.seed)."""
+        np.random.seed(self.cfg.seed)
+        test_prop = float(self.cfg.test_prop) if self.cfg.test_prop else 0.2
+        tr_list, te_list = [], []
+        users = np.unique(uid[rows])
+        for u in users:
+            grp = rows[uid[rows] == u]
+            n_items_u = len(grp)
+            if n_items_u > 1:
+                idx = np.zeros(n_items_u, dtype='bool')
+                sz = max(int(test_prop * n_items_u), 1)
+                idx[np.random.choice(n_items_u, size=sz, replace=False).astype('int64')] = True
+                tr_list.append(grp[np.logical_not(idx)])
+                te_list.append(grp[idx])
+            else:
+                logger.warning("Skipped user in test set: number of ratings <= 1.")
+        cat = lambda lst: np.concatenate(lst) if lst else np.zeros(0, dtype=np.int64)   # noqa: E731
+        return cat(tr_list), cat(te_list)
+
+    def process(self):
+        """Run the whole pre-processing (data.py:98-213)."""
+        np.random.seed(int(self.cfg.seed))
+        logger.info("Reading data file %s.", self.cfg.data_path)
+        names, cols = self._read_raw()
+        keep = np.arange(len(cols[0]) if cols else 0)
+        if self.cfg.threshold:
+            keep = keep[cols[2][keep] > float(self.cfg.threshold)]
+        logger.info("Applying filtering.")
+        uid, iid = cols[0], cols[1]
+        imin, umin = int(self.cfg.i_min), int(self.cfg.u_min)
+        if imin > 0:
+            items, cnt = self._counts(iid[keep])
+            keep = keep[np.isin(iid[keep], items[cnt >= imin])]
+        if umin > 0:
+            users, cnt = self._counts(uid[keep])
+            keep = keep[np.isin(uid[keep], users[cnt >= umin])]
+        unique_uid = np.unique(uid[keep])                       # group-by index: ascending user ids
+        idx_perm = np.random.permutation(unique_uid.size)
+        unique_uid = unique_uid[idx_perm]
+        n_users = unique_uid.size
+        n_heldout = int(self.cfg.heldout)
+
+        logger.info("Calculating splits.")
+        tr_users = unique_uid[:(n_users - n_heldout * 2)]
+        vd_users = unique_uid[(n_users - n_heldout * 2): (n_users - n_heldout)]
+        te_users = unique_uid[(n_users - n_heldout):]
+        train_rows = keep[np.isin(uid[keep], tr_users)]
+        _, first = np.unique(iid[train_rows], return_index=True)
+        unique_iid = iid[train_rows][np.sort(first)]            # pd.unique: order of first appearance
+
+        logger.info("Creating validation and test set.")
+
+        def heldout_rows(users):
+            rows = keep[np.isin(uid[keep], users)]
+            rows = rows[np.isin(iid[rows], unique_iid)]
+            us, cnt = self._counts(uid[rows])
+            kept = rows[np.isin(uid[rows], us[cnt >= 2])]
+            return kept, len(us) - len(np.unique(uid[kept]))
+
+        val_rows, vdiff = heldout_rows(vd_users)
+        test_rows, tdiff = heldout_rows(te_users)
+        if vdiff > 0:
+            logger.warning("Skipped %d users in validation set.", vdiff)
+        if tdiff > 0:
+            logger.warning("Skipped %d users in test set.", tdiff)
+        val_tr, val_te = self._split_train_test(uid, val_rows)
+        test_tr, test_te = self._split_train_test(uid, test_rows)
+
+        us = set(np.unique(uid[val_rows]).tolist()) | set(np.unique(uid[test_rows]).tolist())
+        unique_uid = list(unique_uid.tolist())
+        unique_uid = unique_uid[:len(tr_users)] + [u for u in unique_uid[len(tr_users):] if u in us]
+        self.i2id = dict((i, k) for (k, i) in enumerate(unique_iid.tolist()))
+        self.u2id = dict((u, k) for (k, u) in enumerate(unique_uid))
+
+        pro_dir = self.cfg.proc_path
+        if not os.path.exists(pro_dir):
+            os.makedirs(pro_dir)
+        logger.info("Saving unique_iid.txt.")
+        with open(os.path.join(pro_dir, 'unique_iid.txt'), 'w') as f:
+            for i in unique_iid.tolist():
+                f.write('%s\n' % _fmt(i))
+        logger.info("Saving unique_uid.txt.")
+        with open(os.path.join(pro_dir, 'unique_uid.txt'), 'w') as f:
+            for u in unique_uid:
+                f.write('%s\n' % _fmt(u))
+
+        logger.info("Saving all the files.")
+        extra = [] if self.cfg.topn else list(range(2, len(cols)))
+
+        def save(name, rows):
+            with open(os.path.join(pro_dir, name), 'w') as f:
+                f.write(",".join(['uid', 'iid'] + [str(names[c]) for c in extra]) + "\n")
+                for r in rows.tolist():
+                    rec = [str(self.u2id[uid[r].item() if hasattr(uid[r], "item") else uid[r]]),
+                           str(self.i2id[iid[r].item() if hasattr(iid[r], "item") else iid[r]])]
+                    rec += [_fmt(cols[c][r]) for c in extra]
+                    f.write(",".join(rec) + "\n")
+
+        save('train.csv', train_rows)
+        save('validation_tr.csv', val_tr)
+        save('validation_te.csv', val_te)
+        save('test_tr.csv', test_tr)
+        save('test_te.csv', test_te)
+        logger.info("Preprocessing complete!")
 
 
 class DataReader():

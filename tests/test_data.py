@@ -184,3 +184,88 @@ def test_ingest_random_files_match_scipy(tmp_path):
         assert m.shape == ref.shape
         assert np.array_equal(m.indptr, ref.indptr) and np.array_equal(m.indices, ref.indices), case
         assert np.allclose(m.data, ref.data, rtol=0, atol=1e-12), case
+
+
+RAW = ("1 1 4\n1 2 5\n1 3 2\n1 5 4\n" "2 2 3\n2 3 1\n2 5 4\n" "3 1 5\n3 2 5\n3 4 3\n3 5 4\n" "4 1 1\n4 3 4\n4 4 2\n4 5 4\n")
+
+
+def _process(tmp_path, raw, cfg_extra, sep=" "):
+    from rectorch_b200.data import DataProcessing
+    rp = os.path.join(tmp_path, "raw.txt")
+    with open(rp, "w") as fh:
+        fh.write(raw)
+    out = os.path.join(tmp_path, "proc")
+    cfg = {"data_path": rp, "proc_path": out, "seed": 42, "threshold": 2.5, "separator": sep, "u_min": 1, "i_min": 1,
+           "heldout": 1, "test_prop": 0.5}
+    cfg.update(cfg_extra)
+    cp = os.path.join(tmp_path, "cfg.json")
+    json.dump(cfg, open(cp, "w"))
+    dp = DataProcessing(cp)
+    dp.process()
+    return dp, cp, {n: open(os.path.join(out, n)).read() for n in os.listdir(out)}
+
+
+def test_DataProcessing_reference_known_answers_topn(tmp_path):
+    """Exact file contents expected by rectorch/tests/test_data.py:14-101 (they depend on the numpy RNG call
+    sequence: user permutation and the per-user train/test choice)."""
+    from rectorch_b200.data import DataProcessing
+    with pytest.raises(TypeError):
+        DataProcessing(1)
+    dp, cp, files = _process(tmp_path, RAW, {"topn": 1})
+    assert set(files) == {'validation_te.csv', 'validation_tr.csv', 'unique_iid.txt', 'unique_uid.txt', 'test_tr.csv',
+                          'test_te.csv', 'train.csv'}
+    assert files['train.csv'] == 'uid,iid\n0,0\n0,1\n1,2\n1,1\n'
+    assert files['unique_iid.txt'] == '2\n5\n3\n'
+    assert files['unique_uid.txt'] == '2\n4\n1\n3\n'
+    assert files['validation_tr.csv'] == 'uid,iid\n2,0\n' and files['validation_te.csv'] == 'uid,iid\n2,1\n'
+    assert files['test_tr.csv'] == 'uid,iid\n3,0\n' and files['test_te.csv'] == 'uid,iid\n3,1\n'
+    assert DataProcessing(DataConfig(cp)).cfg == dp.cfg
+    assert dp.u2id == {2: 0, 4: 1, 1: 2, 3: 3} and dp.i2id == {2: 0, 5: 1, 3: 2}
+    sp = DataReader(cp).load_data("full")             # and the reader takes it from there (test_data.py:153-162)
+    r, c = sp.nonzero()
+    assert np.all(r == np.array([0, 0, 1, 1, 2, 2, 3, 3])) and np.all(c == np.array([0, 1, 1, 2, 0, 1, 0, 1]))
+
+
+def test_DataProcessing_reference_known_answers_rated(tmp_path):
+    """rectorch/tests/test_data.py:280-359 (no ``topn`` key: the rating column is kept, named after its position)."""
+    _, cp, files = _process(tmp_path, RAW, {})
+    assert files['train.csv'] == 'uid,iid,2\n0,0,3\n0,1,4\n1,2,4\n1,1,4\n'
+    assert files['validation_tr.csv'] == 'uid,iid,2\n2,0,5\n' and files['validation_te.csv'] == 'uid,iid,2\n2,1,4\n'
+    assert files['test_tr.csv'] == 'uid,iid,2\n3,0,5\n' and files['test_te.csv'] == 'uid,iid,2\n3,1,4\n'
+    sp = DataReader(cp).load_data("full")
+    assert np.all(sp.data == np.array([3., 4., 4., 4., 5., 4., 5., 4.]))
+
+
+def test_DataProcessing_pipeline_invariants(tmp_path):
+    """A larger file with a header, string user ids and float ratings: every step's contract holds and the reader
+    can load what was written."""
+    rng = np.random.default_rng(3)
+    n_users, n_items = 120, 60
+    lines = ["user,item,rating,ts"]
+    for u in range(n_users):
+        for i in rng.choice(n_items, size=int(rng.integers(1, 15)), replace=False):
+            lines.append("u%03d,%d,%s,%d" % (u, 100 + i, repr(float(rng.integers(1, 11)) / 2), 1000 + u))
+    dp, cp, files = _process(tmp_path, "\n".join(lines) + "\n",
+                             {"header": 0, "threshold": 1.0, "u_min": 3, "i_min": 2, "heldout": 15, "test_prop": 0.2,
+                              "seed": 7}, sep=",")
+    uids = files['unique_uid.txt'].split()
+    iids = files['unique_iid.txt'].split()
+    assert len(set(uids)) == len(uids) and all(u.startswith("u") for u in uids) and len(set(iids)) == len(iids)
+    assert files['train.csv'].splitlines()[0] == "uid,iid,rating,ts"
+    reader = DataReader(cp)
+    assert reader.n_items == len(iids)
+    tr = reader.load_data("train")
+    vtr, vte = reader.load_data("validation")
+    ttr, tte = reader.load_data("test")
+    n_tr = len(uids) - vtr.shape[0] - ttr.shape[0]
+    assert tr.shape == (n_tr, len(iids)) and n_tr == len(uids) - 2 * 15 + (15 - vtr.shape[0]) + (15 - ttr.shape[0])
+    assert np.diff(tr.indptr).min() >= 3                                   # u_min survived the item filter order
+    for a, b in ((vtr, vte), (ttr, tte)):
+        assert a.shape == b.shape and a.shape[0] <= 15
+        la, lb = np.diff(a.indptr), np.diff(b.indptr)
+        assert la.min() >= 1 and lb.min() >= 1                            # at least one item on each side
+        assert np.all(lb == np.maximum((0.2 * (la + lb)).astype(int), 1))  # test_prop with the at-least-one rule
+        assert a.multiply(b).nnz == 0                                       # the two parts are disjoint
+    assert tr.data.min() > 1.0                                              # threshold applied (values kept: no topn)
+    full = reader.load_data("full")
+    assert full.shape == (len(uids), len(iids)) and full.nnz == tr.nnz + vtr.nnz + vte.nnz + ttr.nnz + tte.nnz
