@@ -90,13 +90,11 @@ int launch_build_cond_batch(Ctx* c, const int32_t* ex_rows, const int32_t* ex_co
                             const uint64_t* item_cond_mask, cudaStream_t s);
 int launch_target_fixup(Ctx* c, const BatchView& tgt, float* PT, int64_t ldp, const float* rowscale, float inv_Bg,
                         float* loss_row, cudaStream_t s);
-int launch_spmm_zero(Ctx* c, const BatchView& v, const float* vals, int H, float* dWt, cudaStream_t s);
 int launch_row_sums(Ctx* c, const BatchView& v, float* out, cudaStream_t s);
 int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const float* Wt, int H,
                        const float* bias, int act, float* out, cudaStream_t s);
 int launch_spmm_scatter(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
                         int H, float* dWt, cudaStream_t s);
-int launch_bias_scatter(Ctx* c, const BatchView& v, float scale, float* db, cudaStream_t s);
 int launch_spmm_scatter_bias(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
                              int H, float* dWt, float* db, cudaStream_t s);
 int launch_dense_count(Ctx* c, const float* dense, int B, int I, int64_t* lens, cudaStream_t s);
@@ -149,8 +147,6 @@ int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float
                 const float* norm_ptr, float* shadow, int64_t sh_lo, int64_t sh_hi, int64_t z_lo, int64_t z_hi,
                 const AdamOpt& opt, cudaStream_t s);
 int launch_round_tf32(Ctx* c, const float* x, float* y, int64_t n, cudaStream_t s);
-int launch_tanh_grad(Ctx* c, float* d, const float* y, int64_t n, cudaStream_t s);
-int launch_axpy(Ctx* c, float* y, const float* x, float a, int64_t n, cudaStream_t s);
 
 // topk.cu
 int launch_topk_metrics(Ctx* c, const float* scores, int I, const BatchView& gt, const int32_t* kinds,

@@ -307,33 +307,6 @@ int launch_round_tf32(Ctx* c, const float* x, float* y, int64_t n, cudaStream_t 
     return 0;
 }
 
-__global__ void k_tanh_grad(float* __restrict__ d, const float* __restrict__ y, int64_t n) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        float t = y[i];
-        d[i] *= (1.f - t * t);
-    }
-}
-int launch_tanh_grad(Ctx* c, float* d, const float* y, int64_t n, cudaStream_t s) {
-    if (n == 0) return 0;
-    k_tanh_grad<<<(int)cdiv(n, 256), 256, 0, s>>>(d, y, n);
-    note(c, __func__, s);
-    B200_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-__global__ void k_axpy(float* __restrict__ y, const float* __restrict__ x, float a, int64_t n) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) y[i] = fmaf(a, x[i], y[i]);
-}
-int launch_axpy(Ctx* c, float* y, const float* x, float a, int64_t n, cudaStream_t s) {
-    if (n == 0) return 0;
-    k_axpy<<<(int)cdiv(n, 256), 256, 0, s>>>(y, x, a, n);
-    note(c, __func__, s);
-    B200_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
 }  // namespace b200
 
 // ------------------------------------------------------------------------------------------

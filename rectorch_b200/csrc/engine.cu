@@ -160,12 +160,6 @@ static int forward_hidden(Ctx* c, FwdState* st, int B, bool train, float p, uint
     return 0;
 }
 
-// row-scale helper: rs[r] = T[r] * a
-__global__ void k_scale_rows(const float* __restrict__ T, float a, int B, float* __restrict__ rs) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < B) rs[i] = T[i] * a;
-}
-
 // h [B x H] -> h_r [B x H] (tf32-rounded copy) and hT [(H+8) x Bp]: rows 0..H-1 = h_r^T, row H = 1
 // (bias-gradient column), rest 0.
 __global__ void k_transpose_ones(const float* __restrict__ h, int B, int H, int Bp, float* __restrict__ hT,

@@ -385,68 +385,6 @@ int launch_spmm_scatter_bias(Ctx* c, const BatchView& v, const float* vals, floa
     return 0;
 }
 
-// Re-zero exactly the gradient rows a batch touched (after Adam consumed them): the dense encoder-0
-// gradient stays all-zero between steps without a 4*I*H-byte memset per step.
-template <int VEC>
-__global__ void __launch_bounds__(256)
-k_spmm_zero(BatchView v, const float* __restrict__ vals, int H, float* __restrict__ dWt) {
-    if ((int)blockIdx.x >= v.sp[v.B]) return;
-    const int r = find_row(v.sp, v.B, blockIdx.x);
-    const int seg = blockIdx.x - v.sp[r];
-    const int64_t gr = v.row_ids ? (int64_t)v.row_ids[r] : (int64_t)r;
-    const int64_t a = v.indptr[gr];
-    const int len = (int)(v.indptr[gr + 1] - a);
-    const int k0 = seg * SPMM_SEG, k1 = min(len, k0 + SPMM_SEG);
-    const float* xv = vals ? vals + v.bp[r] : nullptr;
-    const int32_t* cols = v.indices + a;
-    for (int h0 = threadIdx.x * VEC; h0 < H; h0 += blockDim.x * VEC) {
-        for (int k = k0; k < k1; ++k) {
-            if (xv && xv[k] == 0.f) continue;
-            float* row = dWt + (int64_t)cols[k] * H + h0;
-            if (VEC == 4) *reinterpret_cast<float4*>(row) = make_float4(0.f, 0.f, 0.f, 0.f);
-            else *row = 0.f;
-        }
-    }
-}
-
-int launch_spmm_zero(Ctx* c, const BatchView& v, const float* vals, int H, float* dWt, cudaStream_t s) {
-    if (v.B == 0) return 0;
-    bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(dWt) & 15) == 0);
-    const int grid = spmm_grid(c, v);
-    if (vec) {
-        int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));
-        k_spmm_zero<4><<<grid, threads, 0, s>>>(v, vals, H, dWt);
-    } else {
-        int threads = (int)std::min<int64_t>(256, round_up(H, 32));
-        k_spmm_zero<1><<<grid, threads, 0, s>>>(v, vals, H, dWt);
-    }
-    note(c, __func__, s);
-    B200_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-// db[col_k] += scale * value_k     (sparse part of the decoder bias gradient)
-__global__ void k_bias_scatter(BatchView v, float scale, float* __restrict__ db) {
-    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    int lane = threadIdx.x & 31;
-    if (warp >= v.B) return;
-    int64_t gr = v.row_ids ? (int64_t)v.row_ids[warp] : (int64_t)warp;
-    int64_t a = v.indptr[gr], b = v.indptr[gr + 1];
-    for (int64_t k = a + lane; k < b; k += 32) {
-        float x = v.values ? v.values[k] : 1.f;
-        atomicAdd(db + v.indices[k], scale * x);
-    }
-}
-
-int launch_bias_scatter(Ctx* c, const BatchView& v, float scale, float* db, cudaStream_t s) {
-    if (v.B == 0) return 0;
-    int threads = 256;
-    k_bias_scatter<<<(int)cdiv((int64_t)v.B * 32, threads), threads, 0, s>>>(v, scale, db);
-    note(c, __func__, s);
-    B200_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
 // ------------------------------------------------------------------------------------------
 // dense <-> CSR
 // ------------------------------------------------------------------------------------------
