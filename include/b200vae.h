@@ -53,7 +53,8 @@ typedef struct {
     int32_t max_batch;                       /* rows per call, capacity                       */
     int64_t max_batch_nnz;                   /* non-zeros per batch, capacity (input+target)  */
     int32_t use_tensor_cores;                /* 1 = tcgen05 path for the item-sized GEMMs when
-                                                shapes allow (default), 0 = fp32 SIMT kernels */
+                                                shapes allow (last hidden width % 8 == 0, n_items >= 1024;
+                                                default), 0 = fp32 SIMT kernels */
     int32_t cond_dim;                        /* CMultiVAE_net(cond_dim, ...) (nets.py:455-480): the encoder input is
                                                 [n_items ratings | cond_dim condition flags], enc_dims[0] ==
                                                 n_items + cond_dim; the condition columns bypass F.normalize and
@@ -76,7 +77,7 @@ int  b200vae_ctx_destroy(b200vae_ctx* ctx);
 int  b200vae_bind_params(b200vae_ctx* ctx, float* w, float* g, float* m, float* v,
                          int64_t n_elems, const int64_t* w_off, const int64_t* b_off);
 
-/* Refresh the copies the engine derives from the weight arena (the tf32-rounded image of
+/* Refresh the copies the engine derives from the weight arena (the fp16 image of
  * the decoder output weight that the tensor cores read).  b200vae_adam_step keeps them in
  * step; call this after anything else wrote the arena (init_weights, load_state_dict,
  * nets.py:235-247 / models.py:513). */
@@ -229,20 +230,24 @@ int  b200vae_kl_rows(const float* mu, const float* logvar, int32_t B, int32_t L,
 
 /* ---- per-kernel entry points (unit parity tests, ncu captures) ---------------------- */
 
-/* C[M x N] = A[M x K] * B^T  with tcgen05 TF32 (fp32 accumulate in TMEM).
+/* C[M x N] = A[M x K] * B^T  with tcgen05 kind::f16 (fp16 operands, fp32 accumulate in TMEM).
+ * A, B are IEEE fp16 arrays.
  * a_mn_major = 0: A is [M x K] row-major (K contiguous); 1: A is given as [K x M] (M contiguous)
  * b_mn_major = 0: B is [N x K] row-major (K contiguous); 1: B is given as [K x N] (N contiguous)
- * Leading dimensions in elements; must be multiples of 4; pointers 16-byte aligned. */
-int  b200vae_gemm_tf32(b200vae_ctx* ctx, const float* A, int64_t lda, int a_mn_major,
-                       const float* B, int64_t ldb, int b_mn_major,
-                       float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, void* stream);
+ * Leading dimensions in elements; must be multiples of 8; pointers 16-byte aligned.
+ * Replaces: the torch.nn.functional.linear call sites of the item-sized layers (nets.py:417, their autograd
+ * backward at models.py:832), whose operands the engine keeps as fp16 images (10-bit mantissa, like tf32). */
+int  b200vae_gemm_f16(b200vae_ctx* ctx, const void* A, int64_t lda, int a_mn_major,
+                      const void* B, int64_t ldb, int b_mn_major,
+                      float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, void* stream);
 
 /* K4 standalone: lse[r] = log sum_j exp(h[r,:].W[j,:] + b[j]) for r < B without
  * materialising the [B x n_items] logits (F.log_softmax over the decoder output,
- * models.py:813 / nets.py:417).  h [B x H] row-major, W [n_items x H] row-major.
+ * models.py:813 / nets.py:417).  h16 [B x H] and W16 [n_items x H] are row-major fp16 arrays (H % 8 == 0),
+ * bias is fp32.
  * lse == NULL launches only the fused GEMM + log-sum-exp kernel (the per-tile partials stay in
  * the context's workspace): used to time that kernel back to back. */
-int  b200vae_dec_fwd_lse(b200vae_ctx* ctx, const float* h, const float* W, const float* bias,
+int  b200vae_dec_fwd_lse(b200vae_ctx* ctx, const void* h16, const void* W16, const float* bias,
                          int32_t B, int32_t n_items, int32_t H, float* lse, void* stream);
 
 /* Introspection for bench.py: kernels launched by this context since the last reset. */

@@ -76,7 +76,7 @@ _SIGS = {
                                          c_void_p, c_int64, c_void_p]),
     "b200vae_multinomial_nll_rows": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "b200vae_kl_rows": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
-    "b200vae_gemm_tf32": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int,
+    "b200vae_gemm_f16": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int,
                                   c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p]),
     "b200vae_dec_fwd_lse": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                     c_void_p, c_void_p]),

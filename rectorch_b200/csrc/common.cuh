@@ -1,6 +1,7 @@
 // common.cuh -- shared declarations of the b200vae engine (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -88,7 +89,8 @@ int launch_batch_prep(Ctx* c, const BatchView& in, float p, uint64_t seed, uint6
                       int32_t* mark, int32_t mark_step, cudaStream_t s);
 int launch_build_cond_batch(Ctx* c, const int32_t* ex_rows, const int32_t* ex_conds, int B,
                             const uint64_t* item_cond_mask, cudaStream_t s);
-int launch_target_fixup(Ctx* c, const BatchView& tgt, float* PT, int64_t ldp, const float* rowscale, float inv_Bg,
+int launch_target_fixup(Ctx* c, const BatchView& tgt, __half* PT, int64_t ldp, const float* T, const float* lse,
+                        const __half* h16, int64_t ldh, const __half* W16, int64_t ldw, const float* bias, int H,
                         float* loss_row, cudaStream_t s);
 int launch_row_sums(Ctx* c, const BatchView& v, float* out, cudaStream_t s);
 int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const float* Wt, int H,
@@ -144,23 +146,26 @@ struct AdamOpt {
 };
 int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float lr_over_bc1,
                 float beta1, float beta2, float bc2_sqrt, float eps, float wd, float lam,
-                const float* norm_ptr, float* shadow, int64_t sh_lo, int64_t sh_hi, int64_t z_lo, int64_t z_hi,
+                const float* norm_ptr, __half* shadow, int64_t sh_lo, int64_t sh_hi, int64_t z_lo, int64_t z_hi,
                 const AdamOpt& opt, cudaStream_t s);
-int launch_round_tf32(Ctx* c, const float* x, float* y, int64_t n, cudaStream_t s);
+int launch_to_f16(Ctx* c, const float* x, __half* y, int64_t rows, int cols, int64_t ldy, cudaStream_t s);
 
 // topk.cu
 int launch_topk_metrics(Ctx* c, const float* scores, int I, const BatchView& gt, const int32_t* kinds,
                         const int32_t* ks, int n_metrics, int kmax, float* out, int32_t* topk_idx,
                         cudaStream_t s);
 
-// tc_gemm.cu  (tcgen05 / TMEM / TMA)
+// tc_gemm.cu  (tcgen05 / TMEM / TMA; fp16 operands, fp32 accumulate)
 enum { TC_EPI_STORE = 0, TC_EPI_LSE = 1, TC_EPI_PROB = 2 };
+constexpr float PROB_LOG2_SCALE = 14.f;   // P~ = softmax * 2^14 (fp16: <= 16384, normal down to 3.7e-9)
+constexpr float HS_LOG2_SCALE = 8.f;      // hs = h * (T_u / max T) * 2^8
 struct TcEpi {
     const float* bias = nullptr;       // per column
-    float* part_max = nullptr;         // TC_EPI_LSE partials [n_tiles_n x M]
+    float* part_max = nullptr;         // TC_EPI_LSE partials [part_rows x M]
     float* part_sum = nullptr;
+    int part_rows = 0;                 // capacity of the partial buffers (rows of M floats)
     const float* lse = nullptr;        // TC_EPI_PROB
-    const float* rowscale = nullptr;
+    float prob_log2_scale = PROB_LOG2_SCALE;
     float* bias_grad = nullptr;        // TC_EPI_STORE: column `bias_col` of the product goes here
     int bias_col = -1;
     int split_k = 1;                   // TC_EPI_STORE: partial products C[s] at C + s*split_stride
@@ -168,18 +173,22 @@ struct TcEpi {
     int transpose_out = 0;             // TC_EPI_STORE: write C[n*ldc + m] (a warp stores 32 consecutive m = 128 B);
                                        // bias_col then names the ROW m whose values go to bias_grad[n]
     int n_fastest = 0;                 // walk N tiles first (A tile shared through L2 by consecutive CTAs)
+    float out_scale = 1.f;             // TC_EPI_STORE: product * out_scale * (*out_scale_ptr)
+    const float* out_scale_ptr = nullptr;
 };
+// pitches (lda, ldb) in halfs, multiples of 8; A / B are __half arrays; C is float (STORE) or __half (PROB)
 bool tc_supported(int M, int N, int K, int64_t lda, int64_t ldb);
-int launch_tc_gemm(Ctx* c, int mode, const float* A, int64_t lda, int a_mn, const float* B, int64_t ldb,
-                   int b_mn, float* C, int64_t ldc, int M, int N, int K, const TcEpi& e,
+int launch_tc_gemm(Ctx* c, int mode, const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb,
+                   int b_mn, void* C, int64_t ldc, int M, int N, int K, const TcEpi& e,
                    cudaStream_t s);
-int tc_lse_tiles(int M, int N, int num_sms);   // (max, sum) partial rows per user the LSE epilogue writes
-int tc_output_tiles(int M, int N, int b_mn);   // output tiles of the current tiling (pair tiles in CTA-pair mode)
-int tc_parallel_tiles(int num_sms);            // tiles that run concurrently (SMs, or SM pairs)
+int tc_lse_parts(int M, int N, int K, int num_sms);   // (max, sum) partial rows per user the LSE epilogue writes
+int tc_lse_parts_max(int N, int num_sms);             // upper bound over all batch sizes / hidden widths
+int tc_output_tiles(int M, int N);             // output tiles of the current tiling (256-row pair tiles)
+int tc_parallel_tiles(int num_sms);            // tiles that run concurrently (SM pairs)
 int launch_splitk_reduce(Ctx* c, const float* parts, int n_split, int64_t split_stride, float* out,
                          int64_t ld_out, int M, int N, int64_t ld_part, const float* addend,
                          int64_t ld_add, float addend_scale, const float* mulY, int64_t ldy,
-                         cudaStream_t s);
+                         const float* rowscale, float scale, cudaStream_t s);
 
 // ---- device helpers ----------------------------------------------------------------------
 #ifdef __CUDACC__
@@ -207,13 +216,8 @@ __device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
     }
     return c;
 }
-// round-to-nearest fp32 -> tf32 (the tensor core itself truncates the low 13 mantissa bits,
-// which would bias every product towards zero; operands are pre-rounded instead)
-__device__ __forceinline__ float tf32_rn(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// tensor-core operands are fp16 images (round to nearest) of fp32 values: keep them finite
+__device__ __forceinline__ float f16_clamp(float x) { return fminf(fmaxf(x, -65504.f), 65504.f); }
 __device__ __forceinline__ float u32_to_unit(uint32_t x) {   // (0,1]
     return (float)(x >> 8) * (1.0f / 16777216.0f) + (0.5f / 16777216.0f);
 }

@@ -50,10 +50,13 @@ struct Ctx {
     float* z = nullptr;               // [B x latent]
     float* eps = nullptr;             // [B x latent]
     float* gvec = nullptr;            // [B x H_last]   sum_j t_uj W_d[j,:]
-    float* P = nullptr;               // [B x n_items]  softmax * T/B  (or its transpose)
-    float* hT = nullptr;              // [(H_last+8) x Bpad] transposed last hidden + ones row (tf32-rounded)
-    float* h_r = nullptr;             // [B x H_last] tf32-rounded copy of the last hidden activation
-    float* wd_shadow = nullptr;       // [n_items x H_last] tf32-rounded copy of W_d, maintained by Adam
+    float* P = nullptr;               // SIMT path only: [B x n_items] softmax * T/B
+    // tensor-core path: fp16 operand images (round to nearest; 10-bit mantissa like tf32, half the bytes)
+    __half* P16 = nullptr;            // [n_items x Bpad] P~^T = (softmax - t/T) * 2^14, users contiguous
+    __half* hsT = nullptr;            // [(H_last+8) x Bpad] (h * T_u/(B*R) * 2^8)^T + the row of T_u/(B*R) * 2^8
+    __half* h16 = nullptr;            // [B x H_last] last hidden activation
+    __half* wd16 = nullptr;           // [n_items x H_last] W_d, maintained by Adam
+    float* dw_scale = nullptr;        // [1] R = power of two >= max_u T_u/B of the current batch (un-scales dW_d)
     int32_t* d_specs = nullptr;       // [128] metric specs for topk
     float* spmm_acc = nullptr;        // [B x max(width)] zeroed accumulator for multi-segment gathers
     int*   spmm_ticket = nullptr;     // [B] zeroed per-row completion tickets

@@ -1,4 +1,5 @@
 // elementwise.cu -- reparameterisation + KL, loss assembly, parameter norms and the fused Adam.
+#include <cuda_fp16.h>
 #include <algorithm>
 #include "ctx.cuh"
 
@@ -191,7 +192,7 @@ template <bool EXTRAS, int FILTER>
 __global__ void __launch_bounds__(256)
 k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
        int64_t n, float neg_step, float b1c, float b2, float b2c, float bc2_sqrt, float eps, float wd,
-       float lam, const float* __restrict__ norm_ptr, float* __restrict__ shadow, int64_t sh_lo, int64_t sh_hi,
+       float lam, const float* __restrict__ norm_ptr, __half* __restrict__ shadow, int64_t sh_lo, int64_t sh_hi,
        int64_t z_lo, int64_t z_hi, const int32_t* __restrict__ mark, int32_t mark_step, int row_len) {
     float reg = 0.f;
     if (EXTRAS && norm_ptr) {
@@ -229,9 +230,14 @@ k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, floa
         // here, touching only the (few) rows that actually received a gradient
         if (in_z && !zero_g && (gg.x != 0.f || gg.y != 0.f || gg.z != 0.f || gg.w != 0.f))
             g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (shadow && e0 >= sh_lo && e0 < sh_hi)   // tf32 image of W_d for the tensor-core GEMMs
-            *reinterpret_cast<float4*>(shadow + (e0 - sh_lo)) =
-                make_float4(tf32_rn(ww.x), tf32_rn(ww.y), tf32_rn(ww.z), tf32_rn(ww.w));
+        if (shadow && e0 >= sh_lo && e0 < sh_hi) {   // fp16 image of W_d for the tensor-core GEMMs
+            const __half2 lo = __floats2half2_rn(f16_clamp(ww.x), f16_clamp(ww.y));
+            const __half2 hi = __floats2half2_rn(f16_clamp(ww.z), f16_clamp(ww.w));
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(shadow + (e0 - sh_lo)) = pk;
+        }
     }
     // tail (n not a multiple of 4)
     for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -252,13 +258,13 @@ k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, floa
         w[i] = ww;
         m[i] = mm;
         v[i] = vv;
-        if (shadow && i >= sh_lo && i < sh_hi) shadow[i - sh_lo] = tf32_rn(ww);
+        if (shadow && i >= sh_lo && i < sh_hi) shadow[i - sh_lo] = __float2half_rn(f16_clamp(ww));
     }
 }
 
 int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float lr_over_bc1,
                 float beta1, float beta2, float bc2_sqrt, float eps, float wd, float lam,
-                const float* norm_ptr, float* shadow, int64_t sh_lo, int64_t sh_hi, int64_t z_lo, int64_t z_hi,
+                const float* norm_ptr, __half* shadow, int64_t sh_lo, int64_t sh_hi, int64_t z_lo, int64_t z_hi,
                 const AdamOpt& opt, cudaStream_t s) {
     if (n == 0) return 0;
     B200_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
@@ -293,15 +299,23 @@ int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float
     return 0;
 }
 
-__global__ void k_round_tf32(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+// y[r * ldy + c] = fp16(x[r * cols + c]) (round to nearest, clamped to the finite fp16 range): operand images for
+// the tensor cores (W_d after anything but Adam wrote it; the last hidden activation in predict)
+__global__ void k_to_f16(const float* __restrict__ x, __half* __restrict__ y, int64_t rows, int cols, int64_t ldy) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) y[i] = tf32_rn(x[i]);
+    const int64_t n = rows * cols;
+    if (ldy == cols) {
+        for (; i < n; i += stride) y[i] = __float2half_rn(f16_clamp(x[i]));
+    } else {
+        for (; i < n; i += stride) y[(i / cols) * ldy + (i % cols)] = __float2half_rn(f16_clamp(x[i]));
+    }
 }
-int launch_round_tf32(Ctx* c, const float* x, float* y, int64_t n, cudaStream_t s) {
+int launch_to_f16(Ctx* c, const float* x, __half* y, int64_t rows, int cols, int64_t ldy, cudaStream_t s) {
+    const int64_t n = rows * cols;
     if (n == 0) return 0;
     int blocks = (int)std::min<int64_t>(cdiv(n, 256), (int64_t)c->num_sms * 8);
-    k_round_tf32<<<blocks, 256, 0, s>>>(x, y, n);
+    k_to_f16<<<blocks, 256, 0, s>>>(x, y, rows, cols, ldy);
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -42,10 +42,10 @@ static void free_ctx(Ctx* c) {
     F(c->xt); F(c->T); F(c->loss_row); F(c->kl_row); F(c->lse); F(c->rowscale);
     for (float* p : c->act_enc) F(p);
     for (float* p : c->act_dec) F(p);
-    F(c->z); F(c->eps); F(c->gvec); F(c->P); F(c->hT); F(c->dbuf[0]); F(c->dbuf[1]);
+    F(c->z); F(c->eps); F(c->gvec); F(c->P); F(c->P16); F(c->hsT); F(c->dbuf[0]); F(c->dbuf[1]);
     F(c->part_max); F(c->part_sum); F(c->splitk); F(c->norms); F(c->norm_partial);
     F(c->d_toff); F(c->d_tlen); F(c->loss_dev); F(c->d_err); F(c->lens_tmp); F(c->lens_tmp2);
-    F(c->h_r); F(c->wd_shadow); F(c->d_specs); F(c->spmm_acc); F(c->spmm_ticket);
+    F(c->h16); F(c->wd16); F(c->dw_scale); F(c->d_specs); F(c->spmm_acc); F(c->spmm_ticket);
     for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventDestroy(c->ev[i][j]);
     for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
@@ -160,54 +160,82 @@ static int forward_hidden(Ctx* c, FwdState* st, int B, bool train, float p, uint
     return 0;
 }
 
-// h [B x H] -> h_r [B x H] (tf32-rounded copy) and hT [(H+8) x Bp]: rows 0..H-1 = h_r^T, row H = 1
-// (bias-gradient column), rest 0.
-__global__ void k_transpose_ones(const float* __restrict__ h, int B, int H, int Bp, float* __restrict__ hT,
-                                 float* __restrict__ h_r) {
+// Operand prep of the decoder-output GEMMs: h [B x H] fp32 ->
+//   h16 [B x H]          fp16 image (A operand of K4 / K5)
+//   hsT [(H+8) x Bp]     rows 0..H-1 = (h * rs_u/R * 2^8)^T, row H = rs_u/R * 2^8 (bias-gradient row), rest 0,
+//                        with rs_u = T_u / B_global and R = the power of two >= max_u rs_u, so that every entry is
+//                        <= 256 in magnitude: the per-user factor of dlogits = rs_u * (softmax - t/T_u) rides on
+//                        this operand of the dW_d GEMM and P~ stays a pure probability.  R goes to *dw_scale.
+__global__ void __launch_bounds__(256)
+k_prep_h16(const float* __restrict__ h, int B, int H, int Bp, const float* __restrict__ T, float inv_Bg,
+           __half* __restrict__ h16, __half* __restrict__ hsT, float* __restrict__ dw_scale) {
     __shared__ float tile[32][33];
-    int b0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
-    int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+    __shared__ float red[8];
+    const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+    const int tid = ty * 32 + tx;
+    float R = 1.f;
+    if (hsT) {
+        float mx = 0.f;
+        for (int i = tid; i < B; i += 256) mx = fmaxf(mx, fabsf(T[i]));
+        mx = warp_max(mx);
+        if (tx == 0) red[ty] = mx;
+        __syncthreads();
+        mx = fmaxf(fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])), fmaxf(fmaxf(red[4], red[5]), fmaxf(red[6], red[7])));
+        mx *= inv_Bg;
+        if (mx > 0.f) {
+            int e;
+            frexpf(mx, &e);          // mx = f * 2^e, f in [0.5, 1)
+            R = ldexpf(1.f, e);
+        }
+        if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *dw_scale = R;
+    }
+    const float hs_mul = ldexpf(inv_Bg / R, (int)HS_LOG2_SCALE);
+    const int b0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
     for (int i = ty; i < 32; i += 8) {
-        int b = b0 + i, hh = h0 + tx;
-        float val = (hh == H && b < B) ? 1.f : 0.f;
-        if (b < B && hh < H) {
-            val = tf32_rn(h[(int64_t)b * H + hh]);
-            h_r[(int64_t)b * H + hh] = val;
+        const int b = b0 + i, hh = h0 + tx;
+        float val = 0.f;
+        if (b < B) {
+            const float rs = hsT ? T[b] * hs_mul : 0.f;
+            if (hh < H) {
+                const float x = h[(int64_t)b * H + hh];
+                h16[(int64_t)b * H + hh] = __float2half_rn(f16_clamp(x));
+                val = x * rs;
+            } else if (hh == H) {
+                val = rs;
+            }
         }
         tile[i][tx] = val;
     }
+    if (!hsT) return;
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
-        int hh = h0 + i, b = b0 + tx;
-        if (hh < H + 8 && b < Bp) hT[(int64_t)hh * Bp + b] = tile[tx][i];
+        const int hh = h0 + i, b = b0 + tx;
+        if (hh < H + 8 && b < Bp) hsT[(int64_t)hh * Bp + b] = __float2half_rn(f16_clamp(tile[tx][i]));
     }
 }
 
 // fused decoder GEMM + per-tile (max, sum exp) partials; the merge happens in row_loss.  With
-// `for_backward` the tf32 operand prep also emits the transposed hT the dW_d GEMM needs.
-static int dec_lse(Ctx* c, const float* h, int B, int H, int* n_tiles, bool for_backward, cudaStream_t s) {
+// `for_backward` the operand prep also emits the scaled, transposed hsT the dW_d GEMM needs (T must be final).
+static int dec_lse(Ctx* c, const float* h, int B, int H, int Bg, int* n_tiles, bool for_backward, cudaStream_t s) {
     const Layer& L = c->dec.back();
     const float* W = c->w + L.w_off;
     const float* b = c->w + L.b_off;
     int I = c->n_items;
     if (c->tc_dec) {
-        // tensor-core operands: tf32-rounded copies (h_r / hT made here, W_d shadow kept by Adam)
-        if (for_backward) {
-            const int Bp = (int)round_up(B, 4);
-            dim3 tg((unsigned)cdiv(Bp, 32), (unsigned)cdiv(H + 8, 32));
-            k_transpose_ones<<<tg, dim3(32, 8), 0, s>>>(h, B, H, Bp, c->hT, c->h_r);
-            note(c, "prep_h_tf32", s);
-        } else {
-            B200_CHECK(launch_round_tf32(c, h, c->h_r, (int64_t)B * H, s));
-        }
+        const int Bp = (int)round_up(B, 8);
+        dim3 tg((unsigned)cdiv(Bp, 32), (unsigned)cdiv(H + 8, 32));
+        k_prep_h16<<<tg, dim3(32, 8), 0, s>>>(h, B, H, Bp, c->T, 1.0f / (float)Bg, c->h16, for_backward ? c->hsT : nullptr,
+                                              c->dw_scale);
+        note(c, "prep_h16", s);
         TcEpi e;
         e.bias = b;
         e.part_max = c->part_max;
         e.part_sum = c->part_sum;
+        e.part_rows = c->n_lse_tiles;
         tick(c, 0, 0, s);      // K4 proper: the tcgen05 GEMM + log-sum-exp kernel alone (operand prep is outside)
-        B200_CHECK(launch_tc_gemm(c, TC_EPI_LSE, c->h_r, H, 0, c->wd_shadow, H, 0, nullptr, 0, B, I, H, e, s));
+        B200_CHECK(launch_tc_gemm(c, TC_EPI_LSE, c->h16, H, 0, c->wd16, H, 0, nullptr, 0, B, I, H, e, s));
         tick(c, 0, 1, s);
-        *n_tiles = tc_lse_tiles(B, I, c->num_sms);
+        *n_tiles = tc_lse_parts(B, I, H, c->num_sms);
     } else {
         GemmEpi e;
         e.bias = b;
@@ -266,7 +294,7 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
     const int H = st.H;
     const float* Wd = c->w + DL.w_off;
     int n_lse_tiles = 0;
-    B200_CHECK(dec_lse(c, st.h_last, B, H, &n_lse_tiles, true, s));
+    B200_CHECK(dec_lse(c, st.h_last, B, H, Bg, &n_lse_tiles, true, s));
     if (c->tc_dec) {
         // merge the LSE partials, T/B; the sparse loss term is taken from P^T after the recompute kernel (target_fixup)
         B200_CHECK(launch_row_loss(c, st.tgt, st.h_last, nullptr, H, c->w + DL.b_off, c->part_max, c->part_sum, n_lse_tiles,
@@ -284,37 +312,41 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
     float* d0 = c->dbuf[0];
     float* d1 = c->dbuf[1];
     if (c->tc_dec) {
-        // P^T [I x Bp] (item-major, users contiguous) from the recompute kernel
-        const int Bp = (int)round_up(B, 4);
+        // P~^T [I x Bp] (item-major, users contiguous, fp16) = softmax * 2^14 from the recompute kernel
+        const int Bp = (int)round_up(B, 8);
         TcEpi e;
         e.bias = c->w + DL.b_off;
         e.lse = c->lse;
-        e.rowscale = rowscale;
         tick(c, 2, 0, s);
-        B200_CHECK(launch_tc_gemm(c, TC_EPI_PROB, c->h_r, H, 0, c->wd_shadow, H, 0, c->P, Bp, B, I, H, e, s));
+        B200_CHECK(launch_tc_gemm(c, TC_EPI_PROB, c->h16, H, 0, c->wd16, H, 0, c->P16, Bp, B, I, H, e, s));
         tick(c, 2, 1, s);
-        // sparse part of dlogits + the sparse loss term, straight on P^T
-        B200_CHECK(launch_target_fixup(c, st.tgt, c->P, Bp, rowscale, inv_Bg, c->loss_row, s));
-        // (dW_d | db_d)^T = [h | 1]^T [(H+8) x B] * P [B x I]: A = hT (K-major, from dec_lse), B = P^T (K-major).
-        // Computing the transpose puts the hidden index on the TMEM lanes, so each epilogue store
-        // instruction writes 32 consecutive floats of a dW_d row (full 128 B lines) instead of 32 rows x 16 B.
+        // sparse part of dlogits + the sparse loss term, straight on P~^T
+        B200_CHECK(launch_target_fixup(c, st.tgt, c->P16, Bp, c->T, c->lse, c->h16, H, c->wd16, H, c->w + DL.b_off, H,
+                                       c->loss_row, s));
+        // (dW_d | db_d)^T = [hs | rs]^T [(H+8) x B] * P~ [B x I]: A = hsT (K-major, from dec_lse; stays resident in
+        // shared memory), B = P~^T (K-major).  Computing the transpose puts the hidden index on the TMEM lanes, so each
+        // epilogue store instruction writes 32 consecutive floats of a dW_d row (full 128 B lines).  The epilogue
+        // un-scales by R * 2^-(8+14).
         TcEpi e2;
         e2.bias_grad = dbd;
-        e2.bias_col = H;       // row H of the product (the ones row of hT) is the bias gradient
+        e2.bias_col = H;       // row H of the product (the rs row of hsT) is the bias gradient
         e2.transpose_out = 1;
+        e2.out_scale = exp2f(-(HS_LOG2_SCALE + PROB_LOG2_SCALE));
+        e2.out_scale_ptr = c->dw_scale;
         tick(c, 3, 0, s);
-        B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->hT, Bp, 0, c->P, Bp, 0, dWd, H, H + 8, I, B, e2, s));
+        B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->hsT, Bp, 0, c->P16, Bp, 0, dWd, H, H + 8, I, B, e2, s));
         tick(c, 3, 1, s);
-        // dh = P W_d : A = P^T given as [K=I x M=Bp] (MN-major), B = W_d [K=I x N=H] (MN-major)
+        // dh = rs_u * 2^-14 * (P~ W_d) : A = P~^T given as [K=I x M=Bp] (MN-major), B = W_d [K=I x N=H] (MN-major);
+        // the per-user factor and tanh' are applied by the split-K reduction
         TcEpi e3;
-        int split = std::max(1, std::min(64, tc_parallel_tiles(c->num_sms) / tc_output_tiles(B, H, 1)));
+        int split = std::max(1, std::min(64, tc_parallel_tiles(c->num_sms) / tc_output_tiles(B, H)));
         e3.split_k = split;
         e3.split_stride = (int64_t)B * H;
         B200_REQUIRE((int64_t)split * B * H <= c->splitk_elems, B200VAE_ECAPACITY, "split-K workspace too small");
         tick(c, 4, 0, s);
-        B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->P, Bp, 1, c->wd_shadow, H, 1, c->splitk, H, B, H, I, e3, s));
+        B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->P16, Bp, 1, c->wd16, H, 1, c->splitk, H, B, H, I, e3, s));
         B200_CHECK(launch_splitk_reduce(c, c->splitk, split, e3.split_stride, d0, H, B, H, H, nullptr, 0,
-                                        0.f, st.h_last_tanh, H, s));
+                                        0.f, st.h_last_tanh, H, rowscale, exp2f(-PROB_LOG2_SCALE), s));
         tick(c, 4, 1, s);
     } else {
         GemmEpi e;
@@ -404,7 +436,7 @@ static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo, i
     float bc2_sqrt = (float)std::sqrt(bc2);
     tick(c, 1, 0, s);
     const Layer& DL = c->dec.back();
-    float* shadow = c->tc_dec ? c->wd_shadow : nullptr;
+    __half* shadow = c->tc_dec ? c->wd16 : nullptr;
     const int64_t sh_lo = DL.w_off, sh_hi = DL.w_off + (int64_t)DL.in * DL.out;
     // Adam re-zeroes the encoder-0 gradient rows it consumed (sparse writes), so forward_backward never memsets
     const Layer& E0 = c->enc[0];
@@ -450,7 +482,7 @@ static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo, i
 // One single-GPU optimisation step.  Timeline (main stream | side stream):
 //   batch scan, batch_prep (stamps the touched encoder-0 rows)  | -
 //   encoder, decoder, loss, decoder-output backward (tcgen05)   | Adam of the untouched encoder-0 rows
-//   hidden-layer backward, sparse scatter                       | Adam of W_d, b_d (+ tf32 image), once dW_d is final
+//   hidden-layer backward, sparse scatter                       | Adam of W_d, b_d (+ fp16 image), once dW_d is final
 //   Adam of the touched encoder-0 rows and the small tensors    |
 // The side launches are narrow grid-stride kernels (side_ctas CTAs per SM) so the small kernels of the main stream
 // run beside them; the tcgen05 kernels need whole SMs and simply start when a side launch has drained.  Every
@@ -527,8 +559,8 @@ static int predict(Ctx* c, const int32_t* row_ids, int B, int remove_train, int 
     if (c->tc_dec) {
         TcEpi e;
         e.bias = c->w + DL.b_off;
-        B200_CHECK(launch_round_tf32(c, st.h_last, c->h_r, (int64_t)B * st.H, s));
-        B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->h_r, st.H, 0, c->wd_shadow, st.H, 0, scores, I, B, I, st.H, e, s));
+        B200_CHECK(launch_to_f16(c, st.h_last, c->h16, B, st.H, st.H, s));
+        B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->h16, st.H, 0, c->wd16, st.H, 0, scores, I, B, I, st.H, e, s));
     } else {
         B200_CHECK(linear_fwd(c, st.h_last, B, DL, scores, s));
     }
@@ -623,7 +655,7 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
 
     const int64_t Bm = cfg->max_batch, I = c->n_items, nnz = cfg->max_batch_nnz;
     const int H = c->dec.back().in;
-    const int64_t Bp = round_up(Bm, 4);
+    const int64_t Bp = round_up(Bm, 8);
     c->tc_dec = c->use_tc && tc_supported((int)Bm, (int)I, H, H, H) && (I >= 1024);
     int rc = 0;
 #define A_(expr) do { if (!rc) rc = (expr); } while (0)
@@ -640,16 +672,18 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     for (size_t i = 0; i + 1 < c->dec.size(); ++i) { float* p = nullptr; A_(dmalloc(&p, Bm * c->dec[i].out)); c->act_dec.push_back(p); }
     A_(dmalloc(&c->z, Bm * c->latent)); A_(dmalloc(&c->eps, Bm * c->latent));
     A_(dmalloc(&c->gvec, Bm * H));
-    A_(dmalloc(&c->P, Bp * I));
-    A_(dmalloc(&c->hT, (int64_t)(H + 8) * Bp));
-    A_(dmalloc(&c->h_r, Bm * H));
-    A_(dmalloc(&c->wd_shadow, c->tc_dec ? I * H : 1));
+    A_(dmalloc(&c->P, c->tc_dec ? 1 : Bm * I));
+    A_(dmalloc(&c->P16, c->tc_dec ? Bp * I : 1));
+    A_(dmalloc(&c->hsT, c->tc_dec ? (int64_t)(H + 8) * Bp : 1));
+    A_(dmalloc(&c->h16, c->tc_dec ? Bm * H : 1));
+    A_(dmalloc(&c->wd16, c->tc_dec ? I * H : 1));
+    A_(dmalloc(&c->dw_scale, 1));
     A_(dmalloc(&c->d_specs, 128));
     A_(dmalloc(&c->spmm_acc, Bm * std::max(c->max_width, H)));
     A_(dmalloc(&c->spmm_ticket, Bm));
     A_(dmalloc(&c->mark, c->enc_in));
     A_(dmalloc(&c->dbuf[0], Bm * c->max_width)); A_(dmalloc(&c->dbuf[1], Bm * c->max_width));
-    c->n_lse_tiles = (int)std::max<int64_t>(cdiv(I, 64), 1);
+    c->n_lse_tiles = (int)std::max<int64_t>(std::max<int64_t>(cdiv(I, 64), tc_lse_parts_max((int)I, c->num_sms)), 1);
     A_(dmalloc(&c->part_max, (int64_t)c->n_lse_tiles * Bm)); A_(dmalloc(&c->part_sum, (int64_t)c->n_lse_tiles * Bm));
     c->splitk_elems = c->tc_dec ? (int64_t)64 * Bm * H : 1;
     A_(dmalloc(&c->splitk, c->splitk_elems));
@@ -806,13 +840,13 @@ int b200vae_adam_step_range(b200vae_ctx* ctx, float lr, float beta1, float beta2
 }
 
 int b200vae_sync_weights(b200vae_ctx* ctx, void* stream) {
-    // refresh every derived copy of the parameters (the tf32 image of W_d read by the tensor cores);
+    // refresh every derived copy of the parameters (the fp16 image of W_d read by the tensor cores);
     // call after the weight arena was modified by anything other than b200vae_adam_step
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     B200_REQUIRE(c && c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
     if (!c->tc_dec) return 0;
     const Layer& DL = c->dec.back();
-    return launch_round_tf32(c, c->w + DL.w_off, c->wd_shadow, (int64_t)DL.in * DL.out, (cudaStream_t)stream);
+    return launch_to_f16(c, c->w + DL.w_off, c->wd16, DL.out, DL.in, DL.in, (cudaStream_t)stream);
 }
 
 int b200vae_adam_step(b200vae_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay,
@@ -970,8 +1004,8 @@ int b200vae_decode(b200vae_ctx* ctx, const float* z, int32_t B, float* scores, v
     if (c->tc_dec) {
         TcEpi e;
         e.bias = c->w + DL.b_off;
-        B200_CHECK(launch_round_tf32(c, h, c->h_r, (int64_t)B * DL.in, s));
-        return launch_tc_gemm(c, TC_EPI_STORE, c->h_r, DL.in, 0, c->wd_shadow, DL.in, 0, scores, c->n_items, B, c->n_items, DL.in, e, s);
+        B200_CHECK(launch_to_f16(c, h, c->h16, B, DL.in, DL.in, s));
+        return launch_tc_gemm(c, TC_EPI_STORE, c->h16, DL.in, 0, c->wd16, DL.in, 0, scores, c->n_items, B, c->n_items, DL.in, e, s);
     }
     return linear_fwd(c, h, B, DL, scores, s);
 }
@@ -998,30 +1032,31 @@ int b200vae_topk_metrics(b200vae_ctx* ctx, const float* scores, const int32_t* g
     return launch_topk_metrics(c, scores, c->n_items, gt, c->d_specs, c->d_specs + 64, n_metrics, kmax, out, topk_idx, s);
 }
 
-int b200vae_gemm_tf32(b200vae_ctx* ctx, const float* A, int64_t lda, int a_mn_major, const float* B, int64_t ldb,
-                      int b_mn_major, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, void* stream) {
+int b200vae_gemm_f16(b200vae_ctx* ctx, const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
+                     int b_mn_major, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     B200_REQUIRE(c && A && B && C, B200VAE_EINVAL, "null argument");
     TcEpi e;
     return launch_tc_gemm(c, TC_EPI_STORE, A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, e, (cudaStream_t)stream);
 }
 
-int b200vae_dec_fwd_lse(b200vae_ctx* ctx, const float* h, const float* W, const float* bias, int32_t B,
+int b200vae_dec_fwd_lse(b200vae_ctx* ctx, const void* h16, const void* W16, const float* bias, int32_t B,
                         int32_t n_items, int32_t H, float* lse, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     cudaStream_t s = (cudaStream_t)stream;
-    B200_REQUIRE(c && h && W, B200VAE_EINVAL, "null argument");
+    B200_REQUIRE(c && h16 && W16, B200VAE_EINVAL, "null argument");
     B200_REQUIRE(B <= c->cfg.max_batch && n_items <= c->n_items, B200VAE_ECAPACITY, "exceeds context capacity");
-    B200_REQUIRE(tc_supported(B, n_items, H, H, H), B200VAE_EINVAL, "shape not supported by the tcgen05 path (H %% 4 != 0?)");
+    B200_REQUIRE(tc_supported(B, n_items, H, H, H), B200VAE_EINVAL, "shape not supported by the tcgen05 path (H %% 8 != 0?)");
     TcEpi e;
     e.bias = bias;
     e.part_max = c->part_max;
     e.part_sum = c->part_sum;
+    e.part_rows = c->n_lse_tiles;
     tick(c, 0, 0, s);
-    B200_CHECK(launch_tc_gemm(c, TC_EPI_LSE, h, H, 0, W, H, 0, nullptr, 0, B, n_items, H, e, s));
+    B200_CHECK(launch_tc_gemm(c, TC_EPI_LSE, h16, H, 0, W16, H, 0, nullptr, 0, B, n_items, H, e, s));
     tick(c, 0, 1, s);
-    if (lse)   // lse == NULL: only the fused GEMM + log-sum-exp kernel (per-tile partials stay in the workspace)
-        B200_CHECK(launch_lse_merge(c, c->part_max, c->part_sum, tc_lse_tiles(B, n_items, c->num_sms), B, lse, s));
+    if (lse)   // lse == NULL: only the fused GEMM + log-sum-exp kernel (the partials stay in the workspace)
+        B200_CHECK(launch_lse_merge(c, c->part_max, c->part_sum, tc_lse_parts(B, n_items, H, c->num_sms), B, lse, s));
     return 0;
 }
 
@@ -1079,6 +1114,11 @@ int b200vae_check_error_flag(b200vae_ctx* ctx) {
     B200_CUDA_OK(cudaMemcpy(&flag, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flag) {
         cudaMemset(c->d_err, 0, sizeof(int));
+        if (flag & 2) {
+            set_error("a target row had |t| > 4 |sum t| (mixed-sign ratings are not multinomial targets): "
+                      "the gradients of that step were clamped");
+            return B200VAE_EINVAL;
+        }
         set_error("a batch exceeded max_batch_nnz (%lld): results of that step are invalid", (long long)c->cfg.max_batch_nnz);
         return B200VAE_ECAPACITY;
     }

@@ -613,29 +613,50 @@ __global__ void k_row_loss(BatchView tgt, const float* __restrict__ h, const flo
     }
 }
 
-// Tensor-core path: after the recompute kernel stored P^T[j,u] = softmax_uj * T_u/B (dense part of dlogits),
-// walk the TARGET non-zeros once:
-//   loss_u  = -sum_j t_uj * log(P_uj / (T_u/B))            (== sum_j t_uj (lse_u - logit_uj), models.py:813)
-//   P^T[j,u] -= t_uj / B                                    (sparse part of dlogits)
+// Tensor-core path: after the recompute kernel stored P~^T[j,u] = softmax_uj * 2^S (fp16, the dense part of
+// dlogits up to the per-user factor T_u/B that travels with the other GEMM operand), walk the TARGET non-zeros once:
+//   loss_u   = -sum_j t_uj * log softmax_uj                 (== sum_j t_uj (lse_u - logit_uj), models.py:813)
+//   P~^T[j,u] -= (t_uj / T_u) * 2^S                          (sparse part of dlogits: softmax*T/B - t/B =
+//                                                             (T/B) * (softmax - t/T))
 // so dW_d, db_d and dh come out of the two GEMMs complete: no gather of W_d rows for the loss and no
-// scatter into dW_d.  One warp per user row; ~nnz_B scattered 4-byte read-modify-writes.
+// scatter into dW_d.  One CTA per user row; ~nnz_B scattered 2-byte read-modify-writes.
+// log softmax is read back from P~ where that is a normal fp16 number (>= 2^-14, i.e. softmax >= 3.7e-9: 11
+// significant bits like every other tensor-core operand here); below that it is recomputed exactly from the
+// operands, h_u . W_d[j] + b_j - lse_u, by the thread that found it (rare: a target item the model gives ~0).
 __global__ void __launch_bounds__(128)
-k_target_fixup(BatchView tgt, float* __restrict__ PT, int64_t ldp, const float* __restrict__ rowscale,
-               float inv_Bg, float* __restrict__ loss_row) {
-    // one CTA per user row: all of the row's non-zeros are in flight at once (the accesses are
-    // scattered 4-byte read-modify-writes, i.e. pure latency)
+k_target_fixup(BatchView tgt, __half* __restrict__ PT, int64_t ldp, const float* __restrict__ T,
+               const float* __restrict__ lse, const __half* __restrict__ h16, int64_t ldh,
+               const __half* __restrict__ W16, int64_t ldw, const float* __restrict__ bias, int H,
+               float log2_scale, float* __restrict__ loss_row, int* __restrict__ err) {
     __shared__ float sh[4];
     const int u = blockIdx.x;
-    const float rs = rowscale[u];
+    const float Tu = T[u];
+    const float sub = (Tu != 0.f) ? exp2f(log2_scale) / Tu : 0.f;
     int64_t gr = tgt.row_ids ? (int64_t)tgt.row_ids[u] : (int64_t)u;
     int64_t a = tgt.indptr[gr], b = tgt.indptr[gr + 1];
     float acc = 0.f;
     for (int64_t k = a + threadIdx.x; k < b; k += blockDim.x) {
         const float t = tgt.values ? tgt.values[k] : 1.f;
-        float* q = PT + (int64_t)tgt.indices[k] * ldp + u;
-        const float p = *q;
-        acc = fmaf(t, logf(p / rs), acc);
-        *q = tf32_rn(p - t * inv_Bg);
+        const int j = tgt.indices[k];
+        __half* q = PT + (int64_t)j * ldp + u;
+        const float p = __half2float(*q);
+        float lsm;
+        if (p >= 6.103515625e-05f) {
+            lsm = (log2f(p) - log2_scale) * 0.6931471805599453f;
+        } else {
+            float dot = bias ? bias[j] : 0.f;
+            const __half* hr = h16 + (int64_t)u * ldh;
+            const __half* wr = W16 + (int64_t)j * ldw;
+            for (int i = 0; i < H; ++i) dot = fmaf(__half2float(hr[i]), __half2float(wr[i]), dot);
+            lsm = dot - lse[u];
+        }
+        acc = fmaf(t, lsm, acc);
+        float nv = p - t * sub;
+        if (!(fabsf(nv) <= 65504.f)) {      // |t / T_u| > ~4: not a multinomial target (mixed-sign ratings)
+            atomicOr(err, 2);
+            nv = fminf(fmaxf(nv, -65504.f), 65504.f);
+        }
+        *q = __float2half_rn(nv);
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
@@ -643,10 +664,12 @@ k_target_fixup(BatchView tgt, float* __restrict__ PT, int64_t ldp, const float* 
     if (threadIdx.x == 0) loss_row[u] = -((sh[0] + sh[1]) + (sh[2] + sh[3]));
 }
 
-int launch_target_fixup(Ctx* c, const BatchView& tgt, float* PT, int64_t ldp, const float* rowscale, float inv_Bg,
+int launch_target_fixup(Ctx* c, const BatchView& tgt, __half* PT, int64_t ldp, const float* T, const float* lse,
+                        const __half* h16, int64_t ldh, const __half* W16, int64_t ldw, const float* bias, int H,
                         float* loss_row, cudaStream_t s) {
     if (tgt.B == 0) return 0;
-    k_target_fixup<<<tgt.B, 128, 0, s>>>(tgt, PT, ldp, rowscale, inv_Bg, loss_row);
+    k_target_fixup<<<tgt.B, 128, 0, s>>>(tgt, PT, ldp, T, lse, h16, ldh, W16, ldw, bias, H, PROB_LOG2_SCALE, loss_row,
+                                         c->d_err);
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;

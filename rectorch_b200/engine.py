@@ -193,7 +193,7 @@ class Engine:
 
     def _sync_weights_if_dirty(self):
         # torch ops that write the arena (init_weights, load_state_dict, manual edits) bump the
-        # storage version counter; our kernels do not.  Re-derive the tf32 image when it moved.
+        # storage version counter; our kernels do not.  Re-derive the fp16 image when it moved.
         if self.w._version != self._seen_version:
             check(_lib.lib().b200vae_sync_weights(self._ctx, stream_ptr()))
             self._seen_version = self.w._version

@@ -1,5 +1,5 @@
-"""Steady-state throughput of the tcgen05 tf32 GEMM entry point (b200vae_gemm_tf32) for a few shapes.
-Run twice to compare tilings:  B200VAE_TC_1CTA=1 python scripts/gemm_perf.py ; python scripts/gemm_perf.py"""
+"""Steady-state throughput of the tcgen05 fp16 GEMM entry point (b200vae_gemm_f16) for a few shapes.
+Compare schedules:  B200VAE_TC_RESIDENT=0 python scripts/gemm_perf.py ; python scripts/gemm_perf.py"""
 import ctypes
 import os
 import sys
@@ -17,23 +17,23 @@ cfg.dec_dims[0], cfg.dec_dims[1] = 64, 4096
 cfg.max_batch, cfg.max_batch_nnz, cfg.use_tensor_cores = 1024, 1 << 16, 1
 h = ctypes.c_void_p()
 check(_lib.lib().b200vae_ctx_create(ctypes.byref(h), ctypes.byref(cfg)))
-mode = "1cta" if os.environ.get("B200VAE_TC_1CTA") == "1" else "pair"
-shapes = [(4096, 4096, 4096, 0, 0), (8192, 8192, 1024, 0, 0), (512, 50000, 600, 0, 0), (50000, 608, 512, 0, 0),
+mode = "streaming" if os.environ.get("B200VAE_TC_RESIDENT") == "0" else "resident-A"
+shapes = [(4096, 4096, 4096, 0, 0), (8192, 8192, 1024, 0, 0), (512, 50000, 600, 0, 0), (608, 50000, 512, 0, 0), (512, 600, 50000, 1, 1),
           (4096, 4096, 4096, 1, 1), (4096, 4096, 4096, 0, 1)]
 for M, N, K, am, bm in shapes:
-    A = torch.randn((K, M) if am else (M, K), device="cuda")
-    B = torch.randn((K, N) if bm else (N, K), device="cuda")
+    A = torch.randn((K, M) if am else (M, K), device="cuda").half()
+    B = torch.randn((K, N) if bm else (N, K), device="cuda").half()
     C = torch.empty(M, N, device="cuda")
     lda = M if am else K
     ldb = N if bm else K
     for _ in range(3):
-        check(_lib.lib().b200vae_gemm_tf32(h, ptr(A), lda, am, ptr(B), ldb, bm, ptr(C), N, M, N, K, None))
+        check(_lib.lib().b200vae_gemm_f16(h, ptr(A), lda, am, ptr(B), ldb, bm, ptr(C), N, M, N, K, None))
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 10
     e0.record()
     for _ in range(reps):
-        check(_lib.lib().b200vae_gemm_tf32(h, ptr(A), lda, am, ptr(B), ldb, bm, ptr(C), N, M, N, K, None))
+        check(_lib.lib().b200vae_gemm_f16(h, ptr(A), lda, am, ptr(B), ldb, bm, ptr(C), N, M, N, K, None))
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
