@@ -83,6 +83,18 @@ int  b200vae_bind_params(b200vae_ctx* ctx, float* w, float* g, float* m, float* 
  * nets.py:235-247 / models.py:513). */
 int  b200vae_sync_weights(b200vae_ctx* ctx, void* stream);
 
+/* Data parallelism with a sharded optimizer: the fp16 image of W_d lives in a CALLER-owned
+ * device buffer of n_halfs >= n_items * H halfs (a torch tensor, so that torch.distributed can all-gather the
+ * ranks' shards into it).  The context re-derives the image into it at once.
+ * Replaces: nothing in the reference (single process); this is the storage of nets.py:417's weight as the tensor
+ * cores read it. */
+int  b200vae_bind_shadow(b200vae_ctx* ctx, void* wd16, int64_t n_halfs);
+
+/* The next engine call that reads the fp16 image of W_d (forward_backward / train_step / predict / decode) makes its
+ * stream wait for `event` (a cudaEvent_t recorded by the caller on the stream that refreshes the image) right before
+ * the first GEMM that needs it -- the encoder part of the step overlaps the refresh.  One-shot. */
+int  b200vae_defer_wait_event(b200vae_ctx* ctx, void* event);
+
 /* Device-side capacity-overflow flag (a batch had more non-zeros than max_batch_nnz).
  * Synchronises the device; returns B200VAE_ECAPACITY once and clears the flag. */
 int  b200vae_check_error_flag(b200vae_ctx* ctx);

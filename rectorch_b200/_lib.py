@@ -40,6 +40,8 @@ _SIGS = {
     "b200vae_bind_params": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                     POINTER(c_int64), POINTER(c_int64)]),
     "b200vae_sync_weights": (c_int, [c_void_p, c_void_p]),
+    "b200vae_bind_shadow": (c_int, [c_void_p, c_void_p, c_int64]),
+    "b200vae_defer_wait_event": (c_int, [c_void_p, c_void_p]),
     "b200vae_check_error_flag": (c_int, [c_void_p]),
     "b200vae_wait_wd_ready": (c_int, [c_void_p, c_void_p]),
     "b200vae_bind_csr": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64]),

@@ -56,6 +56,8 @@ struct Ctx {
     __half* hsT = nullptr;            // [(H_last+8) x Bpad] (h * T_u/(B*R) * 2^8)^T + the row of T_u/(B*R) * 2^8
     __half* h16 = nullptr;            // [B x H_last] last hidden activation
     __half* wd16 = nullptr;           // [n_items x H_last] W_d, maintained by Adam
+    bool wd16_external = false;       // wd16 is a caller-owned buffer (b200vae_bind_shadow)
+    cudaEvent_t wd16_pending = nullptr;   // the next reader of wd16 waits for this event first (b200vae_defer_wait_event)
     float* dw_scale = nullptr;        // [1] R = power of two >= max_u T_u/B of the current batch (un-scales dW_d)
     int32_t* d_specs = nullptr;       // [128] metric specs for topk
     float* spmm_acc = nullptr;        // [B x max(width)] zeroed accumulator for multi-segment gathers

@@ -45,7 +45,7 @@ static void free_ctx(Ctx* c) {
     F(c->z); F(c->eps); F(c->gvec); F(c->P); F(c->P16); F(c->hsT); F(c->dbuf[0]); F(c->dbuf[1]);
     F(c->part_max); F(c->part_sum); F(c->splitk); F(c->norms); F(c->norm_partial);
     F(c->d_toff); F(c->d_tlen); F(c->loss_dev); F(c->d_err); F(c->lens_tmp); F(c->lens_tmp2);
-    F(c->h16); F(c->wd16); F(c->dw_scale); F(c->d_specs); F(c->spmm_acc); F(c->spmm_ticket);
+    F(c->h16); if (!c->wd16_external) F(c->wd16); F(c->dw_scale); F(c->d_specs); F(c->spmm_acc); F(c->spmm_ticket);
     for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventDestroy(c->ev[i][j]);
     for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
@@ -97,6 +97,16 @@ static int linear_bwd(Ctx* c, const float* dY, const float* inp, int B, const La
         e2.mulY = prev_out;
         e2.ldy = L.in;
         B200_CHECK(launch_simt_gemm(c, EPI_STORE, dY, L.out, 1, c->w + L.w_off, L.in, 1, dinp, L.in, B, L.in, L.out, e2, s));
+    }
+    return 0;
+}
+
+// a data-parallel caller refreshes the fp16 image of W_d on another stream (all-gather of the ranks' shards):
+// whoever reads it next waits for that work first
+static int wait_wd16(Ctx* c, cudaStream_t s) {
+    if (c->wd16_pending) {
+        B200_CUDA_OK(cudaStreamWaitEvent(s, c->wd16_pending, 0));
+        c->wd16_pending = nullptr;
     }
     return 0;
 }
@@ -232,6 +242,7 @@ static int dec_lse(Ctx* c, const float* h, int B, int H, int Bg, int* n_tiles, b
         e.part_max = c->part_max;
         e.part_sum = c->part_sum;
         e.part_rows = c->n_lse_tiles;
+        B200_CHECK(wait_wd16(c, s));
         tick(c, 0, 0, s);      // K4 proper: the tcgen05 GEMM + log-sum-exp kernel alone (operand prep is outside)
         B200_CHECK(launch_tc_gemm(c, TC_EPI_LSE, c->h16, H, 0, c->wd16, H, 0, nullptr, 0, B, I, H, e, s));
         tick(c, 0, 1, s);
@@ -560,6 +571,7 @@ static int predict(Ctx* c, const int32_t* row_ids, int B, int remove_train, int 
         TcEpi e;
         e.bias = c->w + DL.b_off;
         B200_CHECK(launch_to_f16(c, st.h_last, c->h16, B, st.H, st.H, s));
+        B200_CHECK(wait_wd16(c, s));
         B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->h16, st.H, 0, c->wd16, st.H, 0, scores, I, B, I, st.H, e, s));
     } else {
         B200_CHECK(linear_fwd(c, st.h_last, B, DL, scores, s));
@@ -839,6 +851,27 @@ int b200vae_adam_step_range(b200vae_ctx* ctx, float lr, float beta1, float beta2
     return adam_step(c, h, (cudaStream_t)stream, elem_lo, elem_hi, ADAM_ROWS_ALL, narrow ? c->side_ctas[0] : 8);
 }
 
+int b200vae_bind_shadow(b200vae_ctx* ctx, void* wd16, int64_t n_halfs) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    B200_REQUIRE(c && wd16, B200VAE_EINVAL, "null argument");
+    if (!c->tc_dec) return 0;                       // the SIMT path keeps no image
+    const Layer& DL = c->dec.back();
+    B200_REQUIRE(n_halfs >= (int64_t)DL.in * DL.out && ((uintptr_t)wd16 & 15) == 0, B200VAE_EINVAL,
+                 "shadow buffer too small (%lld halfs) or not 16-byte aligned", (long long)n_halfs);
+    B200_CUDA_OK(cudaDeviceSynchronize());
+    if (!c->wd16_external && c->wd16) cudaFree(c->wd16);
+    c->wd16 = reinterpret_cast<__half*>(wd16);
+    c->wd16_external = true;
+    return c->params_bound ? b200vae_sync_weights(ctx, nullptr) : 0;
+}
+
+int b200vae_defer_wait_event(b200vae_ctx* ctx, void* event) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    B200_REQUIRE(c, B200VAE_EINVAL, "null context");
+    c->wd16_pending = reinterpret_cast<cudaEvent_t>(event);
+    return 0;
+}
+
 int b200vae_sync_weights(b200vae_ctx* ctx, void* stream) {
     // refresh every derived copy of the parameters (the fp16 image of W_d read by the tensor cores);
     // call after the weight arena was modified by anything other than b200vae_adam_step
@@ -1005,6 +1038,7 @@ int b200vae_decode(b200vae_ctx* ctx, const float* z, int32_t B, float* scores, v
         TcEpi e;
         e.bias = c->w + DL.b_off;
         B200_CHECK(launch_to_f16(c, h, c->h16, B, DL.in, DL.in, s));
+        B200_CHECK(wait_wd16(c, s));
         return launch_tc_gemm(c, TC_EPI_STORE, c->h16, DL.in, 0, c->wd16, DL.in, 0, scores, c->n_items, B, c->n_items, DL.in, e, s);
     }
     return linear_fwd(c, h, B, DL, scores, s);

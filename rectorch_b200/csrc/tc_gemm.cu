@@ -346,7 +346,7 @@ __device__ __forceinline__ void epi_chunk(const TcArgs& a, const float* v, const
         if (m < a.M) {
             float* crow = reinterpret_cast<float*>(a.C) + (int64_t)sp * a.split_stride + (int64_t)m * a.ldc;
             const int col0 = n0 + c0;
-            if (a.vec_ok && col0 + 32 <= a.n_store) {
+            if (a.vec_ok && nc == 32 && col0 + 32 <= a.n_store) {   // nc < 32: the N tile ends inside this chunk
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + i);

@@ -110,6 +110,7 @@ class Engine:
         self._seen_version = -1
         self.loss_buf = torch.zeros(4, dtype=torch.float32, device=self.device)
         self.adam_steps = 0
+        self.wd16 = None          # caller-owned fp16 image of W_d (data parallelism with a sharded optimizer)
 
     # ---- views ---------------------------------------------------------------------------------
     def _views(self, arena, i):
@@ -167,6 +168,8 @@ class Engine:
         check(_lib.lib().b200vae_bind_params(self._ctx, ptr(self.w), ptr(self.g), ptr(self.m), ptr(self.v),
                                               self.n_elems, w_off, b_off))
         self._seen_version = self.w._version
+        if self.wd16 is not None:
+            check(_lib.lib().b200vae_bind_shadow(self._ctx, ptr(self.wd16), self.wd16.numel()))
         for slot in (0, 1):
             if self._csr[slot] is not None:
                 self._bind(slot, self._csr[slot])
@@ -190,6 +193,20 @@ class Engine:
         self._csr[slot] = csr
         if self._ctx is not None:
             self._bind(slot, csr)
+
+    def use_external_shadow(self):
+        """Keep the fp16 image of the decoder output weight in a torch tensor (so that torch.distributed can
+        all-gather shards of it) instead of a context-owned buffer.  Returns the tensor [n_items * H] (fp16)."""
+        if self.wd16 is None:
+            out_f, in_f = self.shapes[-1]
+            self.wd16 = torch.zeros(out_f * in_f, dtype=torch.float16, device=self.device)
+            if self._ctx is not None:
+                check(_lib.lib().b200vae_bind_shadow(self._ctx, ptr(self.wd16), self.wd16.numel()))
+        return self.wd16
+
+    def defer_wait(self, event):
+        """The next call that reads the fp16 image of W_d waits for ``event`` (torch.cuda.Event, recorded)."""
+        check(_lib.lib().b200vae_defer_wait_event(self._ctx, ctypes.c_void_p(event.cuda_event)))
 
     def _sync_weights_if_dirty(self):
         # torch ops that write the arena (init_weights, load_state_dict, manual edits) bump the

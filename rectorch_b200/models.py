@@ -100,6 +100,57 @@ def _dist_world():
     return 0, 1
 
 
+class _StagedBatch:
+    """Device staging area of ``train_batch_csr`` under data parallelism: the GLOBAL batch as a small CSR matrix
+    that is re-filled from host arrays every step; plays the sampler's role for ``RowBatch``."""
+
+    replicate = True
+    row_offset = 0
+
+    def __init__(self, device, cap_rows, cap_nnz, has_values, n_items, rank, world):
+        self.device, self.cap_rows, self.cap_nnz, self.n_items = device, cap_rows, cap_nnz, n_items
+        self.rank, self.world = rank, world
+        self.indptr = torch.zeros(cap_rows + 1, dtype=torch.int64, device=device)
+        self.indices = torch.zeros(cap_nnz, dtype=torch.int32, device=device)
+        self.values = torch.zeros(cap_nnz, dtype=torch.float32, device=device) if has_values else None
+        self.shape = (cap_rows, n_items)
+        self.nnz = 0
+        self.max_row_nnz = 1
+        self._ar = torch.arange(cap_rows, dtype=torch.int32, device=device)
+
+    def load(self, indptr, indices, values, B, nnz):
+        self.indptr[:B + 1].copy_(indptr, non_blocking=True)
+        self.indices[:nnz].copy_(indices, non_blocking=True)
+        if values is not None:
+            self.values[:nnz].copy_(values, non_blocking=True)
+        self.shape = (B, self.n_items)
+        self.nnz = nnz
+        # capacity hint for the engine: any B/world rows hold at most all the non-zeros of the batch
+        self.max_row_nnz = max(self.max_row_nnz, -(-nnz // max(B // self.world, 1)) + 1)
+
+    def device_csr(self, device=None):
+        return self, None
+
+    def rows(self, B):
+        lb = B // self.world
+        return self._ar[self.rank * lb:(self.rank + 1) * lb]
+
+    def all_rows(self, B):
+        return self._ar[:B]
+
+
+def zero_shard(n_elems, world_size, rank):
+    """Element range ``[lo, hi)`` of a ``n_elems``-long tensor owned by ``rank`` when its optimizer state is
+    sharded evenly over ``world_size`` ranks, or ``None`` when it cannot be (shards must be equal and 16-byte
+    aligned both as fp32 and as fp16: ``n_elems % (8 * world_size) == 0``).  Pure host arithmetic."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError("bad rank/world_size %r/%r" % (rank, world_size))
+    if n_elems <= 0 or n_elems % (8 * world_size) != 0:
+        return None
+    per = n_elems // world_size
+    return rank * per, (rank + 1) * per
+
+
 class AETrainer(TorchNNTrainer):
     """Shared machinery of the two auto-encoder trainers (epoch loop, logging, predict,
     checkpoints: rectorch/models.py:379-516)."""
@@ -126,8 +177,58 @@ class AETrainer(TorchNNTrainer):
         self._pg_small = None
         self._dp_seed = None
         self._delta_bufs = None
+        self._zero = None             # (lo, hi) arena range of the W_d shard this rank optimises (ZeRO-1), or None
+        self._wd_stale = False        # fp32 W_d (and its Adam moments) outside the own shard lag behind
+        self._wd_event = None
         if _dist_world()[1] > 1:
             self._pg_small = dist.new_group()
+            self._broadcast_state()
+            self.network.register_state_dict_pre_hook(lambda *a, **k: self.sync_weights())
+
+    # ---- data-parallel state ----------------------------------------------------------------------------
+    def _broadcast_state(self):
+        """Every data-parallel path assumes bit-identical replicas: take rank 0's weights, Adam moments and step
+        count (construction with different seeds, or a checkpoint loaded on one rank only, would otherwise
+        diverge silently)."""
+        eng = self._engine
+        for t in (eng.w, eng.m, eng.v):
+            dist.broadcast(t, src=0)
+        st = torch.tensor([float(eng.adam_steps)], dtype=torch.float64, device=self.device)
+        dist.broadcast(st, src=0)
+        eng.adam_steps = int(st.item())
+        self._step_tensor.fill_(float(eng.adam_steps))
+        self._wd_stale = False
+
+    def _zero_range(self, world, rank, wd, lam):
+        """Arena range of this rank's shard of the decoder output weight, or None when the sharded optimizer does
+        not apply (MultiDAE's per-tensor norm / weight decay need whole tensors; SIMT path; uneven shards)."""
+        eng = self._engine
+        if not eng.use_tc or wd != 0.0 or lam != 0.0 or os.environ.get("B200VAE_DP_ZERO", "1") == "0":
+            return None
+        out_f, in_f = eng.shapes[-1]
+        sh = zero_shard(out_f * in_f, world, rank)
+        if sh is None:
+            return None
+        cut = eng.w_off[-1]
+        return cut + sh[0], cut + sh[1]
+
+    def sync_weights(self, with_state=True):
+        """Sharded optimizer: all-gather the fp32 decoder output weight (and its Adam moments) so that every rank
+        holds the complete tensors again -- needed before anything reads them as fp32 (``state_dict``,
+        ``save_model``, direct access to ``network.dec_layers[-1].weight``); training itself only needs the fp16
+        image, which every step all-gathers."""
+        if not self._wd_stale:
+            return
+        eng = self._engine
+        rank, world = _dist_world()
+        lo, hi = self._zero
+        cut = eng.w_off[-1]
+        n = (hi - lo) * world
+        torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
+        for arena in ((eng.w, eng.m, eng.v) if with_state else (eng.w,)):
+            dist.all_gather_into_tensor(arena[cut:cut + n], arena[lo:hi])
+        eng._seen_version = eng.w._version      # the fp16 image is already current
+        self._wd_stale = False
 
     # ---- optimizer <-> arena coupling --------------------------------------------------------------
     def _make_optimizer(self, lr):
@@ -215,7 +316,12 @@ class AETrainer(TorchNNTrainer):
         if world == 1:
             eng.train_step(lr=lr, betas=betas, eps=eps, weight_decay=wd, **kw)
         elif replicated:
-            self._step_dp_factors(tr_batch, B_local, world, rank, lr, betas, eps, wd, lam, loss_slot, kw)
+            if self._zero is None and not self._wd_stale:
+                self._zero = self._zero_range(world, rank, wd, lam) or False
+            if self._zero:
+                self._step_dp_zero(tr_batch, B_local, world, rank, lr, betas, eps, loss_slot, kw)
+            else:
+                self._step_dp_factors(tr_batch, B_local, world, rank, lr, betas, eps, wd, lam, loss_slot, kw)
         else:
             # row-sharded data parallelism: local gradients are already scaled by 1/B_global
             eng.forward_backward(B_global=B_local * world, step=eng.adam_steps + 1, row_offset=row_offset, **kw)
@@ -278,6 +384,59 @@ class AETrainer(TorchNNTrainer):
         eng.adam_range(lr, betas, eps, wd, lam, 0, cut, first=True)
         main.wait_stream(side)
         eng.adam_range(lr, betas, eps, wd, lam, cut, eng.n_elems, first=False)
+
+    def _step_dp_zero(self, rb, B_local, world, rank, lr, betas, eps, loss_slot, kw):
+        """Data-parallel step with a ZeRO-1 style sharded optimizer for the decoder output weight W_d (half of
+        the parameters).  Per step and rank:
+
+        * side stream: ``reduce_scatter`` of dW_d as soon as it is final (same NVLink volume as the first half of
+          an all-reduce) -> Adam on the own 1/N shard (1/N of the optimizer's HBM traffic; writes the fp16 image of
+          the shard in the same pass) -> ``all_gather`` of the fp16 image (half the bytes of the fp32 weights).
+          The next step's K4 waits for that all-gather; its sparse encoder runs beside it.
+        * main stream: the encoder-0 gradient from gathered factors (see ``_step_dp_factors``), one small
+          ``all_reduce`` for the hidden-layer tensors and b_d, replicated Adam on those.
+
+        fp32 W_d and its Adam moments stay sharded between steps (``sync_weights`` gathers them on demand)."""
+        eng = self._engine
+        H1 = eng.shapes[0][0]
+        n_rows = int(rb.all_rows.numel())
+        if n_rows != B_local * world:
+            raise RuntimeError("replicated RowBatch: %d global rows for %d ranks x %d local rows" % (n_rows, world, B_local))
+        step = eng.adam_steps + 1
+        if self._delta_bufs is None or self._delta_bufs[0].shape[0] != B_local or self._delta_bufs[1].shape[0] != n_rows:
+            self._delta_bufs = (torch.empty((B_local, H1), dtype=torch.float32, device=self.device),
+                                torch.empty((n_rows, H1), dtype=torch.float32, device=self.device))
+        mine, everyone = self._delta_bufs
+        wd16 = eng.use_external_shadow()
+        eng.forward_backward(B_global=n_rows, step=step, row_offset=0, enc0_delta_out=mine, **kw)
+        lo, hi = self._zero
+        cut = eng.w_off[-1]
+        per = hi - lo
+        n_wd = per * world
+        side = self._comm_stream
+        main = torch.cuda.current_stream(self.device)
+        if self._wd_event is None:
+            self._wd_event = torch.cuda.Event()
+        check(_lib.lib().b200vae_wait_wd_ready(eng._ctx, ctypes.c_void_p(side.cuda_stream)))
+        with torch.cuda.stream(side):
+            dist.reduce_scatter_tensor(eng.g[lo:hi], eng.g[cut:cut + n_wd], op=dist.ReduceOp.SUM)
+            eng.adam_range(lr, betas, eps, 0.0, 0.0, lo, hi, first=True)
+            dist.all_gather_into_tensor(wd16[:n_wd], wd16[lo - cut:hi - cut])
+            dist.all_reduce(loss_slot, op=dist.ReduceOp.SUM)
+            self._wd_event.record(side)
+        eng.defer_wait(self._wd_event)
+        self._wd_stale = True
+        # main stream: exchange the encoder-0 factors and rebuild that gradient for the global batch
+        small = self._pg_small
+        dist.all_gather_into_tensor(everyone, mine, group=small)
+        eng.enc0_grad(rb.all_rows, everyone, kw["dropout_p"], kw["seed"], step, 0)
+        s_lo = eng.w_off[1] if len(eng.w_off) > 1 else cut
+        if s_lo < cut:
+            dist.all_reduce(eng.g[s_lo:cut], op=dist.ReduceOp.SUM, group=small)
+        if cut + n_wd < eng.n_elems:        # b_d (and arena padding): replicated like the hidden layers
+            dist.all_reduce(eng.g[cut + n_wd:], op=dist.ReduceOp.SUM, group=small)
+            eng.adam_range(lr, betas, eps, 0.0, 0.0, cut + n_wd, eng.n_elems, first=False)
+        eng.adam_range(lr, betas, eps, 0.0, 0.0, 0, cut, first=False)
 
     def _loss_from(self, comps, beta, lam):
         """Python float loss from the 4 device components (sum over ranks already applied)."""
@@ -349,6 +508,8 @@ class AETrainer(TorchNNTrainer):
         return total_loss
 
     def _drain(self, window):
+        if _dist_world()[1] > 1:
+            torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
         hist = self._loss_hist[:4 * (max(s for s, _, _ in window) + 1)].view(-1, 4).cpu()
         total = 0.0
         for slot, beta, lam in window:
@@ -369,6 +530,55 @@ class AETrainer(TorchNNTrainer):
         slot = self._loss_hist[:4]
         self._step(tr_batch, te_batch, beta, lam, slot, _rng_tape)
         self._after_step()
+        if _dist_world()[1] > 1:
+            torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
+        return self._loss_from(slot, beta, lam)
+
+    def train_batch_csr(self, indptr, indices, values=None):
+        """One optimisation step on a batch given as HOST CSR arrays -- the sparse counterpart of
+        ``train_batch(dense_tensor)`` (rectorch/models.py:424-447, 817-835) for callers that keep their ratings
+        in CSR form and do not want to densify ``[B x n_items]`` floats per step.
+
+        ``indptr`` int64 ``[B+1]`` (rebased to 0), ``indices`` int32 ``[nnz]``, ``values`` float32 ``[nnz]`` or
+        ``None`` for binary ratings: CPU tensors, ideally pinned.  The call copies them to the device, runs the
+        step and returns the loss as a python float (device -> host sync), every call.
+
+        Under data parallelism every rank passes the same GLOBAL batch (``B`` divisible by the world size);
+        rank r trains on rows ``[r*B/N, (r+1)*B/N)``."""
+        eng = self._engine
+        rank, world = _dist_world()
+        B = int(indptr.numel()) - 1
+        nnz = int(indptr[-1])
+        beta, lam = self._step_coeffs()
+        lr, betas, eps, wd = self._hyper()
+        p = float(self.network.dropout.p)
+        if world == 1:
+            if betas != (0.9, 0.999) or eps != 1e-8:
+                raise ValueError("train_batch_csr runs Adam with torch's default betas / eps")
+            eng._ensure_ctx(B, max(nnz, 1))
+            eng._sync_weights_if_dirty()
+            if getattr(self, "_loss_host", None) is None:
+                self._loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+            eng.adam_steps += 1
+            with torch.cuda.device(self.device):
+                check(_lib.lib().b200vae_train_step_host(
+                    eng._ctx, ptr(indptr), ptr(indices), ptr(values), B, float(beta), float(lam), p, draw_seed(),
+                    eng.adam_steps, float(lr), float(wd), ptr(self._loss_host), stream_ptr()))
+            self._step_tensor += 1.0
+            self._after_step()
+            return float(self._loss_host[0])
+        if B % world != 0:
+            raise ValueError("the global batch (%d rows) must be divisible by the world size (%d)" % (B, world))
+        st = getattr(self, "_stage", None)
+        if st is None or st.cap_rows < B or st.cap_nnz < nnz or (values is not None) != (st.values is not None):
+            st = self._stage = _StagedBatch(self.device, max(B, getattr(st, "cap_rows", 0)),
+                                            max(nnz, getattr(st, "cap_nnz", 0), 1), values is not None,
+                                            int(self._engine.n_items), rank, world)
+        st.load(indptr, indices, values, B, nnz)
+        slot = self._loss_hist[:4]
+        self._step(RowBatch(st, st.rows(B), False, st.all_rows(B)), None, beta, lam, slot)
+        self._after_step()
+        torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
         return self._loss_from(slot, beta, lam)
 
     def predict(self, x, remove_train=True):
@@ -387,15 +597,22 @@ class AETrainer(TorchNNTrainer):
         return (scores, )
 
     def save_model(self, filepath, cur_epoch):
+        self.sync_weights()
         state = {'epoch': cur_epoch,
                  'state_dict': self.network.state_dict(),
                  'optimizer': self.optimizer.state_dict()}
         self._save_checkpoint(filepath, state)
 
     def _save_checkpoint(self, filepath, state):
-        logger.info("Saving model checkpoint to %s...", filepath)
-        torch.save(state, filepath)
-        logger.info("Model checkpoint saved!")
+        """One file per job: under data parallelism the replicas are identical, rank 0 writes and everybody
+        waits for the file."""
+        rank, world = _dist_world()
+        if rank == 0:
+            logger.info("Saving model checkpoint to %s...", filepath)
+            torch.save(state, filepath)
+            logger.info("Model checkpoint saved!")
+        if world > 1:
+            dist.barrier()
 
     def load_model(self, filepath):
         assert os.path.isfile(filepath), "The checkpoint file %s does not exist." % filepath
@@ -404,6 +621,8 @@ class AETrainer(TorchNNTrainer):
         self.network.load_state_dict(checkpoint['state_dict'])
         self.optimizer.load_state_dict(checkpoint['optimizer'])
         self._adopt_optimizer_state(fresh=False)
+        if _dist_world()[1] > 1:
+            self._broadcast_state()
         logger.info("Model checkpoint loaded!")
         return checkpoint
 
@@ -495,6 +714,7 @@ class MultiVAE(AETrainer):
             logger.warning('Handled KeyboardInterrupt: exiting from training early')
 
     def save_model(self, filepath, cur_epoch):
+        self.sync_weights()
         state = {'epoch': cur_epoch,
                  'state_dict': self.network.state_dict(),
                  'optimizer': self.optimizer.state_dict(),

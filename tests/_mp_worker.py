@@ -31,21 +31,29 @@ csr = synth.make_matrix(N_USERS, N_ITEMS, seed=3, mu=3.0, sigma=0.7, min_len=3, 
 torch.manual_seed(0)
 net = MultiVAE_net([32, 96, N_ITEMS]).cuda()
 model = MultiVAE(net, beta=0.3, anneal_steps=10)
-mode = sys.argv[3] if len(sys.argv) > 3 else "factors"   # "factors": replicated CSR, encoder-0 gradient from
-                                                          # gathered factors; "allreduce": sharded CSR, dense all-reduce
-torch.manual_seed(123 + (rank if mode == "factors" else 0))   # factors mode must not depend on per-rank generators
+mode = sys.argv[3] if len(sys.argv) > 3 else "zero"
+# "zero":      replicated CSR, encoder-0 gradient from gathered factors, W_d optimiser state sharded over the ranks
+#              (reduce-scatter -> Adam on the shard -> all-gather of the fp16 image)      [default with N > 1]
+# "factors":   the same exchange with a replicated optimiser (all-reduce of dW_d); B200VAE_DP_ZERO=0
+# "allreduce": sharded CSR, dense all-reduce of the whole gradient arena
+if mode == "factors":
+    os.environ["B200VAE_DP_ZERO"] = "0"
+replicated = mode in ("zero", "factors")
+torch.manual_seed(123 + (rank if replicated else 0))   # replicated modes must not depend on per-rank generators
 losses = []
 if world > 1:
     sampler = DataSampler(csr, None, batch_size=GB, shuffle=False, rank=rank, world_size=world,
-                          replicate=(mode == "factors"))
+                          replicate=replicated)
     for i, rb in enumerate(sampler.iter_rows()):
         if i >= STEPS:
             break
-        assert (rb.all_rows is not None) == (mode == "factors")
+        assert (rb.all_rows is not None) == replicated
         losses.append(model.train_batch(rb))
+    assert bool(model._zero) == (mode == "zero"), (mode, model._zero)
+    model.sync_weights()            # collective: fp32 W_d shards -> every rank (no-op outside "zero")
 else:
     from rectorch_b200.engine import draw_seed
-    if mode == "factors":
+    if replicated:
         model._dp_seed = draw_seed()     # what rank 0 draws and broadcasts in the multi-process run
     sampler = DataSampler(csr, None, batch_size=GB, shuffle=False)
     sampler.device_csr()
@@ -54,9 +62,12 @@ else:
         rows = np.concatenate([r * (N_USERS // ref_world) + np.arange(i * lb, (i + 1) * lb) for r in range(ref_world)])
         rb = RowBatch(sampler, torch.from_numpy(rows.astype(np.int32)).cuda(), False)
         losses.append(model.train_batch(rb))
+sd = {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
+osd = model.optimizer.state_dict()["state"]
+last = len(osd) - 2                       # decoder output weight: the sharded tensor
 if rank == 0:
-    sd = {k: v.detach().cpu().numpy() for k, v in net.state_dict().items()}
-    np.savez(out_path, losses=np.array(losses), **sd)
+    np.savez(out_path, losses=np.array(losses), adam_m_wd=osd[last]["exp_avg"].cpu().numpy(),
+             adam_v_wd=osd[last]["exp_avg_sq"].cpu().numpy(), **sd)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()

@@ -74,6 +74,9 @@ def test_training_parity_with_reference_fixture(name):
     osd = model.optimizer.state_dict()["state"]
     for i, k in enumerate(sd.keys()):
         assert np.abs(osd[i]["exp_avg"].cpu().numpy() - g["adam_m/" + k]).max() <= 5e-5, k
+        if "adam_v/" + k in g:
+            ref_v = g["adam_v/" + k]
+            assert np.abs(osd[i]["exp_avg_sq"].cpu().numpy() - ref_v).max() <= 1e-6 + 1e-3 * np.abs(ref_v).max(), k
         assert float(osd[i]["step"]) == g["steps"]
 
 
@@ -178,6 +181,50 @@ def test_gradients_vs_oracle_tc_path():
             scale = ref.abs().max().item() + 1e-12
             d = (got.detach().cpu() - ref).abs().max().item()
             assert d <= 2e-3 * scale, "%s: max err %g vs scale %g" % (nm, d, scale)
+
+
+@pytest.mark.parametrize("cfg", ["cfg2", "cfg3"])
+def test_parity_at_benchmark_shapes(cfg):
+    """The shapes bench.py measures -- cfg2: MultiVAE [50000-600-200], cfg3: MultiDAE [50000-200] (lam and coupled
+    weight decay on), batch 500, n_items 50000 (209 item tiles of 240 on 74 CTA pairs, two 256-user row groups) --
+    against the oracle: 3 tape-driven steps (loss <= 1e-4 relative), then predict + recall@20 / ndcg@100 on one
+    500-user batch (<= 1e-3).  The oracle's dense [500 x 50000] step takes ~1 s on the GPU box's host cores."""
+    vae = cfg == "cfg2"
+    n_items, B = 50000, 500
+    csr = synth.make_matrix(4 * B, n_items, seed=31)
+    tr, te = synth.split_heldout(csr, 0.2, seed=32)
+    dims = [200, 600, n_items] if vae else [200, n_items]
+    g = {"vae": vae, "dec_dims": dims, "n_users": 4 * B, "n_items": n_items, "batch": B, "p": 0.5,
+         "seed_rng": 4242, "beta": 0.2, "anneal": 20000, "lam": 0.2}
+    torch.manual_seed(7)
+    net = (MultiVAE_net if vae else MultiDAE_net)(list(dims), None, g["p"])
+    sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    model = (MultiVAE(net.cuda(), beta=g["beta"], anneal_steps=g["anneal"]) if vae else MultiDAE(net.cuda(), lam=g["lam"]))
+    assert model._engine.use_tc
+    onet = O.Net.from_state_dict(sd0, vae, g["p"])
+    ost = O.AdamState(onet, lr=1e-3, weight_decay=0.0 if vae else 1e-3)
+    losses, olosses = _run_steps(model, g, tr, te, 3, onet, ost)
+    err = rel_err(losses, olosses)
+    print("%s: device %s oracle %s rel err %s" % (cfg, losses, olosses, err))
+    assert err.max() <= LOSS_RTOL
+    osd = onet.state_dict()
+    for k, v in model.network.state_dict().items():
+        diff = (v.detach().cpu() - osd[k]).abs()
+        assert diff.max().item() <= 3 * 3 * 1e-3, k
+        assert (diff > 2e-4).float().mean().item() < 0.02, k
+    # one 500-user evaluation batch on the trained weights
+    mets = ["recall@20", "ndcg@100"]
+    tr1, te1 = tr.rows(3 * B, 4 * B), te.rows(3 * B, 4 * B)
+    res = evaluate(model, DataSampler(tr1.to_scipy(), te1.to_scipy(), batch_size=B, shuffle=False), mets)
+    ores = O.evaluate(onet, tr1.to_scipy(), te1.to_scipy(), B, mets)
+    for m in mets:
+        assert abs(np.nanmean(res[m]) - np.nanmean(ores[m])) <= METRIC_ATOL, m
+    xs = torch.from_numpy(tr1.rows(0, 64).toarray())
+    pred = model.predict(xs.cuda(), True)[0].cpu()
+    oc = O.forward(onet, xs, False, None, None)
+    ref = oc["logits"] if isinstance(oc, dict) else oc[0]
+    seen = xs != 0
+    assert torch.isinf(pred[seen]).all() and (pred[~seen] - ref[~seen]).abs().max().item() < 2e-3
 
 
 def test_full_size_properties_cfg2_shapes():

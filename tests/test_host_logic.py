@@ -179,6 +179,22 @@ p0 = s0.global_plan()
 assert np.array_equal(p0[1], np.arange(*shard_plan(n_users, bg, 1, world)[:2])[:used])
 s1 = DataSampler(m, None, batch_size=bg, shuffle=False, rank=rank, world_size=world, replicate=False)
 assert not s1.replicate and s1.row_offset == lo
+# sharded optimiser (AETrainer._step_dp_zero): sum over ranks of the local W_d gradients, each rank updates only its
+# shard and the shards are gathered back == the replicated update on the all-reduced gradient
+from rectorch_b200.models import zero_shard
+n_wd = 64 * world * 5
+a, b = zero_shard(n_wd, world, rank)
+assert (b - a) * world == n_wd and a == rank * (b - a) and zero_shard(n_wd + 8, world, rank) is None
+gl = torch.from_numpy(np.random.default_rng(7 + rank).standard_normal(n_wd).astype(np.float32))
+full = gl.clone(); dist.all_reduce(full)
+parts = [torch.empty(b - a) for _ in range(world)]
+for r in range(world):      # reduce_scatter emulated with reduce (gloo has no reduce_scatter)
+    t = gl[r * (b - a):(r + 1) * (b - a)].clone(); dist.reduce(t, dst=r)
+    if r == rank: mine_g = t
+w_new = -0.001 * torch.sign(mine_g)                   # stand-in for Adam on the shard
+lst = [torch.empty(b - a) for _ in range(world)]
+dist.all_gather(lst, w_new)
+assert torch.equal(torch.cat(lst), -0.001 * torch.sign(full)), "sharded update != replicated update"
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 """
