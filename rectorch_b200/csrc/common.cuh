@@ -94,7 +94,7 @@ int launch_target_fixup(Ctx* c, const BatchView& tgt, __half* PT, int64_t ldp, c
                         float* loss_row, cudaStream_t s);
 int launch_row_sums(Ctx* c, const BatchView& v, float* out, cudaStream_t s);
 int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const float* Wt, int H,
-                       const float* bias, int act, float* out, cudaStream_t s);
+                       const float* bias, int act, float* out, cudaStream_t s, __half* out16 = nullptr, int64_t ld16 = 0);
 int launch_spmm_scatter(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
                         int H, float* dWt, cudaStream_t s);
 int launch_spmm_scatter_bias(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
@@ -120,9 +120,9 @@ int launch_lse_merge(Ctx* c, const float* pmax, const float* psum, int n_tiles, 
 // elementwise.cu
 int launch_reparam_kl(Ctx* c, const float* enc_out, int B, int L, bool train, const float* eps_tape,
                       uint64_t seed, uint64_t step, int64_t row_offset, const int32_t* row_ids,
-                      float* z, float* eps_out, float* kl_row, cudaStream_t s);
+                      float* z, float* eps_out, float* kl_row, __half* z16, int64_t ldz16, cudaStream_t s);
 int launch_dz_to_denc(Ctx* c, const float* dz, const float* enc_out, const float* eps, int B, int L,
-                      float beta_over_B, bool train, float* denc, cudaStream_t s);
+                      float beta_over_B, bool train, float* denc, __half* denc16, int64_t ld16, cudaStream_t s);
 int launch_loss_final(Ctx* c, const float* loss_row, const float* kl_row, int B, float inv_Bg,
                       float beta, float lam, const float* norms, int n_tensors, float* loss_out,
                       cudaStream_t s);
@@ -143,6 +143,8 @@ struct AdamOpt {
     int row_len = 0;
     int ctas_per_sm = 8;
     int threads = 256;
+    __half* shadow2 = nullptr;      // fp16 image of the hidden-layer tensors: elements [s2_lo, s2_hi) of THIS launch
+    int64_t s2_lo = 0, s2_hi = 0;   // (indices relative to the launch's base pointers) go to shadow2[e - s2_lo]
 };
 int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float lr_over_bc1,
                 float beta1, float beta2, float bc2_sqrt, float eps, float wd, float lam,
@@ -175,6 +177,12 @@ struct TcEpi {
     int n_fastest = 0;                 // walk N tiles first (A tile shared through L2 by consecutive CTAs)
     float out_scale = 1.f;             // TC_EPI_STORE: product * out_scale * (*out_scale_ptr)
     const float* out_scale_ptr = nullptr;
+    // TC_EPI_STORE, plain (non-transposed, no split-K) output only -- the hidden layers (nets.py:398-404, 413-416):
+    int act = 0;                       // 1 = tanh after the bias
+    const float* mulY = nullptr;       // out *= 1 - Y[m,n]^2   (tanh' of the layer below, backward pass)
+    int64_t ldy = 0;
+    __half* C16 = nullptr;             // fp16 image of the output for the next tensor-core GEMM (pitch ldc16)
+    int64_t ldc16 = 0;
 };
 // pitches (lda, ldb) in halfs, multiples of 8; A / B are __half arrays; C is float (STORE) or __half (PROB)
 bool tc_supported(int M, int N, int K, int64_t lda, int64_t ldb);
@@ -188,7 +196,38 @@ int tc_parallel_tiles(int num_sms);            // tiles that run concurrently (S
 int launch_splitk_reduce(Ctx* c, const float* parts, int n_split, int64_t split_stride, float* out,
                          int64_t ld_out, int M, int N, int64_t ld_part, const float* addend,
                          int64_t ld_add, float addend_scale, const float* mulY, int64_t ldy,
-                         const float* rowscale, float scale, cudaStream_t s);
+                         const float* rowscale, float scale, cudaStream_t s, __half* out16 = nullptr, int64_t ld16 = 0);
+
+// ---- programmatic dependent launch ---------------------------------------------------------
+// A training step is a chain of ~20 short kernels on one stream; between two of them the GPU normally idles for the
+// launch latency of the next.  Every hot-path kernel therefore (a) is launched with the programmatic-stream-
+// serialization attribute (launch_pdl) and (b) starts with pdl_sync(): griddepcontrol.wait blocks until the previous
+// kernel of the stream has completed and its writes are visible -- nothing before it touches global memory -- and
+// griddepcontrol.launch_dependents lets the NEXT kernel be scheduled (its CTAs then park at their own wait).
+// The ordering guarantees are those of a plain stream; only the launch latency is overlapped.  B200VAE_PDL=0 turns
+// the attribute off (the device-side instructions are then no-ops).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                     Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 // ---- device helpers ----------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -59,6 +59,19 @@ struct Ctx {
     bool wd16_external = false;       // wd16 is a caller-owned buffer (b200vae_bind_shadow)
     cudaEvent_t wd16_pending = nullptr;   // the next reader of wd16 waits for this event first (b200vae_defer_wait_event)
     float* dw_scale = nullptr;        // [1] R = power of two >= max_u T_u/B of the current batch (un-scales dW_d)
+    // hidden layers on the tensor cores (tc_hidden): fp16 images of their weights (arena range [ws_lo, ws_hi),
+    // maintained by Adam like wd16) and of every activation / activation gradient they read.  Activation images have
+    // pitch round_up(width + 1, 8) and a column of ones at index `width` (set once): used as the B operand of the
+    // weight-gradient GEMM it makes the bias gradient one more output column (no separate column-sum kernel).
+    bool tc_hidden = false;
+    __half* ws16 = nullptr;
+    int64_t ws_lo = 0, ws_hi = 0;
+    std::vector<__half*> act_enc16, act_dec16;
+    std::vector<int> ld_enc16, ld_dec16;
+    __half* z16 = nullptr;
+    int ldz16 = 0;
+    __half* dbuf16[2] = {nullptr, nullptr};   // fp16 images of the ping-pong activation gradients, pitch ld_d16
+    int ld_d16 = 0;
     int32_t* d_specs = nullptr;       // [128] metric specs for topk
     float* spmm_acc = nullptr;        // [B x max(width)] zeroed accumulator for multi-segment gathers
     int*   spmm_ticket = nullptr;     // [B] zeroed per-row completion tickets

@@ -16,7 +16,8 @@ __global__ void k_reparam_kl(const float* __restrict__ enc_out, int B, int L, in
                              const float* __restrict__ eps_tape, uint64_t seed, uint64_t step,
                              int64_t row_offset, const int32_t* __restrict__ row_ids,
                              float* __restrict__ z, float* __restrict__ eps_out,
-                             float* __restrict__ kl_row) {
+                             float* __restrict__ kl_row, __half* __restrict__ z16, int64_t ldz16) {
+    pdl_sync();
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= B) return;
@@ -44,6 +45,7 @@ __global__ void k_reparam_kl(const float* __restrict__ enc_out, int B, int L, in
             zz = m_ + e * expf(0.5f * v_);
         }
         z[(int64_t)warp * L + l] = zz;
+        if (z16) z16[(int64_t)warp * ldz16 + l] = __float2half_rn(f16_clamp(zz));
     }
     kl = warp_sum(kl);
     if (lane == 0) kl_row[warp] = -0.5f * kl;
@@ -51,11 +53,12 @@ __global__ void k_reparam_kl(const float* __restrict__ enc_out, int B, int L, in
 
 int launch_reparam_kl(Ctx* c, const float* enc_out, int B, int L, bool train, const float* eps_tape,
                       uint64_t seed, uint64_t step, int64_t row_offset, const int32_t* row_ids,
-                      float* z, float* eps_out, float* kl_row, cudaStream_t s) {
+                      float* z, float* eps_out, float* kl_row, __half* z16, int64_t ldz16, cudaStream_t s) {
     if (B == 0) return 0;
     int threads = 256;
-    k_reparam_kl<<<(int)cdiv((int64_t)B * 32, threads), threads, 0, s>>>(
-        enc_out, B, L, train ? 1 : 0, eps_tape, seed, step, row_offset, row_ids, z, eps_out, kl_row);
+    B200_CUDA_OK(launch_pdl(k_reparam_kl, dim3((unsigned)cdiv((int64_t)B * 32, threads)), dim3(threads), 0, s,
+                            enc_out, B, L, train ? 1 : 0, eps_tape, seed, step, row_offset, row_ids, z, eps_out, kl_row, z16,
+                            ldz16));
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -64,7 +67,8 @@ int launch_reparam_kl(Ctx* c, const float* enc_out, int B, int L, bool train, co
 // d(enc_out) from dz:  dmu = dz + beta*mu/B ;  dlogvar = dz*eps*0.5*std + beta*0.5*(exp(lv)-1)/B
 __global__ void k_dz_to_denc(const float* __restrict__ dz, const float* __restrict__ enc_out,
                              const float* __restrict__ eps, int B, int L, float beta_over_B, int train,
-                             float* __restrict__ denc) {
+                             float* __restrict__ denc, __half* __restrict__ denc16, int64_t ld16) {
+    pdl_sync();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * L) return;
     int r = (int)(i / L), l = (int)(i % L);
@@ -72,15 +76,21 @@ __global__ void k_dz_to_denc(const float* __restrict__ dz, const float* __restri
     float d = dz[i];
     float dlv = beta_over_B * 0.5f * (expf(lv) - 1.f);
     if (train) dlv += d * eps[i] * 0.5f * expf(0.5f * lv);
-    denc[(int64_t)r * 2 * L + l] = d + beta_over_B * mu;
+    const float dmu = d + beta_over_B * mu;
+    denc[(int64_t)r * 2 * L + l] = dmu;
     denc[(int64_t)r * 2 * L + L + l] = dlv;
+    if (denc16) {
+        denc16[(int64_t)r * ld16 + l] = __float2half_rn(f16_clamp(dmu));
+        denc16[(int64_t)r * ld16 + L + l] = __float2half_rn(f16_clamp(dlv));
+    }
 }
 
 int launch_dz_to_denc(Ctx* c, const float* dz, const float* enc_out, const float* eps, int B, int L,
-                      float beta_over_B, bool train, float* denc, cudaStream_t s) {
+                      float beta_over_B, bool train, float* denc, __half* denc16, int64_t ld16, cudaStream_t s) {
     int64_t n = (int64_t)B * L;
     if (n == 0) return 0;
-    k_dz_to_denc<<<(int)cdiv(n, 256), 256, 0, s>>>(dz, enc_out, eps, B, L, beta_over_B, train ? 1 : 0, denc);
+    B200_CUDA_OK(launch_pdl(k_dz_to_denc, dim3((unsigned)cdiv(n, 256)), dim3(256), 0, s, dz, enc_out, eps, B, L, beta_over_B,
+                            train ? 1 : 0, denc, denc16, ld16));
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -92,6 +102,7 @@ __global__ void k_loss_final(const float* __restrict__ loss_row, const float* __
                              float inv_Bg, float beta, float lam, const float* __restrict__ norms,
                              int n_tensors, float* __restrict__ loss_out) {
     __shared__ float s1[256], s2[256];
+    pdl_sync();
     float a = 0.f, b = 0.f;
     for (int i = threadIdx.x; i < B; i += 256) {
         a += loss_row[i];
@@ -121,7 +132,8 @@ __global__ void k_loss_final(const float* __restrict__ loss_row, const float* __
 int launch_loss_final(Ctx* c, const float* loss_row, const float* kl_row, int B, float inv_Bg,
                       float beta, float lam, const float* norms, int n_tensors, float* loss_out,
                       cudaStream_t s) {
-    k_loss_final<<<1, 256, 0, s>>>(loss_row, kl_row, B, inv_Bg, beta, lam, norms, n_tensors, loss_out);
+    B200_CUDA_OK(launch_pdl(k_loss_final, dim3(1), dim3(256), 0, s, loss_row, kl_row, B, inv_Bg, beta, lam, norms, n_tensors,
+                            loss_out));
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -193,7 +205,9 @@ __global__ void __launch_bounds__(256)
 k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
        int64_t n, float neg_step, float b1c, float b2, float b2c, float bc2_sqrt, float eps, float wd,
        float lam, const float* __restrict__ norm_ptr, __half* __restrict__ shadow, int64_t sh_lo, int64_t sh_hi,
-       int64_t z_lo, int64_t z_hi, const int32_t* __restrict__ mark, int32_t mark_step, int row_len) {
+       int64_t z_lo, int64_t z_hi, const int32_t* __restrict__ mark, int32_t mark_step, int row_len,
+       __half* __restrict__ shadow2, int64_t s2_lo, int64_t s2_hi) {
+    pdl_sync();
     float reg = 0.f;
     if (EXTRAS && norm_ptr) {
         float nrm = *norm_ptr;
@@ -238,6 +252,14 @@ k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, floa
             pk.y = *reinterpret_cast<const uint32_t*>(&hi);
             *reinterpret_cast<uint2*>(shadow + (e0 - sh_lo)) = pk;
         }
+        if (shadow2 && e0 >= s2_lo && e0 < s2_hi) {  // fp16 image of the hidden-layer tensors
+            const __half2 lo = __floats2half2_rn(f16_clamp(ww.x), f16_clamp(ww.y));
+            const __half2 hi = __floats2half2_rn(f16_clamp(ww.z), f16_clamp(ww.w));
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(shadow2 + (e0 - s2_lo)) = pk;
+        }
     }
     // tail (n not a multiple of 4)
     for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -259,6 +281,7 @@ k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, floa
         m[i] = mm;
         v[i] = vv;
         if (shadow && i >= sh_lo && i < sh_hi) shadow[i - sh_lo] = __float2half_rn(f16_clamp(ww));
+        if (shadow2 && i >= s2_lo && i < s2_hi) shadow2[i - s2_lo] = __float2half_rn(f16_clamp(ww));
     }
 }
 
@@ -266,6 +289,9 @@ int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float
                 float beta1, float beta2, float bc2_sqrt, float eps, float wd, float lam,
                 const float* norm_ptr, __half* shadow, int64_t sh_lo, int64_t sh_hi, int64_t z_lo, int64_t z_hi,
                 const AdamOpt& opt, cudaStream_t s) {
+    // second image window (hidden-layer tensors): absolute arena positions translated to this launch's base
+    __half* shadow2 = opt.shadow2;
+    const int64_t s2_lo = opt.s2_lo, s2_hi = opt.s2_hi;
     if (n == 0) return 0;
     B200_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(m) & 15) == 0 && (reinterpret_cast<uintptr_t>(v) & 15) == 0,
@@ -281,9 +307,9 @@ int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float
     bool extras = (wd != 0.f) || (lam != 0.f && norm_ptr);
     float b1c = 1.f - beta1, b2c = 1.f - beta2;
 #define ADAM_LAUNCH(EX, FI)                                                                                               \
-    k_adam<EX, FI><<<blocks, threads, 0, s>>>(w, g, m, v, n, -lr_over_bc1, b1c, beta2, b2c, bc2_sqrt, eps, EX ? wd : 0.f, \
-                                              EX ? lam : 0.f, EX ? norm_ptr : nullptr, shadow, sh_lo, sh_hi, z_lo, z_hi,  \
-                                              opt.mark, opt.mark_step, opt.row_len)
+    B200_CUDA_OK(launch_pdl(k_adam<EX, FI>, dim3(blocks), dim3(threads), 0, s, w, g, m, v, n, -lr_over_bc1, b1c, beta2, b2c,   \
+                            bc2_sqrt, eps, EX ? wd : 0.f, EX ? lam : 0.f, EX ? norm_ptr : (const float*)nullptr, shadow,  \
+                            sh_lo, sh_hi, z_lo, z_hi, opt.mark, opt.mark_step, opt.row_len, shadow2, s2_lo, s2_hi))
     if (extras) {
         if (filter == ADAM_ROWS_MARKED) ADAM_LAUNCH(true, ADAM_ROWS_MARKED);
         else if (filter == ADAM_ROWS_UNMARKED) ADAM_LAUNCH(true, ADAM_ROWS_UNMARKED);

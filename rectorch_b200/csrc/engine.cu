@@ -19,6 +19,15 @@ namespace b200 {
 
 static thread_local char g_err[512] = "";
 
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("B200VAE_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
@@ -34,6 +43,21 @@ static int dmalloc(T** p, int64_t n) {
     return 0;
 }
 
+// activation image [rows x ld] fp16: zeros with a column of ones at `col` (bias-gradient column, see ctx.cuh)
+__global__ void k_init_image(__half* __restrict__ p, int64_t rows, int64_t ld, int col) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * ld) p[i] = __float2half_rn((i % ld) == col ? 1.f : 0.f);
+}
+static int alloc_image(__half** p, int64_t rows, int width, int* ld_out) {
+    const int64_t ld = round_up((int64_t)width + 1, 8);
+    *p = nullptr;
+    B200_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), (size_t)(rows * ld) * sizeof(__half)));
+    k_init_image<<<(unsigned)cdiv(rows * ld, 256), 256>>>(*p, rows, ld, width);
+    B200_CUDA_OK(cudaGetLastError());
+    *ld_out = (int)ld;
+    return 0;
+}
+
 static void free_ctx(Ctx* c) {
     auto F = [](void* p) { if (p) cudaFree(p); };
     for (int s = 0; s < 2; ++s) {
@@ -45,7 +69,10 @@ static void free_ctx(Ctx* c) {
     F(c->z); F(c->eps); F(c->gvec); F(c->P); F(c->P16); F(c->hsT); F(c->dbuf[0]); F(c->dbuf[1]);
     F(c->part_max); F(c->part_sum); F(c->splitk); F(c->norms); F(c->norm_partial);
     F(c->d_toff); F(c->d_tlen); F(c->loss_dev); F(c->d_err); F(c->lens_tmp); F(c->lens_tmp2);
-    F(c->h16); if (!c->wd16_external) F(c->wd16); F(c->dw_scale); F(c->d_specs); F(c->spmm_acc); F(c->spmm_ticket);
+    F(c->h16); if (!c->wd16_external) F(c->wd16); F(c->dw_scale); F(c->d_specs);
+    F(c->ws16); F(c->z16); F(c->dbuf16[0]); F(c->dbuf16[1]);
+    for (__half* p : c->act_enc16) F(p);
+    for (__half* p : c->act_dec16) F(p); F(c->spmm_acc); F(c->spmm_ticket);
     for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventDestroy(c->ev[i][j]);
     for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
@@ -101,6 +128,40 @@ static int linear_bwd(Ctx* c, const float* dY, const float* inp, int B, const La
     return 0;
 }
 
+// ---- the same two, on the tensor cores (tc_hidden) ----------------------------------------------------------
+// out = act(A W^T + b): A16 [B x in] (pitch lda16), W16 = fp16 image of W [out x in]; writes fp32 `out` [B x out] and,
+// when out16 != NULL, its fp16 image (pitch ld16) for the next GEMM.            (nets.py:398-404, 413-416)
+static int linear_fwd_tc(Ctx* c, const __half* A16, int64_t lda16, int B, const Layer& L, float* out, __half* out16,
+                         int64_t ld16, cudaStream_t s) {
+    TcEpi e;
+    e.bias = c->w + L.b_off;
+    e.act = L.tanh_act ? 1 : 0;
+    e.C16 = out16;
+    e.ldc16 = ld16;
+    if (!e.act && !out16) e.act = 0;
+    return launch_tc_gemm(c, TC_EPI_STORE, A16, lda16, 0, c->ws16 + (L.w_off - c->ws_lo), L.in, 0, out, L.out, B, L.out, L.in, e, s);
+}
+// dW | db = dY^T [inp | 1]  (one GEMM: the ones column of the activation image yields the bias gradient) and
+// dinp = (dY W) * tanh'(prev_out), fp32 + fp16 image.        (autograd of the same layers, models.py:832)
+static int linear_bwd_tc(Ctx* c, const __half* dY16, const __half* inp16, int64_t ld_inp16, int B, const Layer& L,
+                         float* dinp, __half* dinp16, const float* prev_out, cudaStream_t s) {
+    TcEpi e;
+    e.bias_col = L.in;
+    e.bias_grad = c->g + L.b_off;
+    B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, dY16, c->ld_d16, 1, inp16, ld_inp16, 1, c->g + L.w_off, L.in, L.out, L.in + 1, B,
+                              e, s));
+    if (dinp) {
+        TcEpi e2;
+        e2.mulY = prev_out;
+        e2.ldy = L.in;
+        e2.C16 = dinp16;
+        e2.ldc16 = c->ld_d16;
+        B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, dY16, c->ld_d16, 0, c->ws16 + (L.w_off - c->ws_lo), L.in, 1, dinp, L.in, B,
+                                  L.in, L.out, e2, s));
+    }
+    return 0;
+}
+
 // a data-parallel caller refreshes the fp16 image of W_d on another stream (all-gather of the ranks' shards):
 // whoever reads it next waits for that work first
 static int wait_wd16(Ctx* c, cudaStream_t s) {
@@ -143,24 +204,45 @@ static int forward_hidden(Ctx* c, FwdState* st, int B, bool train, float p, uint
         B200_CHECK(adam_step(c, *fused, c->side, e0.w_off, e0.w_off + (int64_t)e0.in * e0.out, ADAM_ROWS_UNMARKED,
                              c->side_ctas[1]));
     }
+    const bool tch = c->tc_hidden;
+    const size_t n_enc = c->enc.size();
+    // the last encoder output of a VAE is (mu | logvar): it feeds the reparameterisation, not a GEMM
+    auto enc_img = [&](size_t i) -> __half* { return (tch && !(c->cfg.is_vae && i + 1 == n_enc)) ? c->act_enc16[i] : nullptr; };
     B200_CHECK(launch_spmm_gather(c, st->in, c->xt, c->w + e0.w_off, e0.out, c->w + e0.b_off,
-                                  e0.tanh_act ? 1 : 0, c->act_enc[0], s));
-    for (size_t i = 1; i < c->enc.size(); ++i)
-        B200_CHECK(linear_fwd(c, c->act_enc[i - 1], B, c->enc[i], c->act_enc[i], s));
+                                  e0.tanh_act ? 1 : 0, c->act_enc[0], s, enc_img(0), tch ? c->ld_enc16[0] : 0));
+    for (size_t i = 1; i < n_enc; ++i) {
+        if (tch) B200_CHECK(linear_fwd_tc(c, c->act_enc16[i - 1], c->ld_enc16[i - 1], B, c->enc[i], c->act_enc[i], enc_img(i),
+                                          c->ld_enc16[i], s));
+        else     B200_CHECK(linear_fwd(c, c->act_enc[i - 1], B, c->enc[i], c->act_enc[i], s));
+    }
     const float* z;
     const float* z_tanh = nullptr;
+    const __half* z16 = nullptr;
+    int64_t ldz16 = 0;
     if (c->cfg.is_vae) {
         B200_CHECK(launch_reparam_kl(c, c->act_enc.back(), B, c->latent, train, eps_tape, seed, step,
-                                     row_offset, st->in.row_ids, c->z, c->eps, c->kl_row, s));
+                                     row_offset, st->in.row_ids, c->z, c->eps, c->kl_row, tch ? c->z16 : nullptr,
+                                     c->ldz16, s));
         z = c->z;
+        z16 = c->z16;
+        ldz16 = c->ldz16;
     } else {
         z = c->act_enc.back();
         z_tanh = z;
+        if (tch) { z16 = c->act_enc16.back(); ldz16 = c->ld_enc16.back(); }
     }
     const float* h = z;
     const float* h_tanh = z_tanh;
+    const __half* h16 = z16;
+    int64_t ldh16 = ldz16;
     for (size_t i = 0; i + 1 < c->dec.size(); ++i) {
-        B200_CHECK(linear_fwd(c, h, B, c->dec[i], c->act_dec[i], s));
+        if (tch) {
+            B200_CHECK(linear_fwd_tc(c, h16, ldh16, B, c->dec[i], c->act_dec[i], c->act_dec16[i], c->ld_dec16[i], s));
+            h16 = c->act_dec16[i];
+            ldh16 = c->ld_dec16[i];
+        } else {
+            B200_CHECK(linear_fwd(c, h, B, c->dec[i], c->act_dec[i], s));
+        }
         h = c->act_dec[i];
         h_tanh = h;
     }
@@ -181,6 +263,7 @@ k_prep_h16(const float* __restrict__ h, int B, int H, int Bp, const float* __res
            __half* __restrict__ h16, __half* __restrict__ hsT, float* __restrict__ dw_scale) {
     __shared__ float tile[32][33];
     __shared__ float red[8];
+    pdl_sync();
     const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
     const int tid = ty * 32 + tx;
     float R = 1.f;
@@ -234,8 +317,8 @@ static int dec_lse(Ctx* c, const float* h, int B, int H, int Bg, int* n_tiles, b
     if (c->tc_dec) {
         const int Bp = (int)round_up(B, 8);
         dim3 tg((unsigned)cdiv(Bp, 32), (unsigned)cdiv(H + 8, 32));
-        k_prep_h16<<<tg, dim3(32, 8), 0, s>>>(h, B, H, Bp, c->T, 1.0f / (float)Bg, c->h16, for_backward ? c->hsT : nullptr,
-                                              c->dw_scale);
+        B200_CUDA_OK(launch_pdl(k_prep_h16, tg, dim3(32, 8), 0, s, h, B, H, Bp, (const float*)c->T, 1.0f / (float)Bg, c->h16,
+                                for_backward ? c->hsT : (__half*)nullptr, c->dw_scale));
         note(c, "prep_h16", s);
         TcEpi e;
         e.bias = b;
@@ -357,7 +440,8 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         tick(c, 4, 0, s);
         B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->P16, Bp, 1, c->wd16, H, 1, c->splitk, H, B, H, I, e3, s));
         B200_CHECK(launch_splitk_reduce(c, c->splitk, split, e3.split_stride, d0, H, B, H, H, nullptr, 0,
-                                        0.f, st.h_last_tanh, H, rowscale, exp2f(-PROB_LOG2_SCALE), s));
+                                        0.f, st.h_last_tanh, H, rowscale, exp2f(-PROB_LOG2_SCALE), s,
+                                        c->tc_hidden ? c->dbuf16[0] : nullptr, c->ld_d16));
         tick(c, 4, 1, s);
     } else {
         GemmEpi e;
@@ -403,24 +487,36 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
     // invariant: `cur` holds d(loss)/d(pre-activation of the layer below the one being processed)
     float* cur = d0;
     float* nxt = d1;
+    const bool tch = c->tc_hidden;
+    __half* cur16 = c->dbuf16[0];     // fp16 images travel with the fp32 buffers (tc_hidden)
+    __half* nxt16 = c->dbuf16[1];
     const float* z_tanh = c->cfg.is_vae ? nullptr : c->act_enc.back();
     const float* z = c->cfg.is_vae ? c->z : c->act_enc.back();
+    const __half* z16 = c->cfg.is_vae ? c->z16 : (tch ? c->act_enc16.back() : nullptr);
+    const int64_t ldz16 = c->cfg.is_vae ? c->ldz16 : (tch ? c->ld_enc16.back() : 0);
     for (int i = (int)c->dec.size() - 2; i >= 0; --i) {
         const float* inp = (i == 0) ? z : c->act_dec[i - 1];
         const float* prev_tanh = (i == 0) ? z_tanh : c->act_dec[i - 1];
-        B200_CHECK(linear_bwd(c, cur, inp, B, c->dec[i], nxt, prev_tanh, s));
+        if (tch) B200_CHECK(linear_bwd_tc(c, cur16, (i == 0) ? z16 : c->act_dec16[i - 1], (i == 0) ? ldz16 : c->ld_dec16[i - 1], B,
+                                          c->dec[i], nxt, nxt16, prev_tanh, s));
+        else     B200_CHECK(linear_bwd(c, cur, inp, B, c->dec[i], nxt, prev_tanh, s));
         std::swap(cur, nxt);
+        std::swap(cur16, nxt16);
     }
     if (c->cfg.is_vae) {
-        B200_CHECK(launch_dz_to_denc(c, cur, c->act_enc.back(), c->eps, B, c->latent, beta * inv_Bg, true, nxt, s));
+        B200_CHECK(launch_dz_to_denc(c, cur, c->act_enc.back(), c->eps, B, c->latent, beta * inv_Bg, true, nxt,
+                                     tch ? nxt16 : nullptr, c->ld_d16, s));
         std::swap(cur, nxt);
+        std::swap(cur16, nxt16);
     }
     // ---------------- backward: encoder ----------------
     for (int i = (int)c->enc.size() - 1; i >= 1; --i) {
         const float* inp = c->act_enc[i - 1];
         const float* prev_tanh = c->enc[i - 1].tanh_act ? c->act_enc[i - 1] : nullptr;
-        B200_CHECK(linear_bwd(c, cur, inp, B, c->enc[i], nxt, prev_tanh, s));
+        if (tch) B200_CHECK(linear_bwd_tc(c, cur16, c->act_enc16[i - 1], c->ld_enc16[i - 1], B, c->enc[i], nxt, nxt16, prev_tanh, s));
+        else     B200_CHECK(linear_bwd(c, cur, inp, B, c->enc[i], nxt, prev_tanh, s));
         std::swap(cur, nxt);
+        std::swap(cur16, nxt16);
     }
     const Layer& e0 = c->enc[0];
     if (enc0_delta_out) {
@@ -459,6 +555,11 @@ static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo, i
     opt.row_len = E0.out;
     opt.ctas_per_sm = ctas_per_sm;
     opt.threads = (ctas_per_sm < 8) ? c->side_threads : 256;
+    if (c->tc_hidden) {     // window positions are relative to each launch's base pointers
+        opt.shadow2 = c->ws16;
+        opt.s2_lo = c->ws_lo - r_lo;
+        opt.s2_hi = c->ws_hi - r_lo;
+    }
     if (h.wd == 0.f && h.lam == 0.f) {
         // kernel indices are relative to the pointers it gets: shift the shadow / re-zero windows by r_lo
         // (the shadow pointer is pre-offset so that shadow[(e - r_lo) - (sh_lo - r_lo)] addresses element e - sh_lo)
@@ -475,6 +576,7 @@ static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo, i
             int64_t o = c->toff[t];
             if (o < r_lo || o >= r_hi) continue;
             const bool is_wd = (o == DL.w_off);
+            if (c->tc_hidden) { opt.s2_lo = c->ws_lo - o; opt.s2_hi = c->ws_hi - o; }
             B200_CHECK(launch_adam(c, c->w + o, c->g + o, c->m + o, c->v + o, c->tlen[t], step_size, h.beta1,
                                    h.beta2, bc2_sqrt, h.eps, h.wd, h.lam, h.lam != 0.f ? c->norms + t : nullptr,
                                    is_wd ? shadow : nullptr, 0, is_wd ? c->tlen[t] : 0,
@@ -669,6 +771,14 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     const int H = c->dec.back().in;
     const int64_t Bp = round_up(Bm, 8);
     c->tc_dec = c->use_tc && tc_supported((int)Bm, (int)I, H, H, H) && (I >= 1024);
+    // hidden layers on the tensor cores: every layer between the two item-sized ones needs 16-byte aligned fp16 rows
+    {
+        const char* ev = getenv("B200VAE_TC_HIDDEN");
+        bool ok = c->tc_dec && !(ev && ev[0] == '0') && (c->enc.size() + c->dec.size() > 2);
+        for (size_t i = 1; i < c->enc.size(); ++i) ok = ok && c->enc[i].in % 8 == 0 && c->enc[i].out % 8 == 0;
+        for (size_t i = 0; i + 1 < c->dec.size(); ++i) ok = ok && c->dec[i].in % 8 == 0 && c->dec[i].out % 8 == 0;
+        c->tc_hidden = ok;
+    }
     int rc = 0;
 #define A_(expr) do { if (!rc) rc = (expr); } while (0)
     for (int s = 0; s < 2; ++s) {
@@ -695,6 +805,17 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     A_(dmalloc(&c->spmm_ticket, Bm));
     A_(dmalloc(&c->mark, c->enc_in));
     A_(dmalloc(&c->dbuf[0], Bm * c->max_width)); A_(dmalloc(&c->dbuf[1], Bm * c->max_width));
+    if (c->tc_hidden) {
+        for (auto& L : c->enc) { __half* p = nullptr; int ld = 0; A_(alloc_image(&p, Bm, L.out, &ld)); c->act_enc16.push_back(p); c->ld_enc16.push_back(ld); }
+        for (size_t i = 0; i + 1 < c->dec.size(); ++i) {
+            __half* p = nullptr; int ld = 0;
+            A_(alloc_image(&p, Bm, c->dec[i].out, &ld));
+            c->act_dec16.push_back(p); c->ld_dec16.push_back(ld);
+        }
+        A_(alloc_image(&c->z16, Bm, c->latent, &c->ldz16));
+        c->ld_d16 = (int)round_up(c->max_width, 8);
+        A_(dmalloc(&c->dbuf16[0], Bm * c->ld_d16)); A_(dmalloc(&c->dbuf16[1], Bm * c->ld_d16));
+    }
     c->n_lse_tiles = (int)std::max<int64_t>(std::max<int64_t>(cdiv(I, 64), tc_lse_parts_max((int)I, c->num_sms)), 1);
     A_(dmalloc(&c->part_max, (int64_t)c->n_lse_tiles * Bm)); A_(dmalloc(&c->part_sum, (int64_t)c->n_lse_tiles * Bm));
     c->splitk_elems = c->tc_dec ? (int64_t)64 * Bm * H : 1;
@@ -738,6 +859,20 @@ int b200vae_bind_params(b200vae_ctx* ctx, float* w, float* g, float* m, float* v
         B200_REQUIRE(L.w_off % 4 == 0 && L.b_off % 4 == 0, B200VAE_EINVAL, "layer %zu offsets must be multiples of 4 floats", l);
         c->toff.push_back(L.w_off); c->tlen.push_back(wl);
         c->toff.push_back(L.b_off); c->tlen.push_back(L.out);
+    }
+    if (c->tc_hidden) {
+        // the hidden-layer tensors lie between encoder layer 0 and the decoder output layer in the arena
+        const Layer& first = c->enc.size() > 1 ? c->enc[1] : c->dec[0];
+        c->ws_lo = first.w_off;
+        c->ws_hi = c->dec.back().w_off;
+        for (size_t l = 1; l + 1 < nl; ++l) {
+            const Layer& L = (l < c->enc.size()) ? c->enc[l] : c->dec[l - c->enc.size()];
+            B200_REQUIRE(L.w_off >= c->ws_lo && L.b_off + L.out <= c->ws_hi && L.w_off % 8 == 0, B200VAE_EINVAL,
+                         "layer %zu lies outside the hidden-layer range of the arena", l);
+        }
+        if (c->ws16) cudaFree(c->ws16);
+        c->ws16 = nullptr;
+        B200_CHECK(dmalloc(&c->ws16, c->ws_hi - c->ws_lo));
     }
     B200_CUDA_OK(cudaMemcpy(c->d_toff, c->toff.data(), c->toff.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
     B200_CUDA_OK(cudaMemcpy(c->d_tlen, c->tlen.data(), c->tlen.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
@@ -879,6 +1014,9 @@ int b200vae_sync_weights(b200vae_ctx* ctx, void* stream) {
     B200_REQUIRE(c && c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
     if (!c->tc_dec) return 0;
     const Layer& DL = c->dec.back();
+    if (c->tc_hidden)
+        B200_CHECK(launch_to_f16(c, c->w + c->ws_lo, c->ws16, 1, (int)(c->ws_hi - c->ws_lo), c->ws_hi - c->ws_lo,
+                                 (cudaStream_t)stream));
     return launch_to_f16(c, c->w + DL.w_off, c->wd16, DL.out, DL.in, DL.in, (cudaStream_t)stream);
 }
 

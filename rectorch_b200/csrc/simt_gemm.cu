@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(128 * V_KSPLIT)
 k_simt_gemm_v(const float* __restrict__ A, int64_t a_ld, const float* __restrict__ B, int64_t b_ld,
               float* __restrict__ C, int64_t ldc, int M, int N, int K, GemmEpi e) {
     constexpr int VBM = 32, VBN = 64, NST = 3;
+    pdl_sync();
     // A: [m][k] if K is contiguous (a_ld = row pitch of m) else [k][m] (a_ld = row pitch of k); same for B with n
     extern __shared__ __align__(16) uint8_t vsmem_raw[];
     const int grp = threadIdx.x >> 7;                 // K-split group
@@ -345,7 +346,8 @@ static int launch_v(dim3 grid, const float* A, int64_t a_ld, const float* B, int
         B200_CUDA_OK(cudaFuncSetAttribute(k_simt_gemm_v<A_KFAST, B_KFAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr = true;
     }
-    k_simt_gemm_v<A_KFAST, B_KFAST><<<grid, 128 * V_KSPLIT, smem, s>>>(A, a_ld, B, b_ld, C, ldc, M, N, K, e);
+    B200_CUDA_OK(launch_pdl(k_simt_gemm_v<A_KFAST, B_KFAST>, grid, dim3(128 * V_KSPLIT), smem, s, A, a_ld, B, b_ld, C, ldc, M, N,
+                            K, e));
     return 0;
 }
 
@@ -401,6 +403,7 @@ int launch_simt_gemm(Ctx* c, int mode, const float* A, int64_t a_rs, int64_t a_c
 __global__ void __launch_bounds__(1024)
 k_colsum(const float* __restrict__ X, int64_t ldx, int M, int N, float* __restrict__ out) {
     __shared__ float sh[32][33];
+    pdl_sync();
     const int n = blockIdx.x * 32 + threadIdx.x;
     float acc = 0.f;
     if (n < N)
@@ -416,7 +419,7 @@ k_colsum(const float* __restrict__ X, int64_t ldx, int M, int N, float* __restri
 
 int launch_colsum(Ctx* c, const float* X, int64_t ldx, int M, int N, float* out, cudaStream_t s) {
     if (N == 0) return 0;
-    k_colsum<<<(int)cdiv(N, 32), dim3(32, 32), 0, s>>>(X, ldx, M, N, out);
+    B200_CUDA_OK(launch_pdl(k_colsum, dim3((unsigned)cdiv(N, 32)), dim3(32, 32), 0, s, X, ldx, M, N, out));
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -23,6 +23,7 @@ __global__ void k_batch_scan(const int64_t* __restrict__ indptr, const int32_t* 
     __shared__ int32_t sg[1024];
     __shared__ int64_t carry;
     __shared__ int32_t carry_s;
+    pdl_sync();
     if (threadIdx.x == 0) { carry = 0; carry_s = 0; }
     __syncthreads();
     for (int base = 0; base < B; base += 1024) {
@@ -61,7 +62,7 @@ __global__ void k_batch_scan(const int64_t* __restrict__ indptr, const int32_t* 
 
 int launch_batch_scan(Ctx* c, const int64_t* indptr, const int32_t* row_ids, int B, int64_t cap,
                       int64_t* bp, int32_t* sp, cudaStream_t s) {
-    k_batch_scan<<<1, 1024, 0, s>>>(indptr, row_ids, B, cap, bp, sp, c->d_err);
+    B200_CUDA_OK(launch_pdl(k_batch_scan, dim3(1), dim3(1024), 0, s, indptr, row_ids, B, cap, bp, sp, c->d_err));
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -110,6 +111,7 @@ __global__ void k_batch_prep(BatchView v, float p, uint64_t seed, uint64_t step,
                              const uint8_t* __restrict__ keep_tape, int train, int64_t cap,
                              float* __restrict__ xt, float* __restrict__ row_sum_out,
                              int32_t* __restrict__ mark, int32_t mark_step, int n_items) {
+    pdl_sync();
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= v.B) return;
@@ -165,15 +167,16 @@ int launch_batch_prep(Ctx* c, const BatchView& in, float p, uint64_t seed, uint6
     if (in.B == 0) return 0;
     int threads = 256;
     int blocks = (int)cdiv((int64_t)in.B * 32, threads);
-    k_batch_prep<<<blocks, threads, 0, s>>>(in, p, seed, step, row_offset, keep_tape, train ? 1 : 0,
-                                            c->cfg.max_batch_nnz, xt, row_sum_out, mark, mark_step,
-                                            c->n_items > 0 ? c->n_items : INT32_MAX);
+    B200_CUDA_OK(launch_pdl(k_batch_prep, dim3(blocks), dim3(threads), 0, s, in, p, seed, step, row_offset, keep_tape,
+                            train ? 1 : 0, c->cfg.max_batch_nnz, xt, row_sum_out, mark, mark_step,
+                            c->n_items > 0 ? c->n_items : INT32_MAX));
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 __global__ void k_row_sums(BatchView v, float* __restrict__ out) {
+    pdl_sync();
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= v.B) return;
@@ -188,7 +191,7 @@ __global__ void k_row_sums(BatchView v, float* __restrict__ out) {
 int launch_row_sums(Ctx* c, const BatchView& v, float* out, cudaStream_t s) {
     if (v.B == 0) return 0;
     int threads = 256;
-    k_row_sums<<<(int)cdiv((int64_t)v.B * 32, threads), threads, 0, s>>>(v, out);
+    B200_CUDA_OK(launch_pdl(k_row_sums, dim3((unsigned)cdiv((int64_t)v.B * 32, threads)), dim3(threads), 0, s, v, out));
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -218,7 +221,8 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 k_spmm_gather(BatchView v, const float* __restrict__ vals, const float* __restrict__ Wt, int H,
               const float* __restrict__ bias, int act, float* __restrict__ out, float* __restrict__ acc_ws,
-              int* __restrict__ ticket) {
+              int* __restrict__ ticket, __half* __restrict__ out16, int64_t ld16) {
+    pdl_sync();
     if ((int)blockIdx.x >= v.sp[v.B]) return;
     const int r = find_row(v.sp, v.B, blockIdx.x);
     const int seg = blockIdx.x - v.sp[r];
@@ -273,6 +277,7 @@ k_spmm_gather(BatchView v, const float* __restrict__ vals, const float* __restri
                 float y = acc[i] + (bias ? bias[h0 + i] : 0.f);
                 if (act) y = tanhf(y);
                 out[(int64_t)r * H + h0 + i] = y;
+                if (out16) out16[(int64_t)r * ld16 + h0 + i] = __float2half_rn(f16_clamp(y));
             }
         } else {
 #pragma unroll
@@ -290,6 +295,7 @@ k_spmm_gather(BatchView v, const float* __restrict__ vals, const float* __restri
                 float y = __ldcg(acc_ws + (int64_t)r * H + h) + (bias ? bias[h] : 0.f);
                 if (act) y = tanhf(y);
                 out[(int64_t)r * H + h] = y;
+                if (out16) out16[(int64_t)r * ld16 + h] = __float2half_rn(f16_clamp(y));
                 acc_ws[(int64_t)r * H + h] = 0.f;
             }
             if (threadIdx.x == 0) ticket[r] = 0;
@@ -304,16 +310,18 @@ static int spmm_grid(Ctx* c, const BatchView& v) {
 }
 
 int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const float* Wt, int H,
-                       const float* bias, int act, float* out, cudaStream_t s) {
+                       const float* bias, int act, float* out, cudaStream_t s, __half* out16, int64_t ld16) {
     if (v.B == 0) return 0;
     bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(Wt) & 15) == 0);
     const int grid = spmm_grid(c, v);
     if (vec) {
         int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));
-        k_spmm_gather<4><<<grid, threads, 0, s>>>(v, vals, Wt, H, bias, act, out, c->spmm_acc, c->spmm_ticket);
+        B200_CUDA_OK(launch_pdl(k_spmm_gather<4>, dim3(grid), dim3(threads), 0, s, v, vals, Wt, H, bias, act, out, c->spmm_acc,
+                                c->spmm_ticket, out16, ld16));
     } else {
         int threads = (int)std::min<int64_t>(256, round_up(H, 32));
-        k_spmm_gather<1><<<grid, threads, 0, s>>>(v, vals, Wt, H, bias, act, out, c->spmm_acc, c->spmm_ticket);
+        B200_CUDA_OK(launch_pdl(k_spmm_gather<1>, dim3(grid), dim3(threads), 0, s, v, vals, Wt, H, bias, act, out, c->spmm_acc,
+                                c->spmm_ticket, out16, ld16));
     }
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
@@ -328,6 +336,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 k_spmm_scatter(BatchView v, const float* __restrict__ vals, float scale, const float* __restrict__ dY,
                int H, float* __restrict__ dWt, float* __restrict__ db) {
+    pdl_sync();
     if ((int)blockIdx.x >= v.sp[v.B]) return;
     const int r = find_row(v.sp, v.B, blockIdx.x);
     const int seg = blockIdx.x - v.sp[r];
@@ -375,10 +384,10 @@ int launch_spmm_scatter_bias(Ctx* c, const BatchView& v, const float* vals, floa
     const int grid = spmm_grid(c, v);
     if (vec) {
         int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));
-        k_spmm_scatter<4><<<grid, threads, 0, s>>>(v, vals, scale, dY, H, dWt, db);
+        B200_CUDA_OK(launch_pdl(k_spmm_scatter<4>, dim3(grid), dim3(threads), 0, s, v, vals, scale, dY, H, dWt, db));
     } else {
         int threads = (int)std::min<int64_t>(256, round_up(H, 32));
-        k_spmm_scatter<1><<<grid, threads, 0, s>>>(v, vals, scale, dY, H, dWt, db);
+        B200_CUDA_OK(launch_pdl(k_spmm_scatter<1>, dim3(grid), dim3(threads), 0, s, v, vals, scale, dY, H, dWt, db));
     }
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
@@ -576,6 +585,7 @@ __global__ void k_row_loss(BatchView tgt, const float* __restrict__ h, const flo
                            const float* __restrict__ psum, int n_tiles, float* __restrict__ lse,
                            const float* __restrict__ T, float inv_Bg, float* __restrict__ loss_row,
                            float* __restrict__ rowscale) {
+    pdl_sync();
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (warp >= tgt.B) return;
@@ -629,6 +639,7 @@ k_target_fixup(BatchView tgt, __half* __restrict__ PT, int64_t ldp, const float*
                const __half* __restrict__ W16, int64_t ldw, const float* __restrict__ bias, int H,
                float log2_scale, float* __restrict__ loss_row, int* __restrict__ err) {
     __shared__ float sh[4];
+    pdl_sync();
     const int u = blockIdx.x;
     const float Tu = T[u];
     const float sub = (Tu != 0.f) ? exp2f(log2_scale) / Tu : 0.f;
@@ -668,8 +679,8 @@ int launch_target_fixup(Ctx* c, const BatchView& tgt, __half* PT, int64_t ldp, c
                         const __half* h16, int64_t ldh, const __half* W16, int64_t ldw, const float* bias, int H,
                         float* loss_row, cudaStream_t s) {
     if (tgt.B == 0) return 0;
-    k_target_fixup<<<tgt.B, 128, 0, s>>>(tgt, PT, ldp, T, lse, h16, ldh, W16, ldw, bias, H, PROB_LOG2_SCALE, loss_row,
-                                         c->d_err);
+    B200_CUDA_OK(launch_pdl(k_target_fixup, dim3(tgt.B), dim3(128), 0, s, tgt, PT, ldp, T, lse, h16, ldh, W16, ldw, bias, H,
+                            PROB_LOG2_SCALE, loss_row, c->d_err));
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -680,8 +691,8 @@ int launch_row_loss(Ctx* c, const BatchView& tgt, const float* h, const float* g
                     const float* T, float inv_Bg, float* loss_row, float* rowscale, cudaStream_t s) {
     if (tgt.B == 0) return 0;
     int threads = 256;
-    k_row_loss<<<(int)cdiv((int64_t)tgt.B * 32, threads), threads, 0, s>>>(tgt, h, gvec, H, bias, pmax, psum, n_tiles,
-                                                                            lse, T, inv_Bg, loss_row, rowscale);
+    B200_CUDA_OK(launch_pdl(k_row_loss, dim3((unsigned)cdiv((int64_t)tgt.B * 32, threads)), dim3(threads), 0, s, tgt, h, gvec,
+                            H, bias, pmax, psum, n_tiles, lse, T, inv_Bg, loss_row, rowscale));
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;

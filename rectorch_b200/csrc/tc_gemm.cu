@@ -205,6 +205,11 @@ struct TcArgs {
     float* bias_grad;
     float out_scale;        // STORE: D * out_scale (* *out_scale_ptr): exact power-of-two un-scaling of fp16 operands
     const float* out_scale_ptr;
+    int act;                // STORE: tanh after the bias
+    const float* mulY;      // STORE: out *= 1 - Y^2
+    int64_t ldy;
+    __half* C16;            // STORE: fp16 image of the output
+    int64_t ldc16;
     float prob_log2_scale;  // PROB: S of P~ = softmax * 2^S
     int vec_ok;             // C rows are 16 B aligned
     int dbg;                // B200VAE_TC_DBG bit mask (probes, garbage results): 1 = no operand loads,
@@ -346,7 +351,26 @@ __device__ __forceinline__ void epi_chunk(const TcArgs& a, const float* v, const
         if (m < a.M) {
             float* crow = reinterpret_cast<float*>(a.C) + (int64_t)sp * a.split_stride + (int64_t)m * a.ldc;
             const int col0 = n0 + c0;
-            if (a.vec_ok && nc == 32 && col0 + 32 <= a.n_store) {   // nc < 32: the N tile ends inside this chunk
+            if (a.act || a.mulY || a.C16) {
+                // hidden-layer epilogue: bias, tanh / tanh', fp32 result + fp16 image for the next GEMM
+                const float* yrow = a.mulY ? a.mulY + (int64_t)m * a.ldy : nullptr;
+                __half* hrow = a.C16 ? a.C16 + (int64_t)m * a.ldc16 : nullptr;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int col = col0 + i;
+                    if (i < nc) {
+                        if (col < a.n_store) {
+                            float y = fmaf(v[i], oscale, bias_s[c0 + i]);
+                            if (a.act) y = tanhf(y);
+                            if (yrow) { const float t = yrow[col]; y *= (1.f - t * t); }
+                            crow[col] = y;
+                            if (hrow) hrow[col] = __float2half_rn(f16_clamp(y));
+                        } else if (col == a.bias_col) {
+                            a.bias_grad[m] = v[i] * oscale;
+                        }
+                    }
+                }
+            } else if (a.vec_ok && nc == 32 && col0 + 32 <= a.n_store) {   // nc < 32: the N tile ends inside this chunk
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + i);
@@ -411,6 +435,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     cluster_sync_all();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // everything above (barriers, tensor-map prefetch, TMEM allocation) overlapped the tail of the previous kernel;
+    // from here on global memory written by it is read
+    pdl_sync();
 
     const int bn_cta = a.BN >> 1;                                    // B rows staged by this CTA
     const int pair = (int)(blockIdx.x >> 1);
@@ -688,6 +715,11 @@ static TcPlan tc_plan(int mode, int M, int N, int K, int a_mn, int b_mn, int spl
     const bool items = (mode == TC_EPI_LSE || mode == TC_EPI_PROB || N >= 1024);
     if (want_res) {
         p.BN = pick_bn_items(N, cdiv(p.tiles_m, groups), ppm);
+    } else if (N < 1024 && p.split_k == 1) {
+        // hidden-layer sized outputs: these GEMMs are latency bound, so spread them over the SM pairs with narrow
+        // N tiles instead of filling 256 columns on a handful of pairs
+        const int64_t want_tiles_n = std::max<int64_t>(1, npairs / std::max(1, p.tiles_m));
+        p.BN = (int)std::min<int64_t>(256, std::max<int64_t>(32, round_up(cdiv(N, want_tiles_n), 16)));
     } else {
         p.BN = items && !b_mn ? pick_bn_items(N, p.tiles_m, npairs) : pick_bn(N);
     }
@@ -742,13 +774,15 @@ static int launch_inst(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcA
     cfg.blockDim = dim3(tc_threads(MODE));
     cfg.dynamicSmemBytes = TC_SMEM;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     B200_CUDA_OK(cudaLaunchKernelEx(&cfg, k_tc_gemm<MODE, A_MN, B_MN>, tmA, tmB, args));
     return 0;
 }
@@ -771,6 +805,9 @@ int launch_tc_gemm(Ctx* c, int mode, const void* A, int64_t lda, int a_mn, const
     a.transpose_out = e.transpose_out;
     a.n_store = (e.bias_col >= 0) ? e.bias_col : (e.transpose_out ? M : N);
     a.out_scale = e.out_scale; a.out_scale_ptr = e.out_scale_ptr; a.prob_log2_scale = e.prob_log2_scale;
+    a.act = e.act; a.mulY = e.mulY; a.ldy = e.ldy; a.C16 = e.C16; a.ldc16 = e.ldc16;
+    B200_REQUIRE(!(a.act || a.mulY || a.C16) || (mode == TC_EPI_STORE && !e.transpose_out && e.split_k <= 1), B200VAE_EINVAL,
+                 "tc_gemm: the activation epilogue needs a plain STORE output");
     a.vec_ok = (mode == TC_EPI_STORE && C && ((uintptr_t)C & 15) == 0 && (ldc % 4 == 0) && (e.split_stride % 4 == 0)) ? 1 : 0;
     a.resident = p.resident; a.n_stages = p.n_stages; a.stage_bytes = p.stage_bytes; a.ring_off = p.ring_off;
     a.b_bytes = p.b_bytes; a.pairs_per_m = p.pairs_per_m; a.n_groups = p.n_groups;
@@ -809,7 +846,8 @@ int launch_tc_gemm(Ctx* c, int mode, const void* A, int64_t lda, int a_mn, const
 __global__ void k_splitk_reduce(const float* __restrict__ parts, int n_split, int64_t split_stride, float* __restrict__ out,
                                 int64_t ld_out, int M, int N, int64_t ld_part, const float* __restrict__ addend, int64_t ld_add,
                                 float addend_scale, const float* __restrict__ mulY, int64_t ldy,
-                                const float* __restrict__ rowscale, float scale) {
+                                const float* __restrict__ rowscale, float scale, __half* __restrict__ out16, int64_t ld16) {
+    pdl_sync();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)M * N) return;
     int m = (int)(i / N), n = (int)(i % N);
@@ -823,15 +861,16 @@ __global__ void k_splitk_reduce(const float* __restrict__ parts, int n_split, in
         acc *= (1.f - t * t);
     }
     out[(int64_t)m * ld_out + n] = acc;
+    if (out16) out16[(int64_t)m * ld16 + n] = __float2half_rn(f16_clamp(acc));
 }
 
 int launch_splitk_reduce(Ctx* c, const float* parts, int n_split, int64_t split_stride, float* out, int64_t ld_out, int M,
                          int N, int64_t ld_part, const float* addend, int64_t ld_add, float addend_scale, const float* mulY,
-                         int64_t ldy, const float* rowscale, float scale, cudaStream_t s) {
+                         int64_t ldy, const float* rowscale, float scale, cudaStream_t s, __half* out16, int64_t ld16) {
     int64_t n = (int64_t)M * N;
     if (n == 0) return 0;
-    k_splitk_reduce<<<(int)cdiv(n, 256), 256, 0, s>>>(parts, n_split, split_stride, out, ld_out, M, N, ld_part, addend, ld_add,
-                                                       addend_scale, mulY, ldy, rowscale, scale);
+    B200_CUDA_OK(launch_pdl(k_splitk_reduce, dim3((unsigned)cdiv(n, 256)), dim3(256), 0, s, parts, n_split, split_stride, out,
+                            ld_out, M, N, ld_part, addend, ld_add, addend_scale, mulY, ldy, rowscale, scale, out16, ld16));
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
