@@ -262,6 +262,11 @@ int  b200vae_gemm_f16(b200vae_ctx* ctx, const void* A, int64_t lda, int a_mn_maj
 int  b200vae_dec_fwd_lse(b200vae_ctx* ctx, const void* h16, const void* W16, const float* bias,
                          int32_t B, int32_t n_items, int32_t H, float* lse, void* stream);
 
+/* Measurement aid (scripts/launch_probe.py): launches an EMPTY kernel with the given grid, block size, dynamic shared
+ * memory and cluster size -- the launch configuration of the tcgen05 kernels -- so that their fixed launch cost can
+ * be separated from their work. */
+int  b200vae_probe_launch(int grid, int threads, int smem_bytes, int cluster, void* stream);
+
 /* Introspection for bench.py: kernels launched by this context since the last reset. */
 int64_t b200vae_launch_count(b200vae_ctx* ctx, int reset);
 

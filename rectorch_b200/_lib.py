@@ -82,6 +82,7 @@ _SIGS = {
                                   c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p]),
     "b200vae_dec_fwd_lse": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                     c_void_p, c_void_p]),
+    "b200vae_probe_launch": (c_int, [c_int, c_int, c_int, c_int, c_void_p]),
     "b200vae_launch_count": (c_int64, [c_void_p, c_int]),
     "b200vae_set_timing": (c_int, [c_void_p, c_int]),
     "b200vae_kernel_ms": (c_float, [c_void_p, c_int]),

@@ -1232,6 +1232,34 @@ int b200vae_dec_fwd_lse(b200vae_ctx* ctx, const void* h16, const void* W16, cons
     return 0;
 }
 
+// ---- launch-cost probe (scripts/launch_probe.py): an empty kernel with a given grid / block / dynamic shared memory /
+// cluster size, so that the fixed cost of the tcgen05 kernel's launch configuration can be measured in isolation
+__global__ void k_probe_empty(int* sink) {
+    extern __shared__ uint8_t probe_smem[];
+    if (sink && threadIdx.x == 0 && blockIdx.x == 0xFFFFFFu) sink[0] = probe_smem[0];
+}
+int b200vae_probe_launch(int grid, int threads, int smem_bytes, int cluster, void* stream) {
+    static int max_set = 0;
+    if (smem_bytes > max_set) {
+        B200_CUDA_OK(cudaFuncSetAttribute(k_probe_empty, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        max_set = smem_bytes;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)std::max(1, cluster);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cluster > 1 ? 1 : 0;
+    B200_CUDA_OK(cudaLaunchKernelEx(&cfg, k_probe_empty, (int*)nullptr));
+    return 0;
+}
+
 int64_t b200vae_launch_count(b200vae_ctx* ctx, int reset) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     if (!c) return -1;

@@ -213,7 +213,9 @@ struct TcArgs {
     float prob_log2_scale;  // PROB: S of P~ = softmax * 2^S
     int vec_ok;             // C rows are 16 B aligned
     int dbg;                // B200VAE_TC_DBG bit mask (probes, garbage results): 1 = no operand loads,
-                            // 2 = epilogue only waits and releases the accumulator, 4 = no MMAs are issued
+                            // 2 = epilogue only waits and releases the accumulator, 4 = no MMAs are issued,
+                            // 8 = no tiles at all (launch + prologue + teardown only), 16 = with 8: also no TMEM
+                            // allocation and no cluster barriers
     // schedule
     int resident;           // the A slice stays in shared memory for all N tiles of a pass
     int n_stages;           // ring depth
@@ -417,6 +419,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_stages = a.n_stages;
 
+    if (a.dbg & 16) return;
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -440,7 +443,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     pdl_sync();
 
     const int bn_cta = a.BN >> 1;                                    // B rows staged by this CTA
-    const int pair = (int)(blockIdx.x >> 1);
+    const int pair = (a.dbg & 8) ? (1 << 29) : (int)(blockIdx.x >> 1);     // probe: a pair index that owns no tile
     const int npairs = (int)(gridDim.x >> 1);
     const uint32_t ring_base = smem_base + (uint32_t)a.ring_off;
     const bool resident = a.resident != 0;

@@ -230,8 +230,23 @@ class Engine:
         x = x.reshape(x.shape[0], -1).to(device, non_blocking=True).contiguous()
         return x
 
-    def _nnz_cap_dense(self, B):
-        return min(B * self.enc_in, max(B * 4096, 1 << 20))
+    def _nnz_cap_dense(self, *dense):
+        """Non-zero capacity for dense batches: counted on the device (one pass + one host sync per batch -- the
+        dense API is PCIe-bound anyway), so that no dense or real-valued input can overflow the context's batch
+        buffers silently; 25 % headroom keeps the context from being re-created for every slightly larger batch."""
+        need = 1
+        for d in dense:
+            if d is None:
+                continue
+            B, n = d.shape
+            with torch.cuda.device(self.device):
+                lens = torch.empty(B + 1, dtype=torch.int64, device=self.device)
+                indptr = torch.empty(B + 1, dtype=torch.int64, device=self.device)
+                check(_lib.lib().b200vae_dense_to_csr_raw(ptr(d), B, n, ptr(lens), ptr(indptr), None, None, 0, stream_ptr()))
+            need = max(need, int(indptr[-1].item()))
+        if need <= self._cap_nnz:
+            return self._cap_nnz
+        return need + need // 4
 
     def _nnz_cap_rows(self, B):
         cap = 0
@@ -251,7 +266,7 @@ class Engine:
         ``enc0_delta_out`` ([B x H1] device tensor) the encoder-0 gradient is left to :meth:`enc0_grad`."""
         if dense is not None:
             B = dense.shape[0]
-            self._prepare(None, dense, B, self._nnz_cap_dense(B), 0)
+            self._prepare(None, dense, B, self._nnz_cap_dense(dense, dense_target), 0)
             if dense_target is not None:
                 check(_lib.lib().b200vae_dense_to_csr(self._ctx, 1, ptr(dense_target), B, stream_ptr()))
                 use_target = True
@@ -304,7 +319,7 @@ class Engine:
             use_target, rid = True, None
         elif dense is not None:
             B = dense.shape[0]
-            self._prepare(None, dense, B, self._nnz_cap_dense(B), 0)
+            self._prepare(None, dense, B, self._nnz_cap_dense(dense, dense_target), 0)
             if dense_target is not None:
                 check(_lib.lib().b200vae_dense_to_csr(self._ctx, 1, ptr(dense_target), B, stream_ptr()))
                 use_target = True
@@ -328,7 +343,7 @@ class Engine:
             rid = None
         elif dense is not None:
             B = dense.shape[0]
-            self._prepare(None, dense, B, self._nnz_cap_dense(B), 0)
+            self._prepare(None, dense, B, self._nnz_cap_dense(dense), 0)
             rid = None
         else:
             B = rows.numel()

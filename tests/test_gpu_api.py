@@ -240,3 +240,28 @@ def test_cfg5_shapes_functional():
     assert abs(gb.sum().item()) < 1e-3 * gb.abs().sum().item() + 1e-6
     scores = model.predict(rb, True)[0]
     assert scores.shape == (B, n_items) and torch.isinf(scores).sum().item() == int(csr.rows(0, B).nnz)
+
+
+def test_dense_real_valued_input_cannot_overflow():
+    """A fully dense, real-valued batch (net(torch.rand(B, n_items)): every entry non-zero, 64 x 20108 = 1.29 M
+    non-zeros, more than the old fixed capacity) goes through the dense API without overflowing the batch buffers:
+    scores and the training loss match the oracle."""
+    from oracle import multvae_oracle as O
+    torch.manual_seed(5)
+    B, n_items = 64, 20108
+    net = MultiDAE_net([40, n_items], None, 0.0)
+    sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    x = torch.rand(B, n_items) + 0.01
+    model = MultiDAE(net.cuda(), lam=0.0)
+    net.eval()
+    got = net(x.cuda()).cpu()
+    onet = O.Net.from_state_dict(sd0, False, 0.0)
+    ref = O.forward(onet, x, False)["logits"]
+    assert (got - ref).abs().max().item() < 5e-3 * ref.abs().max().item()
+    model._engine.check_overflow()
+    net.train()
+    loss = model.train_batch(x.cuda())
+    ost = O.AdamState(onet, lr=1e-3, weight_decay=1e-3)
+    oloss = O.train_step(onet, ost, x, None, beta=0.0, lam=0.0, drop_scale=None, eps=None)
+    assert abs(loss - oloss) / abs(oloss) < 1e-4
+    model._engine.check_overflow()
