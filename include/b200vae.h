@@ -291,6 +291,23 @@ float b200vae_kernel_ms(b200vae_ctx* ctx, int which);
 int  b200vae_build_cond_batch(b200vae_ctx* ctx, const int32_t* ex_rows, const int32_t* ex_conds, int32_t B,
                               const uint64_t* item_cond_mask, void* stream);
 
+/* ---- EASE closed form (EASE.train / EASE.predict, models.py:1006-1026, 1051-1054) ----------
+ * All pointers are DEVICE pointers; the three calls synchronise `stream` before returning.
+ *
+ * G32[n_items x n_items] = X^T X for the CSR matrix X (values NULL = all ones): tcgen05 GEMMs over dense fp16 images
+ * of user chunks (exact for 0/1 and small-integer ratings; counts are exact in fp32 below 2^24).
+ * Replaces: X = train_data.toarray(); G = np.dot(X.T, X)                                   (models.py:1008-1010) */
+int  b200vae_ease_gram(const int64_t* indptr, const int32_t* indices, const float* values, int64_t n_users,
+                       int32_t n_items, float* G32, void* stream);
+/* Bm[n_items x n_items] (fp32) = P / (-diag P) with diag(Bm) = 0 and P = (G + lam I)^-1, inverted in fp64 by a blocked
+ * in-place Gauss-Jordan elimination (the matrix is symmetric positive definite: no pivoting).
+ * Replaces: G[diag] += lam; P = np.linalg.inv(G); B = P / (-np.diag(P)); B[diag] = 0       (models.py:1011-1017) */
+int  b200vae_ease_solve(const float* G32, int32_t n_items, double lam, float* Bm, void* stream);
+/* out[r, :] = X[row_ids[r], :] * Bm for r < n_rows (row_ids NULL = rows 0..n_rows-1; n_rows <= 65535): the rows of
+ * the reference's score matrix np.dot(X, B), computed on demand instead of stored    (models.py:1019, 1051) */
+int  b200vae_ease_scores(const int64_t* indptr, const int32_t* indices, const float* values, const int32_t* row_ids,
+                         int32_t n_rows, int32_t n_items, const float* Bm, float* out, void* stream);
+
 /* ---- data ingest (host side): pre-processed rating files -> canonical CSR ------------------------------
  * Replaces pd.read_csv + scipy.sparse.csr_matrix((values, (rows, cols))) in DataReader._load_train_data /
  * _load_train_test_data (data.py:363-409).  The file has a header line "uid,iid[,<value>,...]" and one

@@ -88,6 +88,9 @@ _SIGS = {
     "b200vae_kernel_ms": (c_float, [c_void_p, c_int]),
     "b200vae_timing_report": (c_int, [c_void_p, c_char_p, c_int]),
     "b200vae_build_cond_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "b200vae_ease_gram": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "b200vae_ease_solve": (c_int, [c_void_p, c_int32, ctypes.c_double, c_void_p, c_void_p]),
+    "b200vae_ease_scores": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "b200vae_csv_open": (c_int, [POINTER(c_void_p), c_char_p, ctypes.c_char, c_int]),
     "b200vae_csv_info": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int32), POINTER(c_int64),
                                  POINTER(c_int64), POINTER(c_int64)]),

@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200vae.so")
-SOURCES = ["engine.cu", "sparse.cu", "simt_gemm.cu", "elementwise.cu", "topk.cu", "tc_gemm.cu", "ingest.cu"]
+SOURCES = ["engine.cu", "sparse.cu", "simt_gemm.cu", "elementwise.cu", "topk.cu", "tc_gemm.cu", "ingest.cu", "ease.cu"]
 HEADERS = ["common.cuh", "ctx.cuh", os.path.join("..", "..", "include", "b200vae.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]

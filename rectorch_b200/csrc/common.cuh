@@ -183,6 +183,7 @@ struct TcEpi {
     int64_t ldy = 0;
     __half* C16 = nullptr;             // fp16 image of the output for the next tensor-core GEMM (pitch ldc16)
     int64_t ldc16 = 0;
+    int accumulate = 0;                // TC_EPI_STORE plain output: C += product (EASE Gram matrix over user chunks)
 };
 // pitches (lda, ldb) in halfs, multiples of 8; A / B are __half arrays; C is float (STORE) or __half (PROB)
 bool tc_supported(int M, int N, int K, int64_t lda, int64_t ldb);

@@ -1072,7 +1072,9 @@ int b200vae_train_step(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int 
 }
 
 // ---- context-free helpers used by rectorch_b200.metrics / models.loss_function ---------------
-static Ctx* null_ctx() {
+}  // extern "C"
+namespace b200 {
+Ctx* null_ctx() {
     static Ctx nc;
     static bool init = false;
     if (!init) {
@@ -1087,6 +1089,8 @@ static Ctx* null_ctx() {
     }
     return &nc;
 }
+}  // namespace b200
+extern "C" {
 
 int b200vae_topk_metrics_csr(const float* scores, int32_t B, int32_t n_items, const int64_t* gt_indptr,
                              const int32_t* gt_indices, const float* gt_values, const int32_t* kinds_dev,

@@ -210,6 +210,7 @@ struct TcArgs {
     int64_t ldy;
     __half* C16;            // STORE: fp16 image of the output
     int64_t ldc16;
+    int accumulate;         // STORE: C += product
     float prob_log2_scale;  // PROB: S of P~ = softmax * 2^S
     int vec_ok;             // C rows are 16 B aligned
     int dbg;                // B200VAE_TC_DBG bit mask (probes, garbage results): 1 = no operand loads,
@@ -375,7 +376,11 @@ __device__ __forceinline__ void epi_chunk(const TcArgs& a, const float* v, const
             } else if (a.vec_ok && nc == 32 && col0 + 32 <= a.n_store) {   // nc < 32: the N tile ends inside this chunk
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + i);
+                    float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + i);
+                    if (a.accumulate) {
+                        const float4 o4 = *reinterpret_cast<const float4*>(crow + col0 + i);
+                        b4.x += o4.x; b4.y += o4.y; b4.z += o4.z; b4.w += o4.w;
+                    }
                     *reinterpret_cast<float4*>(crow + col0 + i) =
                         make_float4(fmaf(v[i], oscale, b4.x), fmaf(v[i + 1], oscale, b4.y), fmaf(v[i + 2], oscale, b4.z),
                                     fmaf(v[i + 3], oscale, b4.w));
@@ -385,7 +390,7 @@ __device__ __forceinline__ void epi_chunk(const TcArgs& a, const float* v, const
                 for (int i = 0; i < 32; ++i) {
                     const int col = col0 + i;
                     if (i < nc) {
-                        if (col < a.n_store) crow[col] = fmaf(v[i], oscale, bias_s[c0 + i]);
+                        if (col < a.n_store) crow[col] = fmaf(v[i], oscale, bias_s[c0 + i]) + (a.accumulate ? crow[col] : 0.f);
                         else if (col == a.bias_col) a.bias_grad[m] = v[i] * oscale;
                     }
                 }
@@ -809,6 +814,9 @@ int launch_tc_gemm(Ctx* c, int mode, const void* A, int64_t lda, int a_mn, const
     a.n_store = (e.bias_col >= 0) ? e.bias_col : (e.transpose_out ? M : N);
     a.out_scale = e.out_scale; a.out_scale_ptr = e.out_scale_ptr; a.prob_log2_scale = e.prob_log2_scale;
     a.act = e.act; a.mulY = e.mulY; a.ldy = e.ldy; a.C16 = e.C16; a.ldc16 = e.ldc16;
+    a.accumulate = e.accumulate;
+    B200_REQUIRE(!a.accumulate || (mode == TC_EPI_STORE && !e.transpose_out && e.split_k <= 1 && !(a.act || a.mulY || a.C16)),
+                 B200VAE_EINVAL, "tc_gemm: accumulate needs a plain STORE output");
     B200_REQUIRE(!(a.act || a.mulY || a.C16) || (mode == TC_EPI_STORE && !e.transpose_out && e.split_k <= 1), B200VAE_EINVAL,
                  "tc_gemm: the activation epilogue needs a plain STORE output");
     a.vec_ok = (mode == TC_EPI_STORE && C && ((uintptr_t)C & 15) == 0 && (ldc % 4 == 0) && (e.split_stride % 4 == 0)) ? 1 : 0;

@@ -31,7 +31,7 @@ from .samplers import CondRowBatch, DataSampler, RowBatch
 from . import _lib
 from ._lib import check, ptr, stream_ptr
 
-__all__ = ['RecSysModel', 'TorchNNTrainer', 'AETrainer', 'MultiDAE', 'MultiVAE', 'CMultiVAE']
+__all__ = ['RecSysModel', 'TorchNNTrainer', 'AETrainer', 'MultiDAE', 'MultiVAE', 'CMultiVAE', 'EASE']
 
 logger = logging.getLogger(__name__)
 
@@ -736,3 +736,122 @@ class CMultiVAE(MultiVAE):
 
     def __init__(self, cmvae_net, beta=1., anneal_steps=0, learning_rate=1e-3):
         super(CMultiVAE, self).__init__(cmvae_net, beta=beta, anneal_steps=anneal_steps, learning_rate=learning_rate)
+
+
+class EASE(RecSysModel):
+    r"""Embarrassingly Shallow AutoEncoder (rectorch/models.py:959-1085): the closed form
+    :math:`\hat B = P / (-\operatorname{diag} P)`, :math:`P = (X^\top X + \lambda I)^{-1}`, :math:`\operatorname{diag}(B)=0`.
+
+    Same constructor, attributes (``lam``, ``model``), ``train`` / ``predict`` / ``save_model`` / ``load_model`` and file
+    format as the reference.  What differs is where the work happens: the Gram matrix is a tcgen05 GEMM over the
+    device-resident CSR matrix, the inverse a blocked fp64 Gauss-Jordan elimination on the device, and the item-item
+    matrix ``B`` stays in HBM -- ``predict`` scores the requested users on demand (:math:`S_u = X_u B`) instead of
+    looking them up in a stored ``[n_users x n_items]`` matrix.  ``model`` (that dense score matrix, a numpy array
+    like the reference's) is still available: it is computed from ``B`` the first time it is read.
+    """
+
+    _MAX_MODEL_BYTES = 8 << 30
+
+    def __init__(self, lam=100.):
+        self.lam = lam
+        self._model = None          # dense score matrix (numpy) once materialised / loaded
+        self._B = None              # item-item weights on the device [n_pad x n_pad] fp32
+        self._X = None              # training matrix on the device
+        self._n_items = 0
+
+    # -- reference attribute ----------------------------------------------------------------------------
+    @property
+    def model(self):
+        if self._model is None and self._B is not None:
+            n_users = self._X.shape[0]
+            if n_users * self._n_items * 8 > self._MAX_MODEL_BYTES:
+                raise MemoryError("the dense %d x %d score matrix is too large to materialise; use predict()"
+                                  % (n_users, self._n_items))
+            parts = [self._scores(np.arange(lo, min(lo + 32768, n_users), dtype=np.int32))
+                     for lo in range(0, n_users, 32768)]
+            self._model = np.concatenate(parts, axis=0) if parts else np.zeros((0, self._n_items))
+        return self._model
+
+    @model.setter
+    def model(self, value):
+        self._model = value
+
+    def _scores(self, ids):
+        """float64 numpy [len(ids) x n_items] = X[ids] B, computed on the device."""
+        from .engine import DeviceCSR   # noqa: F401  (self._X is one)
+        dev = self._X.device
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        n_pad = int(self._B.shape[0])
+        out = np.empty((len(ids), self._n_items), dtype=np.float64)
+        with torch.cuda.device(dev):
+            for lo in range(0, len(ids), 32768):
+                rows = torch.from_numpy(ids[lo:lo + 32768]).to(dev)
+                buf = torch.empty((rows.numel(), n_pad), dtype=torch.float32, device=dev)
+                check(_lib.lib().b200vae_ease_scores(ptr(self._X.indptr), ptr(self._X.indices), ptr(self._X.values),
+                                                      ptr(rows), int(rows.numel()), n_pad, ptr(self._B), ptr(buf),
+                                                      stream_ptr()))
+                out[lo:lo + rows.numel()] = buf[:, :self._n_items].double().cpu().numpy()
+        return out
+
+    # -- reference API ------------------------------------------------------------------------------------
+    def train(self, train_data):
+        """``train_data``: the user x item training matrix (scipy CSR, as in the reference)."""
+        from .engine import DeviceCSR
+        if not torch.cuda.is_available():
+            raise RuntimeError("rectorch_b200.models.EASE needs a CUDA (sm_100a) device: there is no CPU path")
+        logger.info("EASE - start tarining (lam=%.4f)", self.lam)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        X = DeviceCSR(train_data, dev)
+        n_users, n_items = X.shape
+        n_pad = max(16, -(-n_items // 8) * 8)      # tensor-core tile granule; padding items are isolated (G = lam I there)
+        self._X, self._n_items, self._model = X, n_items, None
+        with torch.cuda.device(dev):
+            G = torch.empty((n_pad, n_pad), dtype=torch.float32, device=dev)
+            check(_lib.lib().b200vae_ease_gram(ptr(X.indptr), ptr(X.indices), ptr(X.values), n_users, n_pad, ptr(G),
+                                               stream_ptr()))
+            logger.info("EASE - linear kernel computed")
+            B = torch.empty((n_pad, n_pad), dtype=torch.float32, device=dev)
+            check(_lib.lib().b200vae_ease_solve(ptr(G), n_pad, float(self.lam), ptr(B), stream_ptr()))
+        self._B = B
+        logger.info("EASE - training complete")
+
+    def predict(self, ids_te_users, test_tr, remove_train=True):
+        """Scores of the users ``ids_te_users`` (rows of the training matrix); ``remove_train`` sets the scores of
+        ``test_tr``'s non-zeros to -inf (rectorch/models.py:1051-1054).  Returns a 1-tuple with a numpy array."""
+        ids = np.asarray(ids_te_users)
+        if self._B is not None:
+            pred = self._scores(ids)
+        else:
+            pred = np.array(self.model[ids, :])
+        if remove_train:
+            pred[test_tr.nonzero()] = -np.inf
+        return (pred, )
+
+    def save_model(self, filepath):
+        state = {'lambda': self.lam,
+                 'model': self.model
+                }
+        logger.info("Saving EASE model to %s...", filepath)
+        np.save(filepath, state)
+        logger.info("Model saved!")
+
+    def load_model(self, filepath):
+        assert os.path.isfile(filepath), "The model file %s does not exist." % filepath
+        logger.info("Loading EASE model from %s...", filepath)
+        state = np.load(filepath, allow_pickle=True)[()]
+        self.lam = state["lambda"]
+        self._model = state["model"]
+        self._B = None
+        logger.info("Model loaded!")
+        return state
+
+    def __str__(self):
+        s = "EASE(lambda=%.4f" % self.lam
+        if self._model is not None or self._B is not None:
+            s += ", model size=(%d, %d))" % ((self._X.shape[0], self._n_items) if self._B is not None else self._model.shape)
+        else:
+            s += ") - not trained yet!"
+        return s
+
+    def __repr__(self):
+        return str(self)

@@ -97,3 +97,23 @@ def test_loss_known_answer():
     val = float(O.loss_value(net, c, torch.tensor([[1., 1.], [2., 1.]]), beta=1.0))
     assert abs(val - 2.5 * math.log(2.0)) < 1e-6
     assert abs(val - 1.7328680) < 1e-6
+
+
+def test_ease_oracle_matches_reference_fixture(golden_dir):
+    """oracle/ease_oracle.py (numpy restatement of rectorch/models.py:1006-1026, 1051-1054) against the score matrix
+    and masked predictions the unmodified reference EASE produced (oracle/make_golden_ease.py)."""
+    import os
+    from oracle import ease_oracle as EO
+    from rectorch_b200 import synth
+    z = np.load(os.path.join(golden_dir, "ease_small.npz"))
+    csr = synth.make_matrix(int(z["n_users"]), int(z["n_items"]), seed=int(z["mat_seed"]), mu=2.6, sigma=0.6, min_len=4,
+                            max_len=int(z["n_items"]) // 3)
+    tr, _ = synth.split_heldout(csr, 0.2, seed=int(z["mat_seed"]) + 1)
+    X = tr.to_scipy().toarray()
+    _, S = EO.train(X, float(z["lam"]))
+    assert np.abs(S - z["model"]).max() <= 1e-12
+    ids = z["ids"]
+    pred = EO.predict(S, ids, X[ids], True)
+    assert np.array_equal(np.isinf(pred), np.isinf(z["pred"]))
+    fin = np.isfinite(pred)
+    assert np.abs(pred[fin] - z["pred"][fin]).max() <= 1e-12
