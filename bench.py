@@ -628,6 +628,9 @@ def dp_parity_check(model, sampler, n_users, B, world, rank, dev):
     out = None
     if rank == 0:
         # single-process replay on the same engine: restore the state, run the global batch as ONE local batch
+        sharded = eng._w1_shard
+        if sharded:
+            eng.set_w1_sharding(1, 0)           # the replay is an ordinary single-process step
         eng.w.copy_(w0)
         eng.m.copy_(m0)
         eng.v.copy_(v0)
@@ -639,6 +642,9 @@ def dp_parity_check(model, sampler, n_users, B, world, rank, dev):
         torch.cuda.synchronize(dev)
         loss_1 = float(eng.loss_buf[0].item())
         d = (eng.w - w_dp).abs()
+        if sharded:
+            eng.w.copy_(w_dp)
+            eng.set_w1_sharding(*sharded)
         out = {"loss_dp": loss_dp, "loss_single_process": loss_1, "loss_rel": abs(loss_dp - loss_1) / abs(loss_1),
                "w_max_abs_diff": float(d.max().item()), "w_frac_diff_gt_1e-5": float((d > 1e-5).float().mean().item()),
                "how": "global batch of %d users: %d-rank step vs the same batch in one process on rank 0 "

@@ -93,12 +93,15 @@ int launch_target_fixup(Ctx* c, const BatchView& tgt, __half* PT, int64_t ldp, c
                         const __half* h16, int64_t ldh, const __half* W16, int64_t ldw, const float* bias, int H,
                         float* loss_row, cudaStream_t s);
 int launch_row_sums(Ctx* c, const BatchView& v, float* out, cudaStream_t s);
+// mod_n > 1: Wt is the rank-interleaved gathered copy [mod_n][rows_per x H] (row j lives at (j % mod_n, j / mod_n))
 int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const float* Wt, int H,
-                       const float* bias, int act, float* out, cudaStream_t s, __half* out16 = nullptr, int64_t ld16 = 0);
+                       const float* bias, int act, float* out, cudaStream_t s, __half* out16 = nullptr, int64_t ld16 = 0,
+                       int mod_n = 1, int64_t rows_per = 0);
+// mod_n > 1: only the rows (items) j with j % mod_n == mod_r are written
 int launch_spmm_scatter(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
-                        int H, float* dWt, cudaStream_t s);
+                        int H, float* dWt, cudaStream_t s, int mod_n = 1, int mod_r = 0);
 int launch_spmm_scatter_bias(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
-                             int H, float* dWt, float* db, cudaStream_t s);
+                             int H, float* dWt, float* db, cudaStream_t s, int mod_n = 1, int mod_r = 0);
 int launch_dense_count(Ctx* c, const float* dense, int B, int I, int64_t* lens, cudaStream_t s);
 int launch_dense_fill(Ctx* c, const float* dense, int B, int I, const int64_t* indptr,
                       int32_t* indices, float* values, cudaStream_t s);
@@ -135,7 +138,14 @@ int launch_tensor_norms(Ctx* c, const float* w, const int64_t* offs, const int64
 //   ADAM_ROWS_UNMARKED  only the other rows; their gradient is exactly zero, so g is neither read nor re-zeroed
 // ctas_per_sm x threads is the grid-stride footprint: the full-width default for a launch that owns the GPU,
 // a narrow one for launches that share it with the other stream's kernels.
-enum { ADAM_ROWS_ALL = 0, ADAM_ROWS_MARKED = 1, ADAM_ROWS_UNMARKED = 2 };
+//   ADAM_ROWS_MOD       only rows r with r % mod_n == mod_r (the rank's shard of the encoder-0 weight under data
+//                       parallelism); the updated rows are also written, packed, into block mod_r of w1g
+enum { ADAM_ROWS_ALL = 0, ADAM_ROWS_MARKED = 1, ADAM_ROWS_UNMARKED = 2, ADAM_ROWS_MOD = 3 };
+struct AdamW1 {                     // ADAM_ROWS_MOD (by value to the kernel)
+    float* w1g;
+    int mod_n, mod_r;
+    int64_t rows_per;
+};
 struct AdamOpt {
     const int32_t* mark = nullptr;
     int32_t mark_step = 0;
@@ -143,6 +153,9 @@ struct AdamOpt {
     int row_len = 0;
     int ctas_per_sm = 8;
     int threads = 256;
+    float* w1g = nullptr;           // ADAM_ROWS_MOD: gathered encoder-0 weight [mod_n][rows_per x row_len]
+    int mod_n = 1, mod_r = 0;
+    int64_t rows_per = 0;
     __half* shadow2 = nullptr;      // fp16 image of the hidden-layer tensors: elements [s2_lo, s2_hi) of THIS launch
     int64_t s2_lo = 0, s2_hi = 0;   // (indices relative to the launch's base pointers) go to shadow2[e - s2_lo]
 };

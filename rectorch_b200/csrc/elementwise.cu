@@ -206,7 +206,7 @@ k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, floa
        int64_t n, float neg_step, float b1c, float b2, float b2c, float bc2_sqrt, float eps, float wd,
        float lam, const float* __restrict__ norm_ptr, __half* __restrict__ shadow, int64_t sh_lo, int64_t sh_hi,
        int64_t z_lo, int64_t z_hi, const int32_t* __restrict__ mark, int32_t mark_step, int row_len,
-       __half* __restrict__ shadow2, int64_t s2_lo, int64_t s2_hi) {
+       __half* __restrict__ shadow2, int64_t s2_lo, int64_t s2_hi, AdamW1 w1) {
     pdl_sync();
     float reg = 0.f;
     if (EXTRAS && norm_ptr) {
@@ -223,7 +223,14 @@ k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, floa
         const int64_t e0 = i << 2;
         const bool in_z = e0 >= z_lo && e0 < z_hi;
         bool zero_g = false;
-        if (FILTER != ADAM_ROWS_ALL && in_z) {
+        int64_t w1_pos = -1;            // ADAM_ROWS_MOD: where this float4 goes in the gathered encoder-0 weight
+        if (FILTER == ADAM_ROWS_MOD) {
+            if (in_z) {
+                const int64_t row = (e0 - z_lo) / row_len;
+                if ((int)(row % w1.mod_n) != w1.mod_r) continue;      // another rank's row
+                w1_pos = ((int64_t)w1.mod_r * w1.rows_per + row / w1.mod_n) * row_len + ((e0 - z_lo) - row * row_len);
+            }
+        } else if (FILTER != ADAM_ROWS_ALL && in_z) {
             const bool marked = mark[(e0 - z_lo) / row_len] == mark_step;
             if (FILTER == ADAM_ROWS_MARKED && !marked) continue;
             if (FILTER == ADAM_ROWS_UNMARKED) {
@@ -240,6 +247,7 @@ k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, floa
         w4[i] = ww;
         m4[i] = mm;
         v4[i] = vv;
+        if (FILTER == ADAM_ROWS_MOD && w1_pos >= 0) *reinterpret_cast<float4*>(w1.w1g + w1_pos) = ww;
         // the encoder-0 gradient is accumulated by sparse scatters into an all-zero buffer: restore the zeros
         // here, touching only the (few) rows that actually received a gradient
         if (in_z && !zero_g && (gg.x != 0.f || gg.y != 0.f || gg.z != 0.f || gg.w != 0.f))
@@ -265,7 +273,9 @@ k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, floa
     for (int64_t i = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const bool in_z = i >= z_lo && i < z_hi;
         bool zero_g = false;
-        if (FILTER != ADAM_ROWS_ALL && in_z) {
+        if (FILTER == ADAM_ROWS_MOD) {
+            if (in_z) continue;         // rows are whole float4s (row_len % 4 == 0): the window has no scalar tail
+        } else if (FILTER != ADAM_ROWS_ALL && in_z) {
             const bool marked = mark[(i - z_lo) / row_len] == mark_step;
             if (FILTER == ADAM_ROWS_MARKED && !marked) continue;
             if (FILTER == ADAM_ROWS_UNMARKED) {
@@ -298,8 +308,12 @@ int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float
                  B200VAE_EINVAL, "adam: arenas must be 16-byte aligned");
     const int filter = (z_hi > z_lo) ? opt.filter : ADAM_ROWS_ALL;
     if (filter != ADAM_ROWS_ALL)
-        B200_REQUIRE(opt.mark && opt.row_len > 0 && opt.row_len % 4 == 0 && z_lo % 4 == 0, B200VAE_EINVAL,
-                     "adam: the row filter needs step marks and 16-byte aligned rows");
+        B200_REQUIRE((opt.mark || filter == ADAM_ROWS_MOD) && opt.row_len > 0 && opt.row_len % 4 == 0 && z_lo % 4 == 0 &&
+                     (z_hi - z_lo) % 4 == 0, B200VAE_EINVAL, "adam: the row filter needs step marks and 16-byte aligned rows");
+    if (filter == ADAM_ROWS_MOD)
+        B200_REQUIRE(opt.w1g && opt.mod_n > 1 && opt.mod_r >= 0 && opt.mod_r < opt.mod_n && opt.rows_per > 0, B200VAE_EINVAL,
+                     "adam: bad encoder-0 shard description");
+    const AdamW1 w1 = {opt.w1g, opt.mod_n, opt.mod_r, opt.rows_per};
     // persistent-style grid: a multiple of the SM count (default 8 CTAs of 256 threads per SM)
     const int threads = std::min(256, std::max(32, opt.threads & ~31));
     int64_t want = cdiv(std::max<int64_t>(n >> 2, 1), threads);
@@ -309,14 +323,16 @@ int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float
 #define ADAM_LAUNCH(EX, FI)                                                                                               \
     B200_CUDA_OK(launch_pdl(k_adam<EX, FI>, dim3(blocks), dim3(threads), 0, s, w, g, m, v, n, -lr_over_bc1, b1c, beta2, b2c,   \
                             bc2_sqrt, eps, EX ? wd : 0.f, EX ? lam : 0.f, EX ? norm_ptr : (const float*)nullptr, shadow,  \
-                            sh_lo, sh_hi, z_lo, z_hi, opt.mark, opt.mark_step, opt.row_len, shadow2, s2_lo, s2_hi))
+                            sh_lo, sh_hi, z_lo, z_hi, opt.mark, opt.mark_step, opt.row_len, shadow2, s2_lo, s2_hi, w1))
     if (extras) {
         if (filter == ADAM_ROWS_MARKED) ADAM_LAUNCH(true, ADAM_ROWS_MARKED);
         else if (filter == ADAM_ROWS_UNMARKED) ADAM_LAUNCH(true, ADAM_ROWS_UNMARKED);
+        else if (filter == ADAM_ROWS_MOD) ADAM_LAUNCH(true, ADAM_ROWS_MOD);
         else ADAM_LAUNCH(true, ADAM_ROWS_ALL);
     } else {
         if (filter == ADAM_ROWS_MARKED) ADAM_LAUNCH(false, ADAM_ROWS_MARKED);
         else if (filter == ADAM_ROWS_UNMARKED) ADAM_LAUNCH(false, ADAM_ROWS_UNMARKED);
+        else if (filter == ADAM_ROWS_MOD) ADAM_LAUNCH(false, ADAM_ROWS_MOD);
         else ADAM_LAUNCH(false, ADAM_ROWS_ALL);
     }
 #undef ADAM_LAUNCH

@@ -58,6 +58,29 @@ static int alloc_image(__half** p, int64_t rows, int width, int* ld_out) {
     return 0;
 }
 
+// rank-interleaved layout of the encoder-0 weight rows: row j of [rows x H] <-> block j % n, index j / n.
+// only_r >= 0: pack only the rows of that residue into a [rows_per x H] buffer (block offset dropped).
+__global__ void k_w1_pack(const float* __restrict__ src, float* __restrict__ dst, int rows, int H, int n, int64_t rows_per,
+                          int only_r) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // float4 index
+    const int h4 = H / 4;
+    if (i >= (int64_t)rows * h4) return;
+    const int64_t j = i / h4;
+    const int q = (int)(i - j * h4);
+    const int r = (int)(j % n);
+    if (only_r >= 0 && r != only_r) return;
+    const int64_t blk = only_r >= 0 ? 0 : (int64_t)r * rows_per;
+    reinterpret_cast<float4*>(dst)[(blk + j / n) * h4 + q] = reinterpret_cast<const float4*>(src)[i];
+}
+__global__ void k_w1_unpack(const float* __restrict__ src, float* __restrict__ dst, int rows, int H, int n, int64_t rows_per) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int h4 = H / 4;
+    if (i >= (int64_t)rows * h4) return;
+    const int64_t j = i / h4;
+    const int q = (int)(i - j * h4);
+    reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[((int64_t)(j % n) * rows_per + j / n) * h4 + q];
+}
+
 static void free_ctx(Ctx* c) {
     auto F = [](void* p) { if (p) cudaFree(p); };
     for (int s = 0; s < 2; ++s) {
@@ -208,8 +231,10 @@ static int forward_hidden(Ctx* c, FwdState* st, int B, bool train, float p, uint
     const size_t n_enc = c->enc.size();
     // the last encoder output of a VAE is (mu | logvar): it feeds the reparameterisation, not a GEMM
     auto enc_img = [&](size_t i) -> __half* { return (tch && !(c->cfg.is_vae && i + 1 == n_enc)) ? c->act_enc16[i] : nullptr; };
-    B200_CHECK(launch_spmm_gather(c, st->in, c->xt, c->w + e0.w_off, e0.out, c->w + e0.b_off,
-                                  e0.tanh_act ? 1 : 0, c->act_enc[0], s, enc_img(0), tch ? c->ld_enc16[0] : 0));
+    const bool w1s = c->w1_mod_n > 1;     // sharded encoder-0 optimizer: the gather reads the all-gathered copy
+    B200_CHECK(launch_spmm_gather(c, st->in, c->xt, w1s ? c->w1g : c->w + e0.w_off, e0.out, c->w + e0.b_off,
+                                  e0.tanh_act ? 1 : 0, c->act_enc[0], s, enc_img(0), tch ? c->ld_enc16[0] : 0,
+                                  c->w1_mod_n, c->w1_rows_per));
     for (size_t i = 1; i < n_enc; ++i) {
         if (tch) B200_CHECK(linear_fwd_tc(c, c->act_enc16[i - 1], c->ld_enc16[i - 1], B, c->enc[i], c->act_enc[i], enc_img(i),
                                           c->ld_enc16[i], s));
@@ -352,7 +377,7 @@ static int enc0_grad(Ctx* c, const BatchView& v, const float* xt, const float* d
         if (c->timing) { note(c, "memset_dW1", s); c->launches--; }
     }
     c->dw1_clean = false;
-    B200_CHECK(launch_spmm_scatter(c, v, xt, 1.0f, delta, e0.out, c->g + e0.w_off, s));
+    B200_CHECK(launch_spmm_scatter(c, v, xt, 1.0f, delta, e0.out, c->g + e0.w_off, s, c->w1_mod_n, c->w1_mod_r));
     B200_CHECK(launch_colsum(c, delta, e0.out, B, e0.out, c->g + e0.b_off, s));
     return 0;
 }
@@ -555,6 +580,13 @@ static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo, i
     opt.row_len = E0.out;
     opt.ctas_per_sm = ctas_per_sm;
     opt.threads = (ctas_per_sm < 8) ? c->side_threads : 256;
+    if (c->w1_mod_n > 1 && w1_filter == ADAM_ROWS_ALL) {      // this rank updates only its rows of the encoder-0 weight
+        opt.filter = ADAM_ROWS_MOD;
+        opt.w1g = c->w1g;
+        opt.mod_n = c->w1_mod_n;
+        opt.mod_r = c->w1_mod_r;
+        opt.rows_per = c->w1_rows_per;
+    }
     if (c->tc_hidden) {     // window positions are relative to each launch's base pointers
         opt.shadow2 = c->ws16;
         opt.s2_lo = c->ws_lo - r_lo;
@@ -1000,6 +1032,37 @@ int b200vae_bind_shadow(b200vae_ctx* ctx, void* wd16, int64_t n_halfs) {
     return c->params_bound ? b200vae_sync_weights(ctx, nullptr) : 0;
 }
 
+int b200vae_set_w1_sharding(b200vae_ctx* ctx, float* w1_gathered, int32_t mod_n, int32_t mod_r) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    B200_REQUIRE(c, B200VAE_EINVAL, "null context");
+    if (!w1_gathered || mod_n <= 1) {
+        c->w1g = nullptr; c->w1_mod_n = 1; c->w1_mod_r = 0; c->w1_rows_per = 0;
+        return 0;
+    }
+    const Layer& E0 = c->enc[0];
+    B200_REQUIRE(mod_r >= 0 && mod_r < mod_n && E0.in % mod_n == 0 && E0.out % 4 == 0 && ((uintptr_t)w1_gathered & 15) == 0,
+                 B200VAE_EINVAL, "encoder-0 sharding needs n_inputs %% ranks == 0, a hidden width %% 4 == 0 and an aligned buffer");
+    c->w1g = w1_gathered; c->w1_mod_n = mod_n; c->w1_mod_r = mod_r; c->w1_rows_per = E0.in / mod_n;
+    return c->params_bound ? b200vae_sync_weights(ctx, nullptr) : 0;
+}
+
+int b200vae_w1_rows(b200vae_ctx* ctx, float* arena_base, float* packed, int direction, void* stream) {
+    // direction 0: packed[rows_per x H1] <- this rank's rows of the encoder-0 tensor inside `arena_base` (w, m or v arena)
+    // direction 1: every row of that tensor <- packed_all [mod_n][rows_per x H1] (an all-gathered buffer)
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    B200_REQUIRE(c && arena_base && packed && c->w1_mod_n > 1 && c->params_bound, B200VAE_ESTATE, "encoder-0 sharding is not enabled");
+    const Layer& E0 = c->enc[0];
+    const int64_t n = (int64_t)E0.in * E0.out;
+    if (direction == 0)
+        k_w1_pack<<<(unsigned)cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(arena_base + E0.w_off, packed, E0.in, E0.out,
+                                                                              c->w1_mod_n, c->w1_rows_per, c->w1_mod_r);
+    else
+        k_w1_unpack<<<(unsigned)cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(packed, arena_base + E0.w_off, E0.in, E0.out,
+                                                                                c->w1_mod_n, c->w1_rows_per);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int b200vae_defer_wait_event(b200vae_ctx* ctx, void* event) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     B200_REQUIRE(c, B200VAE_EINVAL, "null context");
@@ -1012,6 +1075,13 @@ int b200vae_sync_weights(b200vae_ctx* ctx, void* stream) {
     // call after the weight arena was modified by anything other than b200vae_adam_step
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     B200_REQUIRE(c && c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
+    if (c->w1_mod_n > 1) {      // the gathered copy of the encoder-0 weight, from the (complete) arena
+        const Layer& E0 = c->enc[0];
+        const int64_t n = (int64_t)E0.in * E0.out;
+        k_w1_pack<<<(unsigned)cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(c->w + E0.w_off, c->w1g, E0.in, E0.out, c->w1_mod_n,
+                                                                              c->w1_rows_per, -1);
+        B200_CUDA_OK(cudaGetLastError());
+    }
     if (!c->tc_dec) return 0;
     const Layer& DL = c->dec.back();
     if (c->tc_hidden)

@@ -221,7 +221,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 k_spmm_gather(BatchView v, const float* __restrict__ vals, const float* __restrict__ Wt, int H,
               const float* __restrict__ bias, int act, float* __restrict__ out, float* __restrict__ acc_ws,
-              int* __restrict__ ticket, __half* __restrict__ out16, int64_t ld16) {
+              int* __restrict__ ticket, __half* __restrict__ out16, int64_t ld16, int mod_n, int64_t rows_per) {
     pdl_sync();
     if ((int)blockIdx.x >= v.sp[v.B]) return;
     const int r = find_row(v.sp, v.B, blockIdx.x);
@@ -250,7 +250,9 @@ k_spmm_gather(BatchView v, const float* __restrict__ vals, const float* __restri
 #pragma unroll
                 for (int i = 0; i < VEC; ++i) w[u][i] = 0.f;
                 if (x[u] != 0.f) {
-                    const float* row = Wt + (int64_t)cols[k + u] * H + h0;
+                    const int j = cols[k + u];
+                    const int64_t jr = (mod_n > 1) ? (int64_t)(j % mod_n) * rows_per + j / mod_n : (int64_t)j;
+                    const float* row = Wt + jr * H + h0;
                     if (VEC == 4) {
                         float4 t = __ldg(reinterpret_cast<const float4*>(row));
                         w[u][0] = t.x; w[u][1 % VEC] = t.y; w[u][2 % VEC] = t.z; w[u][3 % VEC] = t.w;
@@ -267,7 +269,9 @@ k_spmm_gather(BatchView v, const float* __restrict__ vals, const float* __restri
         for (; k < k1; ++k) {
             float x = xv ? xv[k] : (raw ? raw[k] : 1.f);
             if (x == 0.f) continue;
-            const float* row = Wt + (int64_t)cols[k] * H + h0;
+            const int j = cols[k];
+            const int64_t jr = (mod_n > 1) ? (int64_t)(j % mod_n) * rows_per + j / mod_n : (int64_t)j;
+            const float* row = Wt + jr * H + h0;
 #pragma unroll
             for (int i = 0; i < VEC; ++i) acc[i] = fmaf(x, __ldg(row + i), acc[i]);
         }
@@ -310,18 +314,19 @@ static int spmm_grid(Ctx* c, const BatchView& v) {
 }
 
 int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const float* Wt, int H,
-                       const float* bias, int act, float* out, cudaStream_t s, __half* out16, int64_t ld16) {
+                       const float* bias, int act, float* out, cudaStream_t s, __half* out16, int64_t ld16, int mod_n,
+                       int64_t rows_per) {
     if (v.B == 0) return 0;
     bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(Wt) & 15) == 0);
     const int grid = spmm_grid(c, v);
     if (vec) {
         int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));
         B200_CUDA_OK(launch_pdl(k_spmm_gather<4>, dim3(grid), dim3(threads), 0, s, v, vals, Wt, H, bias, act, out, c->spmm_acc,
-                                c->spmm_ticket, out16, ld16));
+                                c->spmm_ticket, out16, ld16, mod_n, rows_per));
     } else {
         int threads = (int)std::min<int64_t>(256, round_up(H, 32));
         B200_CUDA_OK(launch_pdl(k_spmm_gather<1>, dim3(grid), dim3(threads), 0, s, v, vals, Wt, H, bias, act, out, c->spmm_acc,
-                                c->spmm_ticket, out16, ld16));
+                                c->spmm_ticket, out16, ld16, mod_n, rows_per));
     }
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
@@ -335,7 +340,7 @@ int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const floa
 template <int VEC>
 __global__ void __launch_bounds__(256)
 k_spmm_scatter(BatchView v, const float* __restrict__ vals, float scale, const float* __restrict__ dY,
-               int H, float* __restrict__ dWt, float* __restrict__ db) {
+               int H, float* __restrict__ dWt, float* __restrict__ db, int mod_n, int mod_r) {
     pdl_sync();
     if ((int)blockIdx.x >= v.sp[v.B]) return;
     const int r = find_row(v.sp, v.B, blockIdx.x);
@@ -361,6 +366,7 @@ k_spmm_scatter(BatchView v, const float* __restrict__ vals, float scale, const f
         for (int k = k0; k < k1; ++k) {
             float x = xv ? xv[k] : (raw ? raw[k] : 1.f);
             if (x == 0.f) continue;   // dropped entries contribute nothing
+            if (mod_n > 1 && cols[k] % mod_n != mod_r) continue;   // another rank owns this item row
             float* row = dWt + (int64_t)cols[k] * H + h0;
             if (VEC == 4) {
                 atomicAdd(reinterpret_cast<float4*>(row),
@@ -373,21 +379,21 @@ k_spmm_scatter(BatchView v, const float* __restrict__ vals, float scale, const f
 }
 
 int launch_spmm_scatter(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
-                        int H, float* dWt, cudaStream_t s) {
-    return launch_spmm_scatter_bias(c, v, vals, scale, dY, H, dWt, nullptr, s);
+                        int H, float* dWt, cudaStream_t s, int mod_n, int mod_r) {
+    return launch_spmm_scatter_bias(c, v, vals, scale, dY, H, dWt, nullptr, s, mod_n, mod_r);
 }
 
 int launch_spmm_scatter_bias(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
-                             int H, float* dWt, float* db, cudaStream_t s) {
+                             int H, float* dWt, float* db, cudaStream_t s, int mod_n, int mod_r) {
     if (v.B == 0) return 0;
     bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(dWt) & 15) == 0);
     const int grid = spmm_grid(c, v);
     if (vec) {
         int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));
-        B200_CUDA_OK(launch_pdl(k_spmm_scatter<4>, dim3(grid), dim3(threads), 0, s, v, vals, scale, dY, H, dWt, db));
+        B200_CUDA_OK(launch_pdl(k_spmm_scatter<4>, dim3(grid), dim3(threads), 0, s, v, vals, scale, dY, H, dWt, db, mod_n, mod_r));
     } else {
         int threads = (int)std::min<int64_t>(256, round_up(H, 32));
-        B200_CUDA_OK(launch_pdl(k_spmm_scatter<1>, dim3(grid), dim3(threads), 0, s, v, vals, scale, dY, H, dWt, db));
+        B200_CUDA_OK(launch_pdl(k_spmm_scatter<1>, dim3(grid), dim3(threads), 0, s, v, vals, scale, dY, H, dWt, db, mod_n, mod_r));
     }
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());

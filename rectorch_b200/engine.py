@@ -111,6 +111,8 @@ class Engine:
         self.loss_buf = torch.zeros(4, dtype=torch.float32, device=self.device)
         self.adam_steps = 0
         self.wd16 = None          # caller-owned fp16 image of W_d (data parallelism with a sharded optimizer)
+        self.w1g = None           # gathered encoder-0 weight [world][n_items/world x H1] (sharded encoder-0 optimizer)
+        self._w1_shard = None     # (world, rank) while encoder-0 sharding is on
 
     # ---- views ---------------------------------------------------------------------------------
     def _views(self, arena, i):
@@ -170,6 +172,8 @@ class Engine:
         self._seen_version = self.w._version
         if self.wd16 is not None:
             check(_lib.lib().b200vae_bind_shadow(self._ctx, ptr(self.wd16), self.wd16.numel()))
+        if self._w1_shard is not None:
+            check(_lib.lib().b200vae_set_w1_sharding(self._ctx, ptr(self.w1g), self._w1_shard[0], self._w1_shard[1]))
         for slot in (0, 1):
             if self._csr[slot] is not None:
                 self._bind(slot, self._csr[slot])
@@ -203,6 +207,25 @@ class Engine:
             if self._ctx is not None:
                 check(_lib.lib().b200vae_bind_shadow(self._ctx, ptr(self.wd16), self.wd16.numel()))
         return self.wd16
+
+    def set_w1_sharding(self, world, rank):
+        """Turn the sharded encoder-0 optimizer on (world > 1) or off (world <= 1); see b200vae_set_w1_sharding.
+        The gathered copy is rebuilt from the weight arena, which must therefore be complete."""
+        if world > 1:
+            out_f, in_f = self.shapes[0]
+            if self.w1g is None:
+                self.w1g = torch.empty(in_f * out_f, dtype=torch.float32, device=self.device)
+            self._w1_shard = (int(world), int(rank))
+        else:
+            self._w1_shard = None
+        if self._ctx is not None:
+            torch.cuda.synchronize(self.device)
+            check(_lib.lib().b200vae_set_w1_sharding(self._ctx, ptr(self.w1g) if self._w1_shard else None,
+                                                     self._w1_shard[0] if self._w1_shard else 1,
+                                                     self._w1_shard[1] if self._w1_shard else 0))
+
+    def w1_rows(self, arena, packed, unpack):
+        check(_lib.lib().b200vae_w1_rows(self._ctx, ptr(arena), ptr(packed), 1 if unpack else 0, stream_ptr()))
 
     def defer_wait(self, event):
         """The next call that reads the fp16 image of W_d waits for ``event`` (torch.cuda.Event, recorded)."""

@@ -178,7 +178,8 @@ class AETrainer(TorchNNTrainer):
         self._dp_seed = None
         self._delta_bufs = None
         self._zero = None             # (lo, hi) arena range of the W_d shard this rank optimises (ZeRO-1), or None
-        self._wd_stale = False        # fp32 W_d (and its Adam moments) outside the own shard lag behind
+        self._wd_stale = False        # fp32 W_d / encoder-0 rows (and their Adam moments) outside the own shard lag behind
+        self._w1_zero = None          # encoder-0 optimizer sharded too (rows j % world == rank); None = undecided
         self._wd_event = None
         if _dist_world()[1] > 1:
             self._pg_small = dist.new_group()
@@ -227,7 +228,18 @@ class AETrainer(TorchNNTrainer):
         torch.cuda.current_stream(self.device).wait_stream(self._comm_stream)
         for arena in ((eng.w, eng.m, eng.v) if with_state else (eng.w,)):
             dist.all_gather_into_tensor(arena[cut:cut + n], arena[lo:hi])
-        eng._seen_version = eng.w._version      # the fp16 image is already current
+        if self._w1_zero:
+            # encoder layer 0: the gathered weight copy is complete after every step; the moments are gathered here
+            eng.w1_rows(eng.w, eng.w1g, unpack=True)
+            if with_state:
+                blk = eng.w1g.numel() // world
+                own = torch.empty(blk, dtype=torch.float32, device=self.device)
+                full = torch.empty(blk * world, dtype=torch.float32, device=self.device)
+                for arena in (eng.m, eng.v):
+                    eng.w1_rows(arena, own, unpack=False)
+                    dist.all_gather_into_tensor(full, own)
+                    eng.w1_rows(arena, full, unpack=True)
+        eng._seen_version = eng.w._version      # the derived copies are already current
         self._wd_stale = False
 
     # ---- optimizer <-> arena coupling --------------------------------------------------------------
@@ -395,6 +407,10 @@ class AETrainer(TorchNNTrainer):
           The next step's K4 waits for that all-gather; its sparse encoder runs beside it.
         * main stream: the encoder-0 gradient from gathered factors (see ``_step_dp_factors``), one small
           ``all_reduce`` for the hidden-layer tensors and b_d, replicated Adam on those.
+        * encoder layer 0 (the other item-sized tensor) is sharded by item rows ``j % N == rank``: from the gathered
+          factors every rank scatters only into its own rows (1/N of the global batch's scatter instead of all of
+          it), runs Adam on them (1/N of that half of the optimizer traffic) and the ranks ``all_gather`` the updated
+          rows into the copy the next forward pass gathers from.
 
         fp32 W_d and its Adam moments stay sharded between steps (``sync_weights`` gathers them on demand)."""
         eng = self._engine
@@ -408,6 +424,11 @@ class AETrainer(TorchNNTrainer):
                                 torch.empty((n_rows, H1), dtype=torch.float32, device=self.device))
         mine, everyone = self._delta_bufs
         wd16 = eng.use_external_shadow()
+        if self._w1_zero is None:
+            out_f, in_f = eng.shapes[0]
+            self._w1_zero = bool(in_f % world == 0 and out_f % 4 == 0 and os.environ.get("B200VAE_DP_ZERO_W1", "1") != "0")
+            if self._w1_zero:
+                eng.set_w1_sharding(world, rank)
         eng.forward_backward(B_global=n_rows, step=step, row_offset=0, enc0_delta_out=mine, **kw)
         lo, hi = self._zero
         cut = eng.w_off[-1]
@@ -437,6 +458,11 @@ class AETrainer(TorchNNTrainer):
             dist.all_reduce(eng.g[cut + n_wd:], op=dist.ReduceOp.SUM, group=small)
             eng.adam_range(lr, betas, eps, 0.0, 0.0, cut + n_wd, eng.n_elems, first=False)
         eng.adam_range(lr, betas, eps, 0.0, 0.0, 0, cut, first=False)
+        if self._w1_zero:
+            # encoder layer 0 sharded by item rows (j % N == rank): the scatter above touched only the own rows, Adam
+            # updated only those and wrote them into this rank's block of the gathered copy the next forward reads
+            blk = eng.w1g.numel() // world
+            dist.all_gather_into_tensor(eng.w1g, eng.w1g[rank * blk:(rank + 1) * blk], group=small)
 
     def _loss_from(self, comps, beta, lam):
         """Python float loss from the 4 device components (sum over ranks already applied)."""

@@ -36,9 +36,12 @@ mode = sys.argv[3] if len(sys.argv) > 3 else "zero"
 #              (reduce-scatter -> Adam on the shard -> all-gather of the fp16 image)      [default with N > 1]
 # "factors":   the same exchange with a replicated optimiser (all-reduce of dW_d); B200VAE_DP_ZERO=0
 # "allreduce": sharded CSR, dense all-reduce of the whole gradient arena
+# "zero_wd":   "zero" with the encoder-0 optimiser left replicated (B200VAE_DP_ZERO_W1=0)
 if mode == "factors":
     os.environ["B200VAE_DP_ZERO"] = "0"
-replicated = mode in ("zero", "factors")
+if mode == "zero_wd":
+    os.environ["B200VAE_DP_ZERO_W1"] = "0"
+replicated = mode in ("zero", "zero_wd", "factors")
 torch.manual_seed(123 + (rank if replicated else 0))   # replicated modes must not depend on per-rank generators
 losses = []
 if world > 1:
@@ -49,7 +52,8 @@ if world > 1:
             break
         assert (rb.all_rows is not None) == replicated
         losses.append(model.train_batch(rb))
-    assert bool(model._zero) == (mode == "zero"), (mode, model._zero)
+    assert bool(model._zero) == (mode in ("zero", "zero_wd")), (mode, model._zero)
+    assert bool(model._w1_zero) == (mode == "zero"), (mode, model._w1_zero)
     model.sync_weights()            # collective: fp32 W_d shards -> every rank (no-op outside "zero")
 else:
     from rectorch_b200.engine import draw_seed
@@ -67,7 +71,8 @@ osd = model.optimizer.state_dict()["state"]
 last = len(osd) - 2                       # decoder output weight: the sharded tensor
 if rank == 0:
     np.savez(out_path, losses=np.array(losses), adam_m_wd=osd[last]["exp_avg"].cpu().numpy(),
-             adam_v_wd=osd[last]["exp_avg_sq"].cpu().numpy(), **sd)
+             adam_v_wd=osd[last]["exp_avg_sq"].cpu().numpy(), adam_m_w1=osd[0]["exp_avg"].cpu().numpy(),
+             adam_v_w1=osd[0]["exp_avg_sq"].cpu().numpy(), **sd)
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()

@@ -6,7 +6,8 @@ rows with the loss scaled by 1/B_global and applies the identical fused Adam to 
 sampler): only the decoder-output half is all-reduced, the encoder-0 gradient is rebuilt on every rank from
 the all-gathered delta rows (AETrainer._step_dp_factors).  "zero" (default): as "factors", but dW_d is reduce-scattered, every rank
 runs Adam on its 1/N shard of W_d and the ranks all-gather the fp16 image (AETrainer._step_dp_zero); the fp32 weight and
-its Adam moments are gathered back by sync_weights() before they are compared.  Dropout / eps come from Philox keyed by the GLOBAL user row, so the result
+its Adam moments are gathered back by sync_weights() before they are compared; encoder layer 0 is sharded the same way by
+item rows j % N == rank ("zero_wd" leaves it replicated).  Dropout / eps come from Philox keyed by the GLOBAL user row, so the result
 must equal the 1-process run up to fp32 summation order.
 """
 import os
@@ -28,7 +29,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("mode", ["zero", "factors", "allreduce"])
+@pytest.mark.parametrize("mode", ["zero", "zero_wd", "factors", "allreduce"])
 @pytest.mark.parametrize("world", [2])
 def test_sharded_training_matches_single_process(tmp_path, world, mode):
     if torch.cuda.device_count() < world:
@@ -52,6 +53,6 @@ def test_sharded_training_matches_single_process(tmp_path, world, mode):
         # Adam normalises updates: a rounding-level gradient difference can move isolated weights by O(lr)
         assert np.mean(d > 1e-5) < 0.01, "%s: %.4f of the weights differ by > 1e-5 (max %.2e)" % (k, np.mean(d > 1e-5), d.max())
     # the sharded Adam moments of W_d, gathered back: same statistics as the replicated run
-    for k in ("adam_m_wd", "adam_v_wd"):
+    for k in ("adam_m_wd", "adam_v_wd", "adam_m_w1", "adam_v_w1"):
         d = np.abs(a[k] - b[k])
         assert d.max() <= 1e-6 + 1e-3 * np.abs(b[k]).max(), "%s: max diff %.3e" % (k, d.max())
