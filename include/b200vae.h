@@ -93,13 +93,14 @@ int  b200vae_bind_shadow(b200vae_ctx* ctx, void* wd16, int64_t n_halfs);
 /* Data parallelism with a sharded optimizer for ENCODER layer 0 (the other item-sized tensor): this rank owns the
  * item rows j with j % mod_n == mod_r of the [n_items x H1] weight.  With sharding on,
  *   - b200vae_enc0_grad scatters only into the rank's own rows (1/mod_n of the global batch's scatter work),
- *   - the Adam launches update only those rows and also write them, packed, into block mod_r of
- *     w1_gathered[mod_n][n_items/mod_n x H1] (a caller-owned device buffer) -- the caller then all-gathers that buffer
- *     in place over the ranks,
- *   - the forward pass gathers encoder-0 rows from w1_gathered (row j at block j % mod_n, index j / mod_n).
+ *   - the Adam launches update only those rows and also write their fp16 image, packed, into block mod_r of
+ *     w1_gathered[mod_n][n_items/mod_n x H1] (a caller-owned device buffer of fp16) -- the caller then all-gathers
+ *     that buffer in place over the ranks (half the bytes of the fp32 rows),
+ *   - the forward pass gathers encoder-0 rows from w1_gathered (row j at block j % mod_n, index j / mod_n): under
+ *     this mode the encoder's first layer reads fp16 images of its weights like the decoder's last layer does.
  * The call (re)builds w1_gathered from the complete weight arena.  w1_gathered == NULL or mod_n <= 1 turns it off.
  * Replaces: nothing in the reference (single process); cf. torch.optim.Adam over nn.Linear(n_items, H1), models.py:768. */
-int  b200vae_set_w1_sharding(b200vae_ctx* ctx, float* w1_gathered, int32_t mod_n, int32_t mod_r);
+int  b200vae_set_w1_sharding(b200vae_ctx* ctx, void* w1_gathered, int32_t mod_n, int32_t mod_r);
 /* Move the rank's rows of the encoder-0 tensor between an arena (w, m or v: pass the arena's base pointer) and a
  * packed buffer: direction 0 packs the OWN rows into packed[n_items/mod_n x H1]; direction 1 rewrites EVERY row of
  * the tensor from an all-gathered packed_all[mod_n][n_items/mod_n x H1].  Used to rebuild complete fp32 tensors

@@ -93,10 +93,11 @@ int launch_target_fixup(Ctx* c, const BatchView& tgt, __half* PT, int64_t ldp, c
                         const __half* h16, int64_t ldh, const __half* W16, int64_t ldw, const float* bias, int H,
                         float* loss_row, cudaStream_t s);
 int launch_row_sums(Ctx* c, const BatchView& v, float* out, cudaStream_t s);
-// mod_n > 1: Wt is the rank-interleaved gathered copy [mod_n][rows_per x H] (row j lives at (j % mod_n, j / mod_n))
+// Wt16 != NULL (then mod_n > 1): the weight rows are read from the rank-interleaved gathered fp16 image
+// [mod_n][rows_per x H] (row j lives at block j % mod_n, index j / mod_n) instead of Wt
 int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const float* Wt, int H,
                        const float* bias, int act, float* out, cudaStream_t s, __half* out16 = nullptr, int64_t ld16 = 0,
-                       int mod_n = 1, int64_t rows_per = 0);
+                       const __half* Wt16 = nullptr, int mod_n = 1, int64_t rows_per = 0);
 // mod_n > 1: only the rows (items) j with j % mod_n == mod_r are written
 int launch_spmm_scatter(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
                         int H, float* dWt, cudaStream_t s, int mod_n = 1, int mod_r = 0);
@@ -142,7 +143,7 @@ int launch_tensor_norms(Ctx* c, const float* w, const int64_t* offs, const int64
 //                       parallelism); the updated rows are also written, packed, into block mod_r of w1g
 enum { ADAM_ROWS_ALL = 0, ADAM_ROWS_MARKED = 1, ADAM_ROWS_UNMARKED = 2, ADAM_ROWS_MOD = 3 };
 struct AdamW1 {                     // ADAM_ROWS_MOD (by value to the kernel)
-    float* w1g;
+    __half* w1g;
     int mod_n, mod_r;
     int64_t rows_per;
 };
@@ -153,7 +154,7 @@ struct AdamOpt {
     int row_len = 0;
     int ctas_per_sm = 8;
     int threads = 256;
-    float* w1g = nullptr;           // ADAM_ROWS_MOD: gathered encoder-0 weight [mod_n][rows_per x row_len]
+    __half* w1g = nullptr;          // ADAM_ROWS_MOD: gathered fp16 image of the encoder-0 weight [mod_n][rows_per x row_len]
     int mod_n = 1, mod_r = 0;
     int64_t rows_per = 0;
     __half* shadow2 = nullptr;      // fp16 image of the hidden-layer tensors: elements [s2_lo, s2_hi) of THIS launch

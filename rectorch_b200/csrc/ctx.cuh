@@ -57,9 +57,9 @@ struct Ctx {
     __half* h16 = nullptr;            // [B x H_last] last hidden activation
     __half* wd16 = nullptr;           // [n_items x H_last] W_d, maintained by Adam
     // data parallelism with a sharded optimizer for encoder layer 0 (b200vae_set_w1_sharding): this rank owns the item
-    // rows j with j % w1_mod_n == w1_mod_r; w1g is the caller-owned gathered copy [w1_mod_n][w1_rows_per x H1] that the
-    // forward gather reads (row j at block j % n, index j / n) and the ranks all-gather after every Adam step
-    float* w1g = nullptr;
+    // rows j with j % w1_mod_n == w1_mod_r; w1g is the caller-owned gathered fp16 image [w1_mod_n][w1_rows_per x H1] that
+    // the forward gather reads (row j at block j % n, index j / n) and the ranks all-gather after every Adam step
+    __half* w1g = nullptr;
     int w1_mod_n = 1, w1_mod_r = 0;
     int64_t w1_rows_per = 0;
     bool wd16_external = false;       // wd16 is a caller-owned buffer (b200vae_bind_shadow)

@@ -247,7 +247,14 @@ k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, floa
         w4[i] = ww;
         m4[i] = mm;
         v4[i] = vv;
-        if (FILTER == ADAM_ROWS_MOD && w1_pos >= 0) *reinterpret_cast<float4*>(w1.w1g + w1_pos) = ww;
+        if (FILTER == ADAM_ROWS_MOD && w1_pos >= 0) {       // fp16 image of the updated row, into this rank's block
+            const __half2 lo = __floats2half2_rn(f16_clamp(ww.x), f16_clamp(ww.y));
+            const __half2 hi = __floats2half2_rn(f16_clamp(ww.z), f16_clamp(ww.w));
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(w1.w1g + w1_pos) = pk;
+        }
         // the encoder-0 gradient is accumulated by sparse scatters into an all-zero buffer: restore the zeros
         // here, touching only the (few) rows that actually received a gradient
         if (in_z && !zero_g && (gg.x != 0.f || gg.y != 0.f || gg.z != 0.f || gg.w != 0.f))

@@ -72,6 +72,21 @@ __global__ void k_w1_pack(const float* __restrict__ src, float* __restrict__ dst
     const int64_t blk = only_r >= 0 ? 0 : (int64_t)r * rows_per;
     reinterpret_cast<float4*>(dst)[(blk + j / n) * h4 + q] = reinterpret_cast<const float4*>(src)[i];
 }
+// fp16 image of ALL rows in the rank-interleaved layout (what the forward gather reads under encoder-0 sharding)
+__global__ void k_w1_image(const float* __restrict__ src, __half* __restrict__ dst, int rows, int H, int n, int64_t rows_per) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // float4 index
+    const int h4 = H / 4;
+    if (i >= (int64_t)rows * h4) return;
+    const int64_t j = i / h4;
+    const int q = (int)(i - j * h4);
+    const float4 t = reinterpret_cast<const float4*>(src)[i];
+    const __half2 lo = __floats2half2_rn(f16_clamp(t.x), f16_clamp(t.y));
+    const __half2 hi = __floats2half2_rn(f16_clamp(t.z), f16_clamp(t.w));
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+    reinterpret_cast<uint2*>(dst)[((int64_t)(j % n) * rows_per + j / n) * h4 + q] = pk;
+}
 __global__ void k_w1_unpack(const float* __restrict__ src, float* __restrict__ dst, int rows, int H, int n, int64_t rows_per) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int h4 = H / 4;
@@ -232,9 +247,9 @@ static int forward_hidden(Ctx* c, FwdState* st, int B, bool train, float p, uint
     // the last encoder output of a VAE is (mu | logvar): it feeds the reparameterisation, not a GEMM
     auto enc_img = [&](size_t i) -> __half* { return (tch && !(c->cfg.is_vae && i + 1 == n_enc)) ? c->act_enc16[i] : nullptr; };
     const bool w1s = c->w1_mod_n > 1;     // sharded encoder-0 optimizer: the gather reads the all-gathered copy
-    B200_CHECK(launch_spmm_gather(c, st->in, c->xt, w1s ? c->w1g : c->w + e0.w_off, e0.out, c->w + e0.b_off,
+    B200_CHECK(launch_spmm_gather(c, st->in, c->xt, c->w + e0.w_off, e0.out, c->w + e0.b_off,
                                   e0.tanh_act ? 1 : 0, c->act_enc[0], s, enc_img(0), tch ? c->ld_enc16[0] : 0,
-                                  c->w1_mod_n, c->w1_rows_per));
+                                  w1s ? c->w1g : nullptr, c->w1_mod_n, c->w1_rows_per));
     for (size_t i = 1; i < n_enc; ++i) {
         if (tch) B200_CHECK(linear_fwd_tc(c, c->act_enc16[i - 1], c->ld_enc16[i - 1], B, c->enc[i], c->act_enc[i], enc_img(i),
                                           c->ld_enc16[i], s));
@@ -1032,7 +1047,7 @@ int b200vae_bind_shadow(b200vae_ctx* ctx, void* wd16, int64_t n_halfs) {
     return c->params_bound ? b200vae_sync_weights(ctx, nullptr) : 0;
 }
 
-int b200vae_set_w1_sharding(b200vae_ctx* ctx, float* w1_gathered, int32_t mod_n, int32_t mod_r) {
+int b200vae_set_w1_sharding(b200vae_ctx* ctx, void* w1_gathered, int32_t mod_n, int32_t mod_r) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     B200_REQUIRE(c, B200VAE_EINVAL, "null context");
     if (!w1_gathered || mod_n <= 1) {
@@ -1042,7 +1057,7 @@ int b200vae_set_w1_sharding(b200vae_ctx* ctx, float* w1_gathered, int32_t mod_n,
     const Layer& E0 = c->enc[0];
     B200_REQUIRE(mod_r >= 0 && mod_r < mod_n && E0.in % mod_n == 0 && E0.out % 4 == 0 && ((uintptr_t)w1_gathered & 15) == 0,
                  B200VAE_EINVAL, "encoder-0 sharding needs n_inputs %% ranks == 0, a hidden width %% 4 == 0 and an aligned buffer");
-    c->w1g = w1_gathered; c->w1_mod_n = mod_n; c->w1_mod_r = mod_r; c->w1_rows_per = E0.in / mod_n;
+    c->w1g = reinterpret_cast<__half*>(w1_gathered); c->w1_mod_n = mod_n; c->w1_mod_r = mod_r; c->w1_rows_per = E0.in / mod_n;
     return c->params_bound ? b200vae_sync_weights(ctx, nullptr) : 0;
 }
 
@@ -1078,8 +1093,8 @@ int b200vae_sync_weights(b200vae_ctx* ctx, void* stream) {
     if (c->w1_mod_n > 1) {      // the gathered copy of the encoder-0 weight, from the (complete) arena
         const Layer& E0 = c->enc[0];
         const int64_t n = (int64_t)E0.in * E0.out;
-        k_w1_pack<<<(unsigned)cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(c->w + E0.w_off, c->w1g, E0.in, E0.out, c->w1_mod_n,
-                                                                              c->w1_rows_per, -1);
+        k_w1_image<<<(unsigned)cdiv(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(c->w + E0.w_off, c->w1g, E0.in, E0.out, c->w1_mod_n,
+                                                                               c->w1_rows_per);
         B200_CUDA_OK(cudaGetLastError());
     }
     if (!c->tc_dec) return 0;

@@ -221,7 +221,8 @@ template <int VEC>
 __global__ void __launch_bounds__(256)
 k_spmm_gather(BatchView v, const float* __restrict__ vals, const float* __restrict__ Wt, int H,
               const float* __restrict__ bias, int act, float* __restrict__ out, float* __restrict__ acc_ws,
-              int* __restrict__ ticket, __half* __restrict__ out16, int64_t ld16, int mod_n, int64_t rows_per) {
+              int* __restrict__ ticket, __half* __restrict__ out16, int64_t ld16, const __half* __restrict__ Wt16, int mod_n,
+              int64_t rows_per) {
     pdl_sync();
     if ((int)blockIdx.x >= v.sp[v.B]) return;
     const int r = find_row(v.sp, v.B, blockIdx.x);
@@ -251,13 +252,24 @@ k_spmm_gather(BatchView v, const float* __restrict__ vals, const float* __restri
                 for (int i = 0; i < VEC; ++i) w[u][i] = 0.f;
                 if (x[u] != 0.f) {
                     const int j = cols[k + u];
-                    const int64_t jr = (mod_n > 1) ? (int64_t)(j % mod_n) * rows_per + j / mod_n : (int64_t)j;
-                    const float* row = Wt + jr * H + h0;
-                    if (VEC == 4) {
-                        float4 t = __ldg(reinterpret_cast<const float4*>(row));
-                        w[u][0] = t.x; w[u][1 % VEC] = t.y; w[u][2 % VEC] = t.z; w[u][3 % VEC] = t.w;
+                    if (Wt16) {
+                        const __half* row = Wt16 + ((int64_t)(j % mod_n) * rows_per + j / mod_n) * H + h0;
+                        if (VEC == 4) {
+                            const uint2 t = __ldg(reinterpret_cast<const uint2*>(row));
+                            const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+                            const float2 b2 = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+                            w[u][0] = a2.x; w[u][1 % VEC] = a2.y; w[u][2 % VEC] = b2.x; w[u][3 % VEC] = b2.y;
+                        } else {
+                            w[u][0] = __half2float(row[0]);
+                        }
                     } else {
-                        w[u][0] = __ldg(row);
+                        const float* row = Wt + (int64_t)j * H + h0;
+                        if (VEC == 4) {
+                            float4 t = __ldg(reinterpret_cast<const float4*>(row));
+                            w[u][0] = t.x; w[u][1 % VEC] = t.y; w[u][2 % VEC] = t.z; w[u][3 % VEC] = t.w;
+                        } else {
+                            w[u][0] = __ldg(row);
+                        }
                     }
                 }
             }
@@ -270,10 +282,15 @@ k_spmm_gather(BatchView v, const float* __restrict__ vals, const float* __restri
             float x = xv ? xv[k] : (raw ? raw[k] : 1.f);
             if (x == 0.f) continue;
             const int j = cols[k];
-            const int64_t jr = (mod_n > 1) ? (int64_t)(j % mod_n) * rows_per + j / mod_n : (int64_t)j;
-            const float* row = Wt + jr * H + h0;
+            if (Wt16) {
+                const __half* row = Wt16 + ((int64_t)(j % mod_n) * rows_per + j / mod_n) * H + h0;
 #pragma unroll
-            for (int i = 0; i < VEC; ++i) acc[i] = fmaf(x, __ldg(row + i), acc[i]);
+                for (int i = 0; i < VEC; ++i) acc[i] = fmaf(x, __half2float(row[i]), acc[i]);
+            } else {
+                const float* row = Wt + (int64_t)j * H + h0;
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] = fmaf(x, __ldg(row + i), acc[i]);
+            }
         }
         if (nseg == 1) {
 #pragma unroll
@@ -314,19 +331,19 @@ static int spmm_grid(Ctx* c, const BatchView& v) {
 }
 
 int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const float* Wt, int H,
-                       const float* bias, int act, float* out, cudaStream_t s, __half* out16, int64_t ld16, int mod_n,
-                       int64_t rows_per) {
+                       const float* bias, int act, float* out, cudaStream_t s, __half* out16, int64_t ld16,
+                       const __half* Wt16, int mod_n, int64_t rows_per) {
     if (v.B == 0) return 0;
     bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(Wt) & 15) == 0);
     const int grid = spmm_grid(c, v);
     if (vec) {
         int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));
         B200_CUDA_OK(launch_pdl(k_spmm_gather<4>, dim3(grid), dim3(threads), 0, s, v, vals, Wt, H, bias, act, out, c->spmm_acc,
-                                c->spmm_ticket, out16, ld16, mod_n, rows_per));
+                                c->spmm_ticket, out16, ld16, Wt16, mod_n, rows_per));
     } else {
         int threads = (int)std::min<int64_t>(256, round_up(H, 32));
         B200_CUDA_OK(launch_pdl(k_spmm_gather<1>, dim3(grid), dim3(threads), 0, s, v, vals, Wt, H, bias, act, out, c->spmm_acc,
-                                c->spmm_ticket, out16, ld16, mod_n, rows_per));
+                                c->spmm_ticket, out16, ld16, Wt16, mod_n, rows_per));
     }
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());

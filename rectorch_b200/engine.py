@@ -111,7 +111,7 @@ class Engine:
         self.loss_buf = torch.zeros(4, dtype=torch.float32, device=self.device)
         self.adam_steps = 0
         self.wd16 = None          # caller-owned fp16 image of W_d (data parallelism with a sharded optimizer)
-        self.w1g = None           # gathered encoder-0 weight [world][n_items/world x H1] (sharded encoder-0 optimizer)
+        self.w1g = None           # gathered fp16 image of the encoder-0 weight [world][n_items/world x H1] (sharded optimizer)
         self._w1_shard = None     # (world, rank) while encoder-0 sharding is on
 
     # ---- views ---------------------------------------------------------------------------------
@@ -214,7 +214,7 @@ class Engine:
         if world > 1:
             out_f, in_f = self.shapes[0]
             if self.w1g is None:
-                self.w1g = torch.empty(in_f * out_f, dtype=torch.float32, device=self.device)
+                self.w1g = torch.empty(in_f * out_f, dtype=torch.float16, device=self.device)
             self._w1_shard = (int(world), int(rank))
         else:
             self._w1_shard = None

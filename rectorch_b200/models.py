@@ -229,16 +229,15 @@ class AETrainer(TorchNNTrainer):
         for arena in ((eng.w, eng.m, eng.v) if with_state else (eng.w,)):
             dist.all_gather_into_tensor(arena[cut:cut + n], arena[lo:hi])
         if self._w1_zero:
-            # encoder layer 0: the gathered weight copy is complete after every step; the moments are gathered here
-            eng.w1_rows(eng.w, eng.w1g, unpack=True)
-            if with_state:
-                blk = eng.w1g.numel() // world
-                own = torch.empty(blk, dtype=torch.float32, device=self.device)
-                full = torch.empty(blk * world, dtype=torch.float32, device=self.device)
-                for arena in (eng.m, eng.v):
-                    eng.w1_rows(arena, own, unpack=False)
-                    dist.all_gather_into_tensor(full, own)
-                    eng.w1_rows(arena, full, unpack=True)
+            # encoder layer 0: every rank holds its own rows in fp32 (the gathered copy the forward pass reads is an
+            # fp16 image): pack the own rows, all-gather, rewrite the whole tensor
+            blk = eng.w1g.numel() // world
+            own = torch.empty(blk, dtype=torch.float32, device=self.device)
+            full = torch.empty(blk * world, dtype=torch.float32, device=self.device)
+            for arena in ((eng.w, eng.m, eng.v) if with_state else (eng.w,)):
+                eng.w1_rows(arena, own, unpack=False)
+                dist.all_gather_into_tensor(full, own)
+                eng.w1_rows(arena, full, unpack=True)
         eng._seen_version = eng.w._version      # the derived copies are already current
         self._wd_stale = False
 
@@ -426,7 +425,10 @@ class AETrainer(TorchNNTrainer):
         wd16 = eng.use_external_shadow()
         if self._w1_zero is None:
             out_f, in_f = eng.shapes[0]
-            self._w1_zero = bool(in_f % world == 0 and out_f % 4 == 0 and os.environ.get("B200VAE_DP_ZERO_W1", "1") != "0")
+            # pays off from 4 ranks on (the all-gather of the rows costs what half a replicated update does at N = 2);
+            # B200VAE_DP_ZERO_W1 = 1 / 0 forces it on / off
+            want = os.environ.get("B200VAE_DP_ZERO_W1", "1" if world >= 4 else "0") != "0"
+            self._w1_zero = bool(want and in_f % world == 0 and out_f % 4 == 0)
             if self._w1_zero:
                 eng.set_w1_sharding(world, rank)
         eng.forward_backward(B_global=n_rows, step=step, row_offset=0, enc0_delta_out=mine, **kw)

@@ -39,8 +39,7 @@ mode = sys.argv[3] if len(sys.argv) > 3 else "zero"
 # "zero_wd":   "zero" with the encoder-0 optimiser left replicated (B200VAE_DP_ZERO_W1=0)
 if mode == "factors":
     os.environ["B200VAE_DP_ZERO"] = "0"
-if mode == "zero_wd":
-    os.environ["B200VAE_DP_ZERO_W1"] = "0"
+os.environ["B200VAE_DP_ZERO_W1"] = "1" if mode == "zero" else "0"      # (default: on from 4 ranks)
 replicated = mode in ("zero", "zero_wd", "factors")
 torch.manual_seed(123 + (rank if replicated else 0))   # replicated modes must not depend on per-rank generators
 losses = []

