@@ -519,6 +519,17 @@ def run_b200(args, cfg):
         model._bind_sampler(sampler)
         dp_parity = dp_parity_check(model, sampler, n_users, B, world, rank, dev)
 
+    # ---- phases of the data-parallel step (CUDA events on both streams; not part of the timed region above) ----
+    dp_phases = None
+    if world > 1 and args.dp_timing:
+        from rectorch_b200.models import _PhaseTimer
+        model._dp_timer = _PhaseTimer()
+        for i in range(10):
+            step(W + K + 100 + i)
+        barrier()
+        dp_phases = [{"phase": k, "done_at_us": v} for k, v in model._dp_timer.report()]
+        model._dp_timer = None
+
     # ---- per-kernel timing pass (CUDA events inside the library, on the launching stream; serial schedule) ----
     eng.set_timing(True)
     names = ["dec_fwd_lse(K4)", "adam(K8)", "dec_bwd_prob(K5)", "dWd_gemm", "dh_gemm"]
@@ -594,7 +605,7 @@ def run_b200(args, cfg):
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "host_issue_us_per_step": host_us,
                 "roofline": roof_dom, "roofline_k4": roof_k4,
                 "kernel_ms": {n: float(v) for n, v in zip(names, kms)},
-                "cpu_baseline": cpu, "last_loss": last_loss, "dp_parity": dp_parity}
+                "cpu_baseline": cpu, "last_loss": last_loss, "dp_parity": dp_parity, "dp_phases": dp_phases}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -724,6 +735,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--mode", default="train", choices=["train", "eval"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dp-timing", action="store_true", help="N > 1: also report when each phase of the step completes")
     ap.add_argument("--dp", default="zero", choices=["zero", "factors"],
                     help="N > 1: gradient exchange (zero: sharded Adam for W_d; factors: all-reduce of dW_d)")
     args = ap.parse_args()

@@ -100,6 +100,34 @@ def _dist_world():
     return 0, 1
 
 
+class _PhaseTimer:
+    """CUDA-event stopwatch for the phases of a data-parallel step (bench.py --dp-timing): every mark records an
+    event on its stream; ``report`` turns the events of the recorded steps into mean microseconds since the step
+    began (main stream) -- so overlap between the two streams is visible."""
+
+    def __init__(self):
+        self.steps = []
+
+    def begin(self, stream):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        self.steps.append([("begin", e)])
+
+    def mark(self, name, stream=None):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream if stream is not None else torch.cuda.current_stream())
+        self.steps[-1].append((name, e))
+
+    def report(self):
+        torch.cuda.synchronize()
+        acc = {}
+        for st in self.steps:
+            t0 = st[0][1]
+            for name, e in st[1:]:
+                acc.setdefault(name, []).append(t0.elapsed_time(e) * 1e3)
+        return [(k, float(np.mean(v))) for k, v in acc.items()]
+
+
 class _StagedBatch:
     """Device staging area of ``train_batch_csr`` under data parallelism: the GLOBAL batch as a small CSR matrix
     that is re-filled from host arrays every step; plays the sampler's role for ``RowBatch``."""
@@ -180,6 +208,7 @@ class AETrainer(TorchNNTrainer):
         self._zero = None             # (lo, hi) arena range of the W_d shard this rank optimises (ZeRO-1), or None
         self._wd_stale = False        # fp32 W_d / encoder-0 rows (and their Adam moments) outside the own shard lag behind
         self._w1_zero = None          # encoder-0 optimizer sharded too (rows j % world == rank); None = undecided
+        self._dp_timer = None         # _PhaseTimer while a caller wants the phases of the data-parallel step timed
         self._wd_event = None
         if _dist_world()[1] > 1:
             self._pg_small = dist.new_group()
@@ -423,6 +452,9 @@ class AETrainer(TorchNNTrainer):
                                 torch.empty((n_rows, H1), dtype=torch.float32, device=self.device))
         mine, everyone = self._delta_bufs
         wd16 = eng.use_external_shadow()
+        tm = self._dp_timer
+        if tm is not None:
+            tm.begin(torch.cuda.current_stream(self.device))
         if self._w1_zero is None:
             out_f, in_f = eng.shapes[0]
             # pays off from 4 ranks on (the all-gather of the rows costs what half a replicated update does at N = 2);
@@ -432,6 +464,8 @@ class AETrainer(TorchNNTrainer):
             if self._w1_zero:
                 eng.set_w1_sharding(world, rank)
         eng.forward_backward(B_global=n_rows, step=step, row_offset=0, enc0_delta_out=mine, **kw)
+        if tm is not None:
+            tm.mark("main: forward + backward")
         lo, hi = self._zero
         cut = eng.w_off[-1]
         per = hi - lo
@@ -442,29 +476,47 @@ class AETrainer(TorchNNTrainer):
             self._wd_event = torch.cuda.Event()
         check(_lib.lib().b200vae_wait_wd_ready(eng._ctx, ctypes.c_void_p(side.cuda_stream)))
         with torch.cuda.stream(side):
+            if tm is not None:
+                tm.mark("side: wait for dW_d", side)
             dist.reduce_scatter_tensor(eng.g[lo:hi], eng.g[cut:cut + n_wd], op=dist.ReduceOp.SUM)
+            if tm is not None:
+                tm.mark("side: reduce_scatter dW_d", side)
             eng.adam_range(lr, betas, eps, 0.0, 0.0, lo, hi, first=True)
+            if tm is not None:
+                tm.mark("side: Adam on the W_d shard", side)
             dist.all_gather_into_tensor(wd16[:n_wd], wd16[lo - cut:hi - cut])
             dist.all_reduce(loss_slot, op=dist.ReduceOp.SUM)
+            if tm is not None:
+                tm.mark("side: all_gather fp16 W_d + loss", side)
             self._wd_event.record(side)
         eng.defer_wait(self._wd_event)
         self._wd_stale = True
         # main stream: exchange the encoder-0 factors and rebuild that gradient for the global batch
         small = self._pg_small
         dist.all_gather_into_tensor(everyone, mine, group=small)
+        if tm is not None:
+            tm.mark("main: all_gather delta")
         eng.enc0_grad(rb.all_rows, everyone, kw["dropout_p"], kw["seed"], step, 0)
+        if tm is not None:
+            tm.mark("main: encoder-0 gradient of the global batch")
         s_lo = eng.w_off[1] if len(eng.w_off) > 1 else cut
         if s_lo < cut:
             dist.all_reduce(eng.g[s_lo:cut], op=dist.ReduceOp.SUM, group=small)
         if cut + n_wd < eng.n_elems:        # b_d (and arena padding): replicated like the hidden layers
             dist.all_reduce(eng.g[cut + n_wd:], op=dist.ReduceOp.SUM, group=small)
             eng.adam_range(lr, betas, eps, 0.0, 0.0, cut + n_wd, eng.n_elems, first=False)
+        if tm is not None:
+            tm.mark("main: all_reduce hidden layers + b_d")
         eng.adam_range(lr, betas, eps, 0.0, 0.0, 0, cut, first=False)
+        if tm is not None:
+            tm.mark("main: Adam (encoder 0 + hidden layers)")
         if self._w1_zero:
             # encoder layer 0 sharded by item rows (j % N == rank): the scatter above touched only the own rows, Adam
             # updated only those and wrote them into this rank's block of the gathered copy the next forward reads
             blk = eng.w1g.numel() // world
             dist.all_gather_into_tensor(eng.w1g, eng.w1g[rank * blk:(rank + 1) * blk], group=small)
+            if tm is not None:
+                tm.mark("main: all_gather fp16 encoder-0 rows")
 
     def _loss_from(self, comps, beta, lam):
         """Python float loss from the 4 device components (sum over ranks already applied)."""
