@@ -107,6 +107,18 @@ int  b200vae_set_w1_sharding(b200vae_ctx* ctx, void* w1_gathered, int32_t mod_n,
  * (state_dict / checkpoints) from the shards. */
 int  b200vae_w1_rows(b200vae_ctx* ctx, float* arena_base, float* packed, int direction, void* stream);
 
+/* Data-parallel small exchange: instead of four small collectives per step (all-gather of the encoder-0 deltas,
+ * all-reduces of the hidden-layer gradients, of the b_d gradient and of the loss components) every rank all-gathers ONE
+ * packed record [delta | a | b | c].  b200vae_dp_pack writes dst[n_delta ..] = [a | b | c] (the caller lets
+ * b200vae_forward_backward write the deltas straight into dst[0 .. n_delta)); b200vae_dp_unpack reads the gathered
+ * records recv[n_ranks][stride]: delta_all[r * n_delta + i] = record r's delta, a / b / c = the sums over the ranks
+ * in rank order (bit-identical on every rank).  Replaces: the gradient averaging loss.backward() would need under
+ * torch DistributedDataParallel for these tensors (models.py:832). */
+int  b200vae_dp_pack(float* dst, const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc,
+                     void* stream);
+int  b200vae_dp_unpack(const float* recv, int32_t n_ranks, int64_t stride, int64_t n_delta, float* delta_all, float* a,
+                       int64_t na, float* b, int64_t nb, float* c, int64_t nc, void* stream);
+
 /* The next engine call that reads the fp16 image of W_d (forward_backward / train_step / predict / decode) makes its
  * stream wait for `event` (a cudaEvent_t recorded by the caller on the stream that refreshes the image) right before
  * the first GEMM that needs it -- the encoder part of the step overlaps the refresh.  One-shot. */

@@ -42,6 +42,9 @@ _SIGS = {
     "b200vae_sync_weights": (c_int, [c_void_p, c_void_p]),
     "b200vae_bind_shadow": (c_int, [c_void_p, c_void_p, c_int64]),
     "b200vae_defer_wait_event": (c_int, [c_void_p, c_void_p]),
+    "b200vae_dp_pack": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "b200vae_dp_unpack": (c_int, [c_void_p, c_int32, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                  c_void_p, c_int64, c_void_p]),
     "b200vae_set_w1_sharding": (c_int, [c_void_p, c_void_p, c_int32, c_int32]),
     "b200vae_w1_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "b200vae_check_error_flag": (c_int, [c_void_p]),

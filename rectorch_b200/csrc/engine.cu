@@ -1078,6 +1078,57 @@ int b200vae_w1_rows(b200vae_ctx* ctx, float* arena_base, float* packed, int dire
     return 0;
 }
 
+// ---- data-parallel small exchange: one all-gather instead of four small collectives ------------------------------
+// Every rank sends ONE packed record [delta (B x H1) | hidden-layer gradients | b_d gradient | loss[4]]; after the
+// all-gather each rank sums the gradient / loss parts over the ranks itself (fixed rank order: bit-identical on all
+// ranks) and lays the delta parts out as the [N*B x H1] matrix b200vae_enc0_grad reads.
+__global__ void k_dp_pack(float* __restrict__ dst, const float* __restrict__ a, int64_t na, const float* __restrict__ b,
+                          int64_t nb, const float* __restrict__ c, int64_t nc) {
+    pdl_sync();
+    const int64_t n = na + nb + nc;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = i < na ? a[i] : (i < na + nb ? b[i - na] : c[i - na - nb]);
+}
+__global__ void k_dp_unpack(const float* __restrict__ recv, int n_ranks, int64_t stride, int64_t n_delta,
+                            float* __restrict__ delta_all, int64_t na, float* __restrict__ a, int64_t nb,
+                            float* __restrict__ b, int64_t nc, float* __restrict__ c) {
+    pdl_sync();
+    const int64_t n_copy = (int64_t)n_ranks * n_delta, n_sum = na + nb + nc;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_copy + n_sum; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < n_copy) {
+            const int64_t r = i / n_delta, k = i - r * n_delta;
+            delta_all[i] = recv[r * stride + k];
+        } else {
+            const int64_t k = i - n_copy;
+            float acc = 0.f;
+            for (int r = 0; r < n_ranks; ++r) acc += recv[(int64_t)r * stride + n_delta + k];
+            if (k < na) a[k] = acc;
+            else if (k < na + nb) b[k - na] = acc;
+            else c[k - na - nb] = acc;
+        }
+    }
+}
+
+int b200vae_dp_pack(float* dst, const float* a, int64_t na, const float* b, int64_t nb, const float* c, int64_t nc,
+                    void* stream) {
+    B200_REQUIRE(dst && na >= 0 && nb >= 0 && nc >= 0, B200VAE_EINVAL, "bad argument");
+    const int64_t n = na + nb + nc;
+    if (n == 0) return 0;
+    B200_CUDA_OK(launch_pdl(k_dp_pack, dim3((unsigned)std::min<int64_t>(cdiv(n, 256), 1184)), dim3(256), 0, (cudaStream_t)stream,
+                            dst, a, na, b, nb, c, nc));
+    return 0;
+}
+
+int b200vae_dp_unpack(const float* recv, int32_t n_ranks, int64_t stride, int64_t n_delta, float* delta_all, float* a,
+                      int64_t na, float* b, int64_t nb, float* c, int64_t nc, void* stream) {
+    B200_REQUIRE(recv && n_ranks >= 1 && stride >= n_delta + na + nb + nc, B200VAE_EINVAL, "bad argument");
+    const int64_t n = (int64_t)n_ranks * n_delta + na + nb + nc;
+    if (n == 0) return 0;
+    B200_CUDA_OK(launch_pdl(k_dp_unpack, dim3((unsigned)std::min<int64_t>(cdiv(n, 256), 2368)), dim3(256), 0, (cudaStream_t)stream,
+                            recv, (int)n_ranks, stride, n_delta, delta_all, na, a, nb, b, nc, c));
+    return 0;
+}
+
 int b200vae_defer_wait_event(b200vae_ctx* ctx, void* event) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     B200_REQUIRE(c, B200VAE_EINVAL, "null context");

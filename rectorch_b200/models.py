@@ -433,8 +433,9 @@ class AETrainer(TorchNNTrainer):
           an all-reduce) -> Adam on the own 1/N shard (1/N of the optimizer's HBM traffic; writes the fp16 image of
           the shard in the same pass) -> ``all_gather`` of the fp16 image (half the bytes of the fp32 weights).
           The next step's K4 waits for that all-gather; its sparse encoder runs beside it.
-        * main stream: the encoder-0 gradient from gathered factors (see ``_step_dp_factors``), one small
-          ``all_reduce`` for the hidden-layer tensors and b_d, replicated Adam on those.
+        * main stream: ONE small ``all_gather`` of a packed record per rank -- the encoder-0 factors (see
+          ``_step_dp_factors``), the hidden-layer and b_d gradients and the loss components -- which every rank then
+          sums in rank order itself (four latency-bound collectives become one); replicated Adam on those tensors.
         * encoder layer 0 (the other item-sized tensor) is sharded by item rows ``j % N == rank``: from the gathered
           factors every rank scatters only into its own rows (1/N of the global batch's scatter instead of all of
           it), runs Adam on them (1/N of that half of the optimizer traffic) and the ranks ``all_gather`` the updated
@@ -447,10 +448,22 @@ class AETrainer(TorchNNTrainer):
         if n_rows != B_local * world:
             raise RuntimeError("replicated RowBatch: %d global rows for %d ranks x %d local rows" % (n_rows, world, B_local))
         step = eng.adam_steps + 1
-        if self._delta_bufs is None or self._delta_bufs[0].shape[0] != B_local or self._delta_bufs[1].shape[0] != n_rows:
-            self._delta_bufs = (torch.empty((B_local, H1), dtype=torch.float32, device=self.device),
-                                torch.empty((n_rows, H1), dtype=torch.float32, device=self.device))
-        mine, everyone = self._delta_bufs
+        lo, hi = self._zero
+        cut = eng.w_off[-1]
+        per = hi - lo
+        n_wd = per * world
+        # one packed record per rank for everything small that crosses ranks: [delta | hidden-layer grads | b_d grad | loss]
+        s_lo = eng.w_off[1] if len(eng.w_off) > 1 else cut
+        b_lo = cut + n_wd
+        n_delta, na, nb = B_local * H1, cut - s_lo, eng.n_elems - b_lo
+        rec = -(-(n_delta + na + nb + 4) // 4) * 4
+        zb = getattr(self, "_zero_bufs", None)
+        if zb is None or zb[0].numel() != rec or zb[2].shape[0] != n_rows:
+            zb = self._zero_bufs = (torch.zeros(rec, dtype=torch.float32, device=self.device),
+                                    torch.empty(rec * world, dtype=torch.float32, device=self.device),
+                                    torch.empty((n_rows, H1), dtype=torch.float32, device=self.device))
+        send, recv, everyone = zb
+        mine = send[:n_delta].view(B_local, H1)
         wd16 = eng.use_external_shadow()
         tm = self._dp_timer
         if tm is not None:
@@ -466,10 +479,6 @@ class AETrainer(TorchNNTrainer):
         eng.forward_backward(B_global=n_rows, step=step, row_offset=0, enc0_delta_out=mine, **kw)
         if tm is not None:
             tm.mark("main: forward + backward")
-        lo, hi = self._zero
-        cut = eng.w_off[-1]
-        per = hi - lo
-        n_wd = per * world
         side = self._comm_stream
         main = torch.cuda.current_stream(self.device)
         if self._wd_event is None:
@@ -485,28 +494,26 @@ class AETrainer(TorchNNTrainer):
             if tm is not None:
                 tm.mark("side: Adam on the W_d shard", side)
             dist.all_gather_into_tensor(wd16[:n_wd], wd16[lo - cut:hi - cut])
-            dist.all_reduce(loss_slot, op=dist.ReduceOp.SUM)
             if tm is not None:
-                tm.mark("side: all_gather fp16 W_d + loss", side)
+                tm.mark("side: all_gather fp16 W_d", side)
             self._wd_event.record(side)
         eng.defer_wait(self._wd_event)
         self._wd_stale = True
         # main stream: exchange the encoder-0 factors and rebuild that gradient for the global batch
+        # ONE small collective on the main stream: all-gather of the packed records, summed locally in rank order
         small = self._pg_small
-        dist.all_gather_into_tensor(everyone, mine, group=small)
+        g_small, g_bd = eng.g[s_lo:cut], eng.g[b_lo:]
+        check(_lib.lib().b200vae_dp_pack(ptr(send[n_delta:]), ptr(g_small), na, ptr(g_bd), nb, ptr(loss_slot), 4, stream_ptr()))
+        dist.all_gather_into_tensor(recv, send, group=small)
+        check(_lib.lib().b200vae_dp_unpack(ptr(recv), world, rec, n_delta, ptr(everyone), ptr(g_small), na, ptr(g_bd), nb,
+                                           ptr(loss_slot), 4, stream_ptr()))
         if tm is not None:
-            tm.mark("main: all_gather delta")
+            tm.mark("main: packed all_gather (delta, hidden-layer / b_d gradients, loss) + local sums")
         eng.enc0_grad(rb.all_rows, everyone, kw["dropout_p"], kw["seed"], step, 0)
         if tm is not None:
             tm.mark("main: encoder-0 gradient of the global batch")
-        s_lo = eng.w_off[1] if len(eng.w_off) > 1 else cut
-        if s_lo < cut:
-            dist.all_reduce(eng.g[s_lo:cut], op=dist.ReduceOp.SUM, group=small)
-        if cut + n_wd < eng.n_elems:        # b_d (and arena padding): replicated like the hidden layers
-            dist.all_reduce(eng.g[cut + n_wd:], op=dist.ReduceOp.SUM, group=small)
-            eng.adam_range(lr, betas, eps, 0.0, 0.0, cut + n_wd, eng.n_elems, first=False)
-        if tm is not None:
-            tm.mark("main: all_reduce hidden layers + b_d")
+        if nb > 0:        # b_d (and arena padding): replicated like the hidden layers
+            eng.adam_range(lr, betas, eps, 0.0, 0.0, b_lo, eng.n_elems, first=False)
         eng.adam_range(lr, betas, eps, 0.0, 0.0, 0, cut, first=False)
         if tm is not None:
             tm.mark("main: Adam (encoder 0 + hidden layers)")
