@@ -395,6 +395,34 @@ k_spmm_scatter(BatchView v, const float* __restrict__ vals, float scale, const f
     }
 }
 
+// Sharded variant (data parallelism, this rank owns the item rows j % mod_n == mod_r): one CTA per USER row keeps the
+// row's delta in registers and walks all of its non-zeros, touching only the owned items -- 1/mod_n of the reductions
+// of the global batch, and one delta load per user instead of one per 32-non-zero segment.
+__global__ void __launch_bounds__(256)
+k_spmm_scatter_owned(BatchView v, const float* __restrict__ vals, float scale, const float* __restrict__ dY, int H,
+                     float* __restrict__ dWt, int mod_n, int mod_r) {
+    pdl_sync();
+    const int r = blockIdx.x;
+    const int64_t gr = v.row_ids ? (int64_t)v.row_ids[r] : (int64_t)r;
+    const int64_t a = v.indptr[gr];
+    const int len = (int)(v.indptr[gr + 1] - a);
+    const int64_t o = v.bp[r];
+    const int32_t* cols = v.indices + a;
+    const float* xv = vals ? vals + o : nullptr;
+    const float* raw = v.values ? v.values + a : nullptr;
+    for (int h0 = threadIdx.x * 4; h0 < H; h0 += blockDim.x * 4) {
+        const float4 d4 = *reinterpret_cast<const float4*>(dY + (int64_t)r * H + h0);
+        const float d[4] = {d4.x * scale, d4.y * scale, d4.z * scale, d4.w * scale};
+        for (int k = 0; k < len; ++k) {
+            const int j = cols[k];
+            if (j % mod_n != mod_r) continue;
+            const float x = xv ? xv[k] : (raw ? raw[k] : 1.f);
+            if (x == 0.f) continue;
+            atomicAdd(reinterpret_cast<float4*>(dWt + (int64_t)j * H + h0), make_float4(x * d[0], x * d[1], x * d[2], x * d[3]));
+        }
+    }
+}
+
 int launch_spmm_scatter(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
                         int H, float* dWt, cudaStream_t s, int mod_n, int mod_r) {
     return launch_spmm_scatter_bias(c, v, vals, scale, dY, H, dWt, nullptr, s, mod_n, mod_r);
@@ -404,6 +432,12 @@ int launch_spmm_scatter_bias(Ctx* c, const BatchView& v, const float* vals, floa
                              int H, float* dWt, float* db, cudaStream_t s, int mod_n, int mod_r) {
     if (v.B == 0) return 0;
     bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(dWt) & 15) == 0);
+    if (mod_n > 1 && vec && !db && ((reinterpret_cast<uintptr_t>(dY) & 15) == 0)) {
+        const int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));
+        B200_CUDA_OK(launch_pdl(k_spmm_scatter_owned, dim3(v.B), dim3(threads), 0, s, v, vals, scale, dY, H, dWt, mod_n, mod_r));
+        note(c, "launch_spmm_scatter_owned", s);
+        return 0;
+    }
     const int grid = spmm_grid(c, v);
     if (vec) {
         int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));
