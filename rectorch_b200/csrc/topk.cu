@@ -5,11 +5,8 @@
 // n_metrics x B floats leave the device.
 //
 // One CTA (256 threads) per user row:
-//   0. (CACHE) the row's order-preserving uint32 keys are read from HBM ONCE into shared memory (n_items <= ~51 K:
-//      200 KB); every later pass reads shared memory.  Longer rows stream from global memory each pass.
-//   1. 4 passes of an 8-bit histogram over the keys narrow down the k-th largest key T and the number of ties at
-//      T to keep.  Each warp counts into its own histogram and lanes with equal bins are merged first
-//      (__match_any_sync): scores share their leading bits, so a plain shared-memory atomicAdd serialises 32-way;
+//   1. 4 passes of an 8-bit histogram over the order-preserving uint32 image of the scores
+//      narrow down the k-th largest key T and the number of ties at T to keep;
 //   2. all keys > T plus the lowest-index ties are compacted into shared memory
 //      (deterministic tie rule: smaller item id first -- argpartition's is unspecified);
 //   3. a bitonic sort of the <=1024 candidates gives the ranked list (needed by ndcg/mrr);
@@ -27,14 +24,11 @@ __device__ __forceinline__ uint32_t f2key(float x) {
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-template <bool CACHE>
 __global__ void __launch_bounds__(TOPK_THREADS)
 k_topk_metrics(const float* __restrict__ scores, int I, BatchView gt, const int32_t* __restrict__ kinds,
                const int32_t* __restrict__ ks, int n_metrics, int kmax, float* __restrict__ out,
                int32_t* __restrict__ topk_idx) {
-    extern __shared__ uint32_t s_keys[];           // CACHE: [I] keys of the row
     __shared__ unsigned int hist[256];
-    __shared__ unsigned int whist[TOPK_THREADS / 32][256];
     __shared__ unsigned long long cand[TOPK_MAX];
     __shared__ float hitval[TOPK_MAX];
     __shared__ uint32_t s_prefix, s_remaining;
@@ -44,43 +38,18 @@ k_topk_metrics(const float* __restrict__ scores, int I, BatchView gt, const int3
     const int r = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float* row = scores + (int64_t)r * I;
-    if (CACHE) {
-        if ((I & 3) == 0 && ((reinterpret_cast<uintptr_t>(row) & 15) == 0)) {
-            for (int j = tid; j < (I >> 2); j += TOPK_THREADS) {
-                const float4 t = __ldcs(reinterpret_cast<const float4*>(row) + j);
-                reinterpret_cast<uint4*>(s_keys)[j] = make_uint4(f2key(t.x), f2key(t.y), f2key(t.z), f2key(t.w));
-            }
-        } else {
-            for (int j = tid; j < I; j += TOPK_THREADS) s_keys[j] = f2key(row[j]);
-        }
-        __syncthreads();
-    }
-    auto key_at = [&](int j) -> uint32_t { return CACHE ? s_keys[j] : f2key(row[j]); };
 
     // ---- 1. radix select ------------------------------------------------------------------
     if (tid == 0) { s_prefix = 0; s_remaining = (uint32_t)kmax; }
     uint32_t mask = 0;
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
-        for (int b = lane; b < 256; b += 32) whist[wid][b] = 0;
+        hist[tid] = 0;
         __syncthreads();
         const uint32_t prefix = s_prefix;
-        for (int j0 = 0; j0 < I; j0 += TOPK_THREADS) {          // uniform trip count: full-warp match below
-            const int j = j0 + tid;
-            uint32_t bin = 0xFFFFFFFFu;
-            if (j < I) {
-                const uint32_t u = key_at(j);
-                if ((u & mask) == prefix) bin = (u >> shift) & 255u;
-            }
-            const unsigned int same = __match_any_sync(0xffffffffu, bin);
-            if (bin != 0xFFFFFFFFu && lane == __ffs(same) - 1) atomicAdd(&whist[wid][bin], (unsigned int)__popc(same));
-        }
-        __syncthreads();
-        {
-            unsigned int acc = 0;
-#pragma unroll
-            for (int w = 0; w < TOPK_THREADS / 32; ++w) acc += whist[w][tid];
-            hist[tid] = acc;
+        for (int j = tid; j < I; j += TOPK_THREADS) {
+            uint32_t u = f2key(row[j]);
+            if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
         }
         __syncthreads();
         if (tid == 0) {
@@ -106,7 +75,7 @@ k_topk_metrics(const float* __restrict__ scores, int I, BatchView gt, const int3
     __syncthreads();
     // keys strictly above T: any order, the sort fixes it
     for (int j = tid; j < I; j += TOPK_THREADS) {
-        uint32_t u = key_at(j);
+        uint32_t u = f2key(row[j]);
         if (u > T) {
             unsigned int p = atomicAdd(&s_count, 1u);
             cand[p] = ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)j);
@@ -119,7 +88,7 @@ k_topk_metrics(const float* __restrict__ scores, int I, BatchView gt, const int3
     unsigned int my_ties = 0;
     for (int j0 = lo; j0 < hi; j0 += 32) {
         int j = j0 + lane;
-        bool is = (j < hi) && (key_at(j) == T);
+        bool is = (j < hi) && (f2key(row[j]) == T);
         my_ties += __popc(__ballot_sync(0xffffffffu, is));
     }
     if (lane == 0) warp_ties[wid] = my_ties;
@@ -133,7 +102,7 @@ k_topk_metrics(const float* __restrict__ scores, int I, BatchView gt, const int3
         unsigned int pos = warp_ties[wid];
         for (int j0 = lo; j0 < hi && pos < n_ties; j0 += 32) {
             int j = j0 + lane;
-            bool is = (j < hi) && (key_at(j) == T);
+            bool is = (j < hi) && (f2key(row[j]) == T);
             unsigned int m = __ballot_sync(0xffffffffu, is);
             if (is) {
                 unsigned int p = pos + __popc(m & ((1u << lane) - 1u));
@@ -228,18 +197,7 @@ int launch_topk_metrics(Ctx* c, const float* scores, int I, const BatchView& gt,
     B200_REQUIRE(kmax >= 1 && kmax <= TOPK_MAX && kmax <= I, B200VAE_EINVAL,
                  "topk: k must be in [1, min(%d, n_items)] (got %d)", TOPK_MAX, kmax);
     B200_REQUIRE(n_metrics <= TOPK_THREADS, B200VAE_EINVAL, "topk: too many metrics");
-    // rows that fit next to the kernel's static buffers are cached in shared memory (one HBM read per row)
-    constexpr int64_t CACHE_MAX_BYTES = 200 * 1024;
-    if ((int64_t)I * 4 <= CACHE_MAX_BYTES) {
-        static bool attr = false;
-        if (!attr) {
-            B200_CUDA_OK(cudaFuncSetAttribute(k_topk_metrics<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CACHE_MAX_BYTES));
-            attr = true;
-        }
-        k_topk_metrics<true><<<gt.B, TOPK_THREADS, (size_t)round_up((int64_t)I * 4, 16), s>>>(scores, I, gt, kinds, ks, n_metrics, kmax, out, topk_idx);
-    } else {
-        k_topk_metrics<false><<<gt.B, TOPK_THREADS, 0, s>>>(scores, I, gt, kinds, ks, n_metrics, kmax, out, topk_idx);
-    }
+    k_topk_metrics<<<gt.B, TOPK_THREADS, 0, s>>>(scores, I, gt, kinds, ks, n_metrics, kmax, out, topk_idx);
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
