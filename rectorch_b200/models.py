@@ -525,6 +525,20 @@ class AETrainer(TorchNNTrainer):
             if tm is not None:
                 tm.mark("main: all_gather fp16 encoder-0 rows")
 
+    def _valid_stats(self, valid_res):
+        """Mean and standard error of the per-user validation metric.  Under data parallelism every rank evaluates
+        its own shard of the validation users: the sums are all-reduced so that every rank logs / compares the same
+        numbers (and takes the same best-checkpoint decision)."""
+        res = np.asarray(valid_res, dtype=np.float64)
+        n, s1, s2 = float(res.size), float(np.nansum(res)), float(np.nansum(res * res))
+        if _dist_world()[1] > 1:
+            t = torch.tensor([n, s1, s2], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            n, s1, s2 = t.tolist()
+        mu = s1 / max(n, 1.0)
+        var = max(s2 / max(n, 1.0) - mu * mu, 0.0)
+        return mu, np.sqrt(var) / np.sqrt(max(n, 1.0))
+
     def _loss_from(self, comps, beta, lam):
         """Python float loss from the 4 device components (sum over ranks already applied)."""
         c = comps.tolist()
@@ -543,8 +557,7 @@ class AETrainer(TorchNNTrainer):
                     assert valid_metric is not None, \
                         "In case of validation 'valid_metric' must be provided"
                     valid_res = valid_func(self, valid_data, valid_metric)
-                    mu_val = np.mean(valid_res)
-                    std_err_val = np.std(valid_res) / np.sqrt(len(valid_res))
+                    mu_val, std_err_val = self._valid_stats(valid_res)
                     logger.info('| epoch %d | %s %.3f (%.4f) |', epoch, valid_metric, mu_val, std_err_val)
         except KeyboardInterrupt:
             logger.warning('Handled KeyboardInterrupt: exiting from training early')
@@ -791,8 +804,7 @@ class MultiVAE(AETrainer):
                     assert valid_metric is not None, \
                         "In case of validation 'valid_metric' must be provided"
                     valid_res = valid_func(self, valid_data, valid_metric)
-                    mu_val = np.mean(valid_res)
-                    std_err_val = np.std(valid_res) / np.sqrt(len(valid_res))
+                    mu_val, std_err_val = self._valid_stats(valid_res)
                     logger.info('| epoch %d | %s %.3f (%.4f) |', epoch, valid_metric, mu_val, std_err_val)
                     if best_perf < mu_val:
                         self.save_model(best_path, epoch)
