@@ -296,6 +296,11 @@ int  b200vae_dec_fwd_lse(b200vae_ctx* ctx, const void* h16, const void* W16, con
  * be separated from their work. */
 int  b200vae_probe_launch(int grid, int threads, int smem_bytes, int cluster, void* stream);
 
+/* Deterministic mode (what torch.use_deterministic_algorithms(True) asks of the reference's torch ops): the
+ * sparse encoder-0 product and its gradient (the only floating-point atomics of the step) run as ordered
+ * per-row / per-item reductions, so two runs of the same steps give bit-identical weights.  Slower; off by default. */
+int b200vae_set_deterministic(b200vae_ctx* ctx, int enable);
+
 /* Introspection for bench.py: kernels launched by this context since the last reset. */
 int64_t b200vae_launch_count(b200vae_ctx* ctx, int reset);
 

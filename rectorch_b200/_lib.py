@@ -90,6 +90,7 @@ _SIGS = {
     "b200vae_probe_launch": (c_int, [c_int, c_int, c_int, c_int, c_void_p]),
     "b200vae_launch_count": (c_int64, [c_void_p, c_int]),
     "b200vae_set_timing": (c_int, [c_void_p, c_int]),
+    "b200vae_set_deterministic": (c_int, [c_void_p, c_int]),
     "b200vae_kernel_ms": (c_float, [c_void_p, c_int]),
     "b200vae_timing_report": (c_int, [c_void_p, c_char_p, c_int]),
     "b200vae_build_cond_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
@@ -138,6 +139,7 @@ def ptr(t):
     return c_void_p(t.data_ptr())
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """The caller's current torch stream on `device` (default: the current device)."""
     import torch
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)

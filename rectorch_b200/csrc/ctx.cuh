@@ -19,6 +19,20 @@ struct CsrSlot {
     int32_t* sp = nullptr;           // [max_batch+1] segment pointer for the current batch
 };
 
+// Makes the context's device current for the duration of an API call and restores the caller's afterwards (a process
+// that drives several GPUs must not find its current device changed behind its back).
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        if (dev < 0) return;
+        int cur = -1;
+        if (cudaGetDevice(&cur) == cudaSuccess && cur != dev && cudaSetDevice(dev) == cudaSuccess) prev = cur;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 struct Ctx {
     b200vae_config cfg;
     int num_sms = 0;
@@ -79,6 +93,14 @@ struct Ctx {
     __half* dbuf16[2] = {nullptr, nullptr};   // fp16 images of the ping-pong activation gradients, pitch ld_d16
     int ld_d16 = 0;
     int32_t* d_specs = nullptr;       // [128] metric specs for topk
+    // deterministic mode (b200vae_set_deterministic): sparse gather / scatter without floating-point atomics
+    bool deterministic = false;
+    int det_rows = 0;                 // max(encoder-0 input width, n_items)
+    int* det_count = nullptr;         // [det_rows + 1] per-item non-zero counts of the batch
+    int* det_off = nullptr;           // [det_rows + 1] their exclusive scan
+    int* det_cursor = nullptr;        // [det_rows + 1]
+    int64_t* det_ent = nullptr;       // [max_batch_nnz] (row << 32 | position) per item, fill order
+    int64_t* det_sorted = nullptr;    // [max_batch_nnz] the same, ascending per item
     float* spmm_acc = nullptr;        // [B x max(width)] zeroed accumulator for multi-segment gathers
     int*   spmm_ticket = nullptr;     // [B] zeroed per-row completion tickets
     float* dbuf[2] = {nullptr, nullptr};  // [B x max_width] ping-pong activation gradients

@@ -111,6 +111,7 @@ static void free_ctx(Ctx* c) {
     F(c->ws16); F(c->z16); F(c->dbuf16[0]); F(c->dbuf16[1]);
     for (__half* p : c->act_enc16) F(p);
     for (__half* p : c->act_dec16) F(p); F(c->spmm_acc); F(c->spmm_ticket);
+    F(c->det_count); F(c->det_off); F(c->det_cursor); F(c->det_ent); F(c->det_sorted);
     for (int i = 0; i < 5; ++i)
         for (int j = 0; j < 2; ++j) cudaEventDestroy(c->ev[i][j]);
     for (cudaEvent_t e : c->tev) cudaEventDestroy(e);
@@ -750,7 +751,7 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     int ndev = 0;
     B200_CUDA_OK(cudaGetDeviceCount(&ndev));
     B200_REQUIRE(cfg->device >= 0 && cfg->device < ndev, B200VAE_EINVAL, "no such CUDA device %d", cfg->device);
-    B200_CUDA_OK(cudaSetDevice(cfg->device));
+    DeviceGuard dev_guard(cfg->device);
     cudaDeviceProp prop;
     B200_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
     B200_REQUIRE(prop.major == 10, B200VAE_ECUDA,
@@ -883,7 +884,7 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
 int b200vae_ctx_destroy(b200vae_ctx* ctx) {
     if (!ctx) return 0;
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
-    cudaSetDevice(c->cfg.device);
+    DeviceGuard dev_guard(c->cfg.device);
     cudaDeviceSynchronize();
     free_ctx(c);
     return 0;
@@ -892,6 +893,7 @@ int b200vae_ctx_destroy(b200vae_ctx* ctx) {
 int b200vae_bind_params(b200vae_ctx* ctx, float* w, float* g, float* m, float* v, int64_t n_elems,
                         const int64_t* w_off, const int64_t* b_off) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     B200_REQUIRE(c && w && g && m && v && w_off && b_off, B200VAE_EINVAL, "null argument");
     c->w = w; c->g = g; c->m = m; c->v = v; c->n_elems = n_elems;
     c->toff.clear(); c->tlen.clear();
@@ -930,6 +932,7 @@ int b200vae_bind_params(b200vae_ctx* ctx, float* w, float* g, float* m, float* v
 int b200vae_bind_csr(b200vae_ctx* ctx, int slot, const int64_t* indptr, const int32_t* indices,
                      const float* values, int64_t n_rows) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     B200_REQUIRE(c && (slot == 0 || slot == 1), B200VAE_EINVAL, "bad slot");
     B200_REQUIRE(indptr && (indices || n_rows == 0), B200VAE_EINVAL, "null CSR arrays");
     c->slot[slot].indptr = indptr;
@@ -941,6 +944,7 @@ int b200vae_bind_csr(b200vae_ctx* ctx, int slot, const int64_t* indptr, const in
 
 int b200vae_dense_to_csr(b200vae_ctx* ctx, int slot, const float* dense, int32_t B, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     cudaStream_t s = (cudaStream_t)stream;
     B200_REQUIRE(c && dense && (slot == 0 || slot == 1), B200VAE_EINVAL, "bad argument");
     B200_REQUIRE(B >= 1 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
@@ -956,6 +960,7 @@ int b200vae_dense_to_csr(b200vae_ctx* ctx, int slot, const float* dense, int32_t
 int b200vae_build_cond_batch(b200vae_ctx* ctx, const int32_t* ex_rows, const int32_t* ex_conds, int32_t B,
                              const uint64_t* item_cond_mask, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     B200_REQUIRE(c && ex_rows && ex_conds && item_cond_mask, B200VAE_EINVAL, "null argument");
     B200_REQUIRE(B >= 1 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
     B200_REQUIRE(c->cfg.cond_dim >= 1, B200VAE_ESTATE, "the network has no condition inputs (cond_dim == 0)");
@@ -965,6 +970,7 @@ int b200vae_build_cond_batch(b200vae_ctx* ctx, const int32_t* ex_rows, const int
 
 int b200vae_expand_batch(b200vae_ctx* ctx, int slot, const int32_t* row_ids, int32_t B, float* out, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     cudaStream_t s = (cudaStream_t)stream;
     B200_REQUIRE(c && out && (slot == 0 || slot == 1), B200VAE_EINVAL, "bad argument");
     B200_REQUIRE(B >= 0 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
@@ -979,6 +985,7 @@ int b200vae_forward_backward(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B
                              uint64_t step, int64_t row_offset, const uint8_t* keep_tape,
                              const float* eps_tape, float* loss_out, float* enc0_delta_out, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     B200_REQUIRE(c && loss_out, B200VAE_EINVAL, "null argument");
     B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, B200VAE_EINVAL, "dropout_p must be in [0,1)");
     return forward_backward(c, row_ids, B, B_global, use_target, beta, lam, dropout_p, seed, step, row_offset,
@@ -993,6 +1000,7 @@ int b200vae_enc0_grad(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B_total,
     // (same Philox keys as the forward pass of the rank that owns them) and scattered against the gathered
     // delta rows.  delta [B_total x H1] already carries the 1/B_global factor.
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     cudaStream_t s = (cudaStream_t)stream;
     B200_REQUIRE(c && row_ids && delta && B_total >= 1, B200VAE_EINVAL, "bad argument");
     B200_REQUIRE(c->params_bound && c->slot[0].indptr, B200VAE_ESTATE, "parameters / CSR slot 0 are not bound");
@@ -1028,6 +1036,7 @@ int b200vae_enc0_grad(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B_total,
 int b200vae_adam_step_range(b200vae_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay,
                             float lam, int64_t step, int64_t elem_lo, int64_t elem_hi, int narrow, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     B200_REQUIRE(c, B200VAE_EINVAL, "null context");
     AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
     return adam_step(c, h, (cudaStream_t)stream, elem_lo, elem_hi, ADAM_ROWS_ALL, narrow ? c->side_ctas[0] : 8);
@@ -1035,6 +1044,7 @@ int b200vae_adam_step_range(b200vae_ctx* ctx, float lr, float beta1, float beta2
 
 int b200vae_bind_shadow(b200vae_ctx* ctx, void* wd16, int64_t n_halfs) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     B200_REQUIRE(c && wd16, B200VAE_EINVAL, "null argument");
     if (!c->tc_dec) return 0;                       // the SIMT path keeps no image
     const Layer& DL = c->dec.back();
@@ -1049,6 +1059,7 @@ int b200vae_bind_shadow(b200vae_ctx* ctx, void* wd16, int64_t n_halfs) {
 
 int b200vae_set_w1_sharding(b200vae_ctx* ctx, void* w1_gathered, int32_t mod_n, int32_t mod_r) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     B200_REQUIRE(c, B200VAE_EINVAL, "null context");
     if (!w1_gathered || mod_n <= 1) {
         c->w1g = nullptr; c->w1_mod_n = 1; c->w1_mod_r = 0; c->w1_rows_per = 0;
@@ -1065,6 +1076,7 @@ int b200vae_w1_rows(b200vae_ctx* ctx, float* arena_base, float* packed, int dire
     // direction 0: packed[rows_per x H1] <- this rank's rows of the encoder-0 tensor inside `arena_base` (w, m or v arena)
     // direction 1: every row of that tensor <- packed_all [mod_n][rows_per x H1] (an all-gathered buffer)
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     B200_REQUIRE(c && arena_base && packed && c->w1_mod_n > 1 && c->params_bound, B200VAE_ESTATE, "encoder-0 sharding is not enabled");
     const Layer& E0 = c->enc[0];
     const int64_t n = (int64_t)E0.in * E0.out;
@@ -1131,6 +1143,7 @@ int b200vae_dp_unpack(const float* recv, int32_t n_ranks, int64_t stride, int64_
 
 int b200vae_defer_wait_event(b200vae_ctx* ctx, void* event) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     B200_REQUIRE(c, B200VAE_EINVAL, "null context");
     c->wd16_pending = reinterpret_cast<cudaEvent_t>(event);
     return 0;
@@ -1140,6 +1153,7 @@ int b200vae_sync_weights(b200vae_ctx* ctx, void* stream) {
     // refresh every derived copy of the parameters (the fp16 image of W_d read by the tensor cores);
     // call after the weight arena was modified by anything other than b200vae_adam_step
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     B200_REQUIRE(c && c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
     if (c->w1_mod_n > 1) {      // the gathered copy of the encoder-0 weight, from the (complete) arena
         const Layer& E0 = c->enc[0];
@@ -1159,6 +1173,7 @@ int b200vae_sync_weights(b200vae_ctx* ctx, void* stream) {
 int b200vae_adam_step(b200vae_ctx* ctx, float lr, float beta1, float beta2, float eps, float weight_decay,
                       float lam, int64_t step, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     B200_REQUIRE(c, B200VAE_EINVAL, "null context");
     AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
     return adam_step(c, h, (cudaStream_t)stream);
@@ -1170,6 +1185,7 @@ int b200vae_adam_step_split(b200vae_ctx* ctx, float lr, float beta1, float beta2
     // The Adam schedule of the fused step on caller-provided gradients: rows of the encoder-0 weight listed in
     // `touched_items` are the only ones whose gradient may be non-zero.
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     cudaStream_t s = (cudaStream_t)stream;
     B200_REQUIRE(c && (touched_items || n_touched == 0) && n_touched >= 0, B200VAE_EINVAL, "bad argument");
     B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
@@ -1200,6 +1216,7 @@ int b200vae_train_step(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int 
                        const float* eps_tape, float lr, float beta1, float beta2, float eps, float weight_decay,
                        float* loss_out, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     B200_REQUIRE(c && loss_out, B200VAE_EINVAL, "null argument");
     B200_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, B200VAE_EINVAL, "dropout_p must be in [0,1)");
     AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
@@ -1272,6 +1289,7 @@ int b200vae_train_step_host(b200vae_ctx* ctx, const int64_t* indptr_host, const 
                             uint64_t seed, int64_t step, float lr, float weight_decay, float* loss_host,
                             void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     cudaStream_t s = (cudaStream_t)stream;
     B200_REQUIRE(c && indptr_host && indices_host && loss_host, B200VAE_EINVAL, "null argument");
     B200_REQUIRE(B >= 1 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
@@ -1295,6 +1313,7 @@ int b200vae_predict(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int rem
                     float dropout_p, uint64_t seed, uint64_t step, float* scores, float* mu, float* logvar,
                     void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     B200_REQUIRE(c, B200VAE_EINVAL, "null context");
     return predict(c, row_ids, B, remove_train, train_mode, dropout_p, seed, step, scores, mu, logvar, (cudaStream_t)stream);
 }
@@ -1302,6 +1321,7 @@ int b200vae_predict(b200vae_ctx* ctx, const int32_t* row_ids, int32_t B, int rem
 int b200vae_decode(b200vae_ctx* ctx, const float* z, int32_t B, float* scores, void* stream) {
     // AE_net.decode(z) (nets.py:227-233, 413-417): decoder layers on a caller-provided latent batch
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     cudaStream_t s = (cudaStream_t)stream;
     B200_REQUIRE(c && z && scores, B200VAE_EINVAL, "null argument");
     B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
@@ -1327,6 +1347,7 @@ int b200vae_topk_metrics(b200vae_ctx* ctx, const float* scores, const int32_t* g
                          int32_t* topk_idx, void* stream) {
     // kinds / ks are HOST arrays (a handful of ints); they are staged through the context
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     cudaStream_t s = (cudaStream_t)stream;
     B200_REQUIRE(c && scores && kinds && ks && out && n_metrics >= 1 && n_metrics <= 64, B200VAE_EINVAL, "bad argument");
     B200_REQUIRE(B >= 1 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
@@ -1347,6 +1368,7 @@ int b200vae_topk_metrics(b200vae_ctx* ctx, const float* scores, const int32_t* g
 int b200vae_gemm_f16(b200vae_ctx* ctx, const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
                      int b_mn_major, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     B200_REQUIRE(c && A && B && C, B200VAE_EINVAL, "null argument");
     TcEpi e;
     return launch_tc_gemm(c, TC_EPI_STORE, A, lda, a_mn_major, B, ldb, b_mn_major, C, ldc, M, N, K, e, (cudaStream_t)stream);
@@ -1355,6 +1377,7 @@ int b200vae_gemm_f16(b200vae_ctx* ctx, const void* A, int64_t lda, int a_mn_majo
 int b200vae_dec_fwd_lse(b200vae_ctx* ctx, const void* h16, const void* W16, const float* bias, int32_t B,
                         int32_t n_items, int32_t H, float* lse, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     cudaStream_t s = (cudaStream_t)stream;
     B200_REQUIRE(c && h16 && W16, B200VAE_EINVAL, "null argument");
     B200_REQUIRE(B <= c->cfg.max_batch && n_items <= c->n_items, B200VAE_ECAPACITY, "exceeds context capacity");
@@ -1402,14 +1425,35 @@ int b200vae_probe_launch(int grid, int threads, int smem_bytes, int cluster, voi
 
 int64_t b200vae_launch_count(b200vae_ctx* ctx, int reset) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     if (!c) return -1;
     int64_t n = c->launches;
     if (reset) c->launches = 0;
     return n;
 }
 
+int b200vae_set_deterministic(b200vae_ctx* ctx, int enable) {
+    Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
+    if (!c) return B200VAE_EINVAL;
+    if (enable && !c->det_count) {
+        c->det_rows = std::max(c->enc_in, c->dec.back().out);
+        const size_t n = (size_t)c->det_rows + 1, cap = (size_t)std::max<int64_t>(c->cfg.max_batch_nnz, 1);
+        if (cudaMalloc(&c->det_count, n * sizeof(int)) != cudaSuccess || cudaMalloc(&c->det_off, n * sizeof(int)) != cudaSuccess ||
+            cudaMalloc(&c->det_cursor, n * sizeof(int)) != cudaSuccess || cudaMalloc(&c->det_ent, cap * sizeof(int64_t)) != cudaSuccess ||
+            cudaMalloc(&c->det_sorted, cap * sizeof(int64_t)) != cudaSuccess)
+        {
+            set_error("deterministic mode: workspace allocation failed");
+            return B200VAE_ECUDA;
+        }
+    }
+    c->deterministic = enable != 0;
+    return 0;
+}
+
 int b200vae_set_timing(b200vae_ctx* ctx, int enable) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     if (!c) return B200VAE_EINVAL;
     c->timing = enable != 0;
     return 0;
@@ -1417,6 +1461,7 @@ int b200vae_set_timing(b200vae_ctx* ctx, int enable) {
 
 float b200vae_kernel_ms(b200vae_ctx* ctx, int which) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     if (!c || which < 0 || which >= 5 || !c->ev_valid[which]) return -1.f;
     float ms = -1.f;
     if (cudaEventElapsedTime(&ms, c->ev[which][0], c->ev[which][1]) != cudaSuccess) return -1.f;
@@ -1426,6 +1471,7 @@ float b200vae_kernel_ms(b200vae_ctx* ctx, int which) {
 int b200vae_timing_report(b200vae_ctx* ctx, char* buf, int cap) {
     // "name ms\n" per launch of the most recent instrumented step (valid after a stream sync)
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     if (!c || !buf || cap <= 0) return B200VAE_EINVAL;
     int pos = 0;
     buf[0] = 0;
@@ -1441,6 +1487,7 @@ int b200vae_timing_report(b200vae_ctx* ctx, char* buf, int cap) {
 
 int b200vae_wait_wd_ready(b200vae_ctx* ctx, void* stream) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     B200_REQUIRE(c, B200VAE_EINVAL, "null context");
     B200_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, c->ev_wd, 0));
     return 0;
@@ -1449,6 +1496,7 @@ int b200vae_wait_wd_ready(b200vae_ctx* ctx, void* stream) {
 int b200vae_check_error_flag(b200vae_ctx* ctx) {
     // device-side capacity overflow flag (set by the scan kernels); synchronises the device
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
+    DeviceGuard dev_guard(c ? c->cfg.device : -1);
     if (!c) return B200VAE_EINVAL;
     int flag = 0;
     B200_CUDA_OK(cudaMemcpy(&flag, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));

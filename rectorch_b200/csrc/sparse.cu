@@ -222,16 +222,17 @@ __global__ void __launch_bounds__(256)
 k_spmm_gather(BatchView v, const float* __restrict__ vals, const float* __restrict__ Wt, int H,
               const float* __restrict__ bias, int act, float* __restrict__ out, float* __restrict__ acc_ws,
               int* __restrict__ ticket, __half* __restrict__ out16, int64_t ld16, const __half* __restrict__ Wt16, int mod_n,
-              int64_t rows_per) {
+              int64_t rows_per, int det) {
     pdl_sync();
-    if ((int)blockIdx.x >= v.sp[v.B]) return;
-    const int r = find_row(v.sp, v.B, blockIdx.x);
-    const int seg = blockIdx.x - v.sp[r];
-    const int nseg = v.sp[r + 1] - v.sp[r];
+    // det: one CTA per row walks every non-zero in index order (no cross-segment reduction, so no atomics)
+    if (!det && (int)blockIdx.x >= v.sp[v.B]) return;
+    const int r = det ? (int)blockIdx.x : find_row(v.sp, v.B, blockIdx.x);
+    const int seg = det ? 0 : blockIdx.x - v.sp[r];
+    const int nseg = det ? 1 : v.sp[r + 1] - v.sp[r];
     const int64_t gr = v.row_ids ? (int64_t)v.row_ids[r] : (int64_t)r;
     const int64_t a = v.indptr[gr];
     const int len = (int)(v.indptr[gr + 1] - a);
-    const int k0 = seg * SPMM_SEG, k1 = min(len, k0 + SPMM_SEG);
+    const int k0 = seg * SPMM_SEG, k1 = det ? len : min(len, k0 + SPMM_SEG);
     const int64_t o = v.bp[r];
     const int32_t* cols = v.indices + a;
     const float* xv = vals ? vals + o : nullptr;
@@ -335,15 +336,16 @@ int launch_spmm_gather(Ctx* c, const BatchView& v, const float* vals, const floa
                        const __half* Wt16, int mod_n, int64_t rows_per) {
     if (v.B == 0) return 0;
     bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(Wt) & 15) == 0);
-    const int grid = spmm_grid(c, v);
+    const int det = c->deterministic ? 1 : 0;
+    const int grid = det ? v.B : spmm_grid(c, v);
     if (vec) {
         int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));
         B200_CUDA_OK(launch_pdl(k_spmm_gather<4>, dim3(grid), dim3(threads), 0, s, v, vals, Wt, H, bias, act, out, c->spmm_acc,
-                                c->spmm_ticket, out16, ld16, Wt16, mod_n, rows_per));
+                                c->spmm_ticket, out16, ld16, Wt16, mod_n, rows_per, det));
     } else {
         int threads = (int)std::min<int64_t>(256, round_up(H, 32));
         B200_CUDA_OK(launch_pdl(k_spmm_gather<1>, dim3(grid), dim3(threads), 0, s, v, vals, Wt, H, bias, act, out, c->spmm_acc,
-                                c->spmm_ticket, out16, ld16, Wt16, mod_n, rows_per));
+                                c->spmm_ticket, out16, ld16, Wt16, mod_n, rows_per, det));
     }
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
@@ -423,6 +425,123 @@ k_spmm_scatter_owned(BatchView v, const float* __restrict__ vals, float scale, c
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Deterministic scatter (b200vae_set_deterministic): the batch is transposed into per-item lists (integer counting,
+// a single-CTA scan, a cursor fill whose order is then fixed by ranking the (row, position) keys), and one warp per
+// item adds its contributions in ascending (row, position) order with plain stores.  Bit-identical from run to run;
+// several times slower than the atomic version, so it is opt-in.
+// ------------------------------------------------------------------------------------------
+__global__ void k_det_count(BatchView v, const float* __restrict__ vals, int n_rows, int* __restrict__ count) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= v.B) return;
+    const int64_t gr = v.row_ids ? (int64_t)v.row_ids[warp] : (int64_t)warp;
+    const int64_t a = v.indptr[gr];
+    const int len = (int)(v.indptr[gr + 1] - a);
+    const float* xv = vals ? vals + v.bp[warp] : nullptr;
+    const float* raw = v.values ? v.values + a : nullptr;
+    for (int k = lane; k < len; k += 32) {
+        const float x = xv ? xv[k] : (raw ? raw[k] : 1.f);
+        const int j = v.indices[a + k];
+        if (x != 0.f && j < n_rows) atomicAdd(count + j, 1);   // integer: the RESULT does not depend on the order
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_det_scan(const int* __restrict__ count, int n_rows, int* __restrict__ off) {
+    __shared__ int s_part[1024];
+    const int per = (n_rows + 1023) / 1024;
+    const int lo = min(n_rows, (int)threadIdx.x * per), hi = min(n_rows, lo + per);
+    int sum = 0;
+    for (int j = lo; j < hi; ++j) sum += count[j];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        int t = (threadIdx.x >= d) ? s_part[threadIdx.x - d] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    int run = s_part[threadIdx.x] - sum;
+    for (int j = lo; j < hi; ++j) { off[j] = run; run += count[j]; }
+    if (threadIdx.x == 1023) off[n_rows] = s_part[1023];
+}
+
+__global__ void k_det_fill(BatchView v, const float* __restrict__ vals, int n_rows, const int* __restrict__ off,
+                           int* __restrict__ cursor, int64_t* __restrict__ ent) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= v.B) return;
+    const int64_t gr = v.row_ids ? (int64_t)v.row_ids[warp] : (int64_t)warp;
+    const int64_t a = v.indptr[gr];
+    const int len = (int)(v.indptr[gr + 1] - a);
+    const float* xv = vals ? vals + v.bp[warp] : nullptr;
+    const float* raw = v.values ? v.values + a : nullptr;
+    for (int k = lane; k < len; k += 32) {
+        const float x = xv ? xv[k] : (raw ? raw[k] : 1.f);
+        const int j = v.indices[a + k];
+        if (x != 0.f && j < n_rows) ent[off[j] + atomicAdd(cursor + j, 1)] = ((int64_t)warp << 32) | (uint32_t)k;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_det_reduce(BatchView v, const float* __restrict__ vals, float scale, const float* __restrict__ dY, int H, int n_rows,
+             const int* __restrict__ off, const int64_t* __restrict__ ent, int64_t* __restrict__ sorted,
+             float* __restrict__ dWt, float* __restrict__ db, int mod_n, int mod_r) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j >= n_rows) return;
+    if (mod_n > 1 && j % mod_n != mod_r) return;
+    const int o = off[j], n = off[j + 1] - o;
+    if (n == 0) return;
+    // fix the order: rank of each key among the item's keys (keys are distinct)
+    for (int i = lane; i < n; i += 32) {
+        const int64_t key = ent[o + i];
+        int rank = 0;
+        for (int q = 0; q < n; ++q) rank += (ent[o + q] < key);
+        sorted[o + rank] = key;
+    }
+    __syncwarp();
+    float bsum = 0.f;
+    for (int h0 = lane; h0 < H; h0 += 32 * 8) {
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int q = 0; q < n; ++q) {
+            const int64_t key = sorted[o + q];
+            const int r = (int)(key >> 32), k = (int)(key & 0xffffffff);
+            const int64_t gr = v.row_ids ? (int64_t)v.row_ids[r] : (int64_t)r;
+            const float x = vals ? vals[v.bp[r] + k] : (v.values ? v.values[v.indptr[gr] + k] : 1.f);
+            if (h0 == lane) bsum += scale * x;
+            const float* d = dY + (int64_t)r * H;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int h = h0 + 32 * i;
+                if (h < H) acc[i] += x * (d[h] * scale);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int h = h0 + 32 * i;
+            if (h < H) dWt[(int64_t)j * H + h] += acc[i];
+        }
+    }
+    if (db && lane == 0) db[j] += bsum;
+}
+
+static int launch_spmm_scatter_det(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY, int H,
+                                   float* dWt, float* db, cudaStream_t s, int mod_n, int mod_r) {
+    const int n_rows = c->det_rows;
+    B200_CUDA_OK(cudaMemsetAsync(c->det_count, 0, (size_t)(n_rows + 1) * sizeof(int), s));
+    B200_CUDA_OK(cudaMemsetAsync(c->det_cursor, 0, (size_t)(n_rows + 1) * sizeof(int), s));
+    const int wgrid = (int)cdiv((int64_t)v.B * 32, 256);
+    k_det_count<<<wgrid, 256, 0, s>>>(v, vals, n_rows, c->det_count);
+    k_det_scan<<<1, 1024, 0, s>>>(c->det_count, n_rows, c->det_off);
+    k_det_fill<<<wgrid, 256, 0, s>>>(v, vals, n_rows, c->det_off, c->det_cursor, c->det_ent);
+    k_det_reduce<<<(int)cdiv((int64_t)n_rows * 32, 256), 256, 0, s>>>(v, vals, scale, dY, H, n_rows, c->det_off, c->det_ent,
+                                                                   c->det_sorted, dWt, db, mod_n, mod_r);
+    note(c, __func__, s);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int launch_spmm_scatter(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
                         int H, float* dWt, cudaStream_t s, int mod_n, int mod_r) {
     return launch_spmm_scatter_bias(c, v, vals, scale, dY, H, dWt, nullptr, s, mod_n, mod_r);
@@ -431,6 +550,7 @@ int launch_spmm_scatter(Ctx* c, const BatchView& v, const float* vals, float sca
 int launch_spmm_scatter_bias(Ctx* c, const BatchView& v, const float* vals, float scale, const float* dY,
                              int H, float* dWt, float* db, cudaStream_t s, int mod_n, int mod_r) {
     if (v.B == 0) return 0;
+    if (c->deterministic) return launch_spmm_scatter_det(c, v, vals, scale, dY, H, dWt, db, s, mod_n, mod_r);
     bool vec = (H % 4 == 0) && ((reinterpret_cast<uintptr_t>(dWt) & 15) == 0);
     if (mod_n > 1 && vec && !db && ((reinterpret_cast<uintptr_t>(dY) & 15) == 0)) {
         const int threads = (int)std::min<int64_t>(256, round_up(cdiv(H, 4), 32));

@@ -154,9 +154,12 @@ class DataProcessing:
         np.random.seed(self.cfg.seed)
         test_prop = float(self.cfg.test_prop) if self.cfg.test_prop else 0.2
         tr_list, te_list = [], []
-        users = np.unique(uid[rows])
-        for u in users:
-            grp = rows[uid[rows] == u]
+        # one stable sort groups the rows by user (ascending id, file order kept inside a group): the same groups,
+        # in the same order, as a boolean mask per user -- and so the same np.random.choice sequence
+        u_of = uid[rows]
+        order = np.argsort(u_of, kind='stable')
+        _, starts = np.unique(u_of[order], return_index=True)
+        for grp in np.split(rows[order], starts[1:]) if len(rows) else []:
             n_items_u = len(grp)
             if n_items_u > 1:
                 idx = np.zeros(n_items_u, dtype='bool')

@@ -7,6 +7,7 @@ single torch CUDA tensors -- torch is storage only -- re-points the network's
 rectorch/models.py:485-488, 513-514), and drives libb200vae.so through ctypes.
 """
 import ctypes
+import os
 import math
 
 import numpy as np
@@ -113,6 +114,8 @@ class Engine:
         self.wd16 = None          # caller-owned fp16 image of W_d (data parallelism with a sharded optimizer)
         self.w1g = None           # gathered fp16 image of the encoder-0 weight [world][n_items/world x H1] (sharded optimizer)
         self._w1_shard = None     # (world, rank) while encoder-0 sharding is on
+        self.deterministic = (torch.are_deterministic_algorithms_enabled()
+                              or os.environ.get("B200VAE_DETERMINISTIC", "0") not in ("", "0"))
 
     # ---- views ---------------------------------------------------------------------------------
     def _views(self, arena, i):
@@ -174,9 +177,18 @@ class Engine:
             check(_lib.lib().b200vae_bind_shadow(self._ctx, ptr(self.wd16), self.wd16.numel()))
         if self._w1_shard is not None:
             check(_lib.lib().b200vae_set_w1_sharding(self._ctx, ptr(self.w1g), self._w1_shard[0], self._w1_shard[1]))
+        if self.deterministic:
+            check(_lib.lib().b200vae_set_deterministic(self._ctx, 1))
         for slot in (0, 1):
             if self._csr[slot] is not None:
                 self._bind(slot, self._csr[slot])
+
+    def set_deterministic(self, on=True):
+        """Run-to-run bit-identical steps: the sparse encoder-0 product / gradient stop using floating-point atomics
+        (what ``torch.use_deterministic_algorithms(True)`` asks of the reference's torch ops).  Slower."""
+        self.deterministic = bool(on)
+        if self._ctx is not None:
+            check(_lib.lib().b200vae_set_deterministic(self._ctx, 1 if on else 0))
 
     def _destroy_ctx(self):
         if self._ctx is not None:
@@ -225,7 +237,7 @@ class Engine:
                                                      self._w1_shard[1] if self._w1_shard else 0))
 
     def w1_rows(self, arena, packed, unpack):
-        check(_lib.lib().b200vae_w1_rows(self._ctx, ptr(arena), ptr(packed), 1 if unpack else 0, stream_ptr()))
+        check(_lib.lib().b200vae_w1_rows(self._ctx, ptr(arena), ptr(packed), 1 if unpack else 0, stream_ptr(self.device)))
 
     def defer_wait(self, event):
         """The next call that reads the fp16 image of W_d waits for ``event`` (torch.cuda.Event, recorded)."""
@@ -235,7 +247,7 @@ class Engine:
         # torch ops that write the arena (init_weights, load_state_dict, manual edits) bump the
         # storage version counter; our kernels do not.  Re-derive the fp16 image when it moved.
         if self.w._version != self._seen_version:
-            check(_lib.lib().b200vae_sync_weights(self._ctx, stream_ptr()))
+            check(_lib.lib().b200vae_sync_weights(self._ctx, stream_ptr(self.device)))
             self._seen_version = self.w._version
 
     def _prepare(self, rows, dense, B, nnz_hint, slot=0):
@@ -243,7 +255,7 @@ class Engine:
         self._ensure_ctx(B, nnz_hint)
         self._sync_weights_if_dirty()
         if dense is not None:
-            check(_lib.lib().b200vae_dense_to_csr(self._ctx, slot, ptr(dense), B, stream_ptr()))
+            check(_lib.lib().b200vae_dense_to_csr(self._ctx, slot, ptr(dense), B, stream_ptr(self.device)))
 
     @staticmethod
     def _as_dense(x, device):
@@ -265,7 +277,7 @@ class Engine:
             with torch.cuda.device(self.device):
                 lens = torch.empty(B + 1, dtype=torch.int64, device=self.device)
                 indptr = torch.empty(B + 1, dtype=torch.int64, device=self.device)
-                check(_lib.lib().b200vae_dense_to_csr_raw(ptr(d), B, n, ptr(lens), ptr(indptr), None, None, 0, stream_ptr()))
+                check(_lib.lib().b200vae_dense_to_csr_raw(ptr(d), B, n, ptr(lens), ptr(indptr), None, None, 0, stream_ptr(self.device)))
             need = max(need, int(indptr[-1].item()))
         if need <= self._cap_nnz:
             return self._cap_nnz
@@ -291,7 +303,7 @@ class Engine:
             B = dense.shape[0]
             self._prepare(None, dense, B, self._nnz_cap_dense(dense, dense_target), 0)
             if dense_target is not None:
-                check(_lib.lib().b200vae_dense_to_csr(self._ctx, 1, ptr(dense_target), B, stream_ptr()))
+                check(_lib.lib().b200vae_dense_to_csr(self._ctx, 1, ptr(dense_target), B, stream_ptr(self.device)))
                 use_target = True
             rid = None
         else:
@@ -301,7 +313,7 @@ class Engine:
         check(_lib.lib().b200vae_forward_backward(
             self._ctx, ptr(rid), B, B if B_global is None else int(B_global), 1 if use_target else 0,
             float(beta), float(lam), float(dropout_p), int(seed) & (2 ** 64 - 1), int(step), int(row_offset),
-            ptr(keep_tape), ptr(eps_tape), ptr(self.loss_buf), ptr(enc0_delta_out), stream_ptr()))
+            ptr(keep_tape), ptr(eps_tape), ptr(self.loss_buf), ptr(enc0_delta_out), stream_ptr(self.device)))
         return self.loss_buf
 
     def enc0_grad(self, all_rows, delta_all, dropout_p, seed, step, row_offset=0):
@@ -309,12 +321,12 @@ class Engine:
         gathered ``delta_all`` [len(all_rows) x H1]."""
         check(_lib.lib().b200vae_enc0_grad(self._ctx, ptr(all_rows), int(all_rows.numel()), ptr(delta_all),
                                            float(dropout_p), int(seed) & (2 ** 64 - 1), int(step), int(row_offset),
-                                           stream_ptr()))
+                                           stream_ptr(self.device)))
 
     def adam(self, lr, betas, eps, weight_decay, lam):
         self.adam_steps += 1
         check(_lib.lib().b200vae_adam_step(self._ctx, float(lr), float(betas[0]), float(betas[1]), float(eps),
-                                           float(weight_decay), float(lam), self.adam_steps, stream_ptr()))
+                                           float(weight_decay), float(lam), self.adam_steps, stream_ptr(self.device)))
 
     def adam_range(self, lr, betas, eps, weight_decay, lam, lo, hi, first, narrow=False):
         """Adam on arena elements [lo, hi) on the current stream; ``first`` advances the step counter (one step = all
@@ -323,14 +335,14 @@ class Engine:
             self.adam_steps += 1
         check(_lib.lib().b200vae_adam_step_range(self._ctx, float(lr), float(betas[0]), float(betas[1]), float(eps),
                                                  float(weight_decay), float(lam), self.adam_steps, int(lo), int(hi),
-                                                 1 if narrow else 0, stream_ptr()))
+                                                 1 if narrow else 0, stream_ptr(self.device)))
 
     def build_cond_batch(self, rows, conds, item_mask):
         """Conditioned examples (row, cond) -> the context's internal batches: slot 0 = [tr row | one-hot(cond)],
         slot 1 = te row restricted to the items satisfying the condition (ConditionedDataSampler.__iter__)."""
         B = int(rows.numel())
         self._prepare(rows, None, B, self._nnz_cap_rows(B) + B)
-        check(_lib.lib().b200vae_build_cond_batch(self._ctx, ptr(rows), ptr(conds), B, ptr(item_mask), stream_ptr()))
+        check(_lib.lib().b200vae_build_cond_batch(self._ctx, ptr(rows), ptr(conds), B, ptr(item_mask), stream_ptr(self.device)))
         return B
 
     def train_step(self, rows=None, dense=None, dense_target=None, use_target=False, beta=1.0, lam=0.0,
@@ -344,7 +356,7 @@ class Engine:
             B = dense.shape[0]
             self._prepare(None, dense, B, self._nnz_cap_dense(dense, dense_target), 0)
             if dense_target is not None:
-                check(_lib.lib().b200vae_dense_to_csr(self._ctx, 1, ptr(dense_target), B, stream_ptr()))
+                check(_lib.lib().b200vae_dense_to_csr(self._ctx, 1, ptr(dense_target), B, stream_ptr(self.device)))
                 use_target = True
             rid = None
         else:
@@ -356,7 +368,7 @@ class Engine:
             self._ctx, ptr(rid), B, 1 if use_target else 0, float(beta), float(lam), float(dropout_p),
             int(seed) & (2 ** 64 - 1), self.adam_steps, ptr(keep_tape), ptr(eps_tape), float(lr),
             float(betas[0]), float(betas[1]), float(eps), float(weight_decay), ptr(self.loss_buf),
-            stream_ptr()))
+            stream_ptr(self.device)))
         return self.loss_buf
 
     def predict(self, rows=None, dense=None, remove_train=True, train_mode=False, dropout_p=0.0, seed=0,
@@ -380,7 +392,7 @@ class Engine:
                 logvar = torch.empty((B, self.latent), dtype=torch.float32, device=self.device)
         check(_lib.lib().b200vae_predict(self._ctx, ptr(rid), B, 1 if remove_train else 0, 1 if train_mode else 0,
                                          float(dropout_p), int(seed) & (2 ** 64 - 1), 0, ptr(scores), ptr(mu),
-                                         ptr(logvar), stream_ptr()))
+                                         ptr(logvar), stream_ptr(self.device)))
         return scores, mu, logvar
 
     def decode(self, z):
@@ -389,14 +401,14 @@ class Engine:
         self._ensure_ctx(B, 1)
         self._sync_weights_if_dirty()
         scores = torch.empty((B, self.n_items), dtype=torch.float32, device=self.device)
-        check(_lib.lib().b200vae_decode(self._ctx, ptr(z), B, ptr(scores), stream_ptr()))
+        check(_lib.lib().b200vae_decode(self._ctx, ptr(z), B, ptr(scores), stream_ptr(self.device)))
         return scores
 
     def expand(self, slot, rows):
         B = rows.numel()
         self._ensure_ctx(B, self._nnz_cap_rows(B))
         out = torch.empty((B, self.enc_in if slot == 0 else self.n_items), dtype=torch.float32, device=self.device)
-        check(_lib.lib().b200vae_expand_batch(self._ctx, slot, ptr(rows), B, ptr(out), stream_ptr()))
+        check(_lib.lib().b200vae_expand_batch(self._ctx, slot, ptr(rows), B, ptr(out), stream_ptr(self.device)))
         return out
 
     def topk_metrics(self, scores, gt_rows, specs):
@@ -408,7 +420,7 @@ class Engine:
         out = torch.empty((n, B), dtype=torch.float32, device=self.device)
         # gt_rows None = the context's internal slot-1 batch (conditioned examples: the filtered held-out rows)
         check(_lib.lib().b200vae_topk_metrics(self._ctx, ptr(scores), ptr(gt_rows), B, kinds, ks, n, ptr(out), None,
-                                              stream_ptr()))
+                                              stream_ptr(self.device)))
         return out
 
     # ---- instrumentation -------------------------------------------------------------------------------

@@ -503,10 +503,10 @@ class AETrainer(TorchNNTrainer):
         # ONE small collective on the main stream: all-gather of the packed records, summed locally in rank order
         small = self._pg_small
         g_small, g_bd = eng.g[s_lo:cut], eng.g[b_lo:]
-        check(_lib.lib().b200vae_dp_pack(ptr(send[n_delta:]), ptr(g_small), na, ptr(g_bd), nb, ptr(loss_slot), 4, stream_ptr()))
+        check(_lib.lib().b200vae_dp_pack(ptr(send[n_delta:]), ptr(g_small), na, ptr(g_bd), nb, ptr(loss_slot), 4, stream_ptr(self.device)))
         dist.all_gather_into_tensor(recv, send, group=small)
         check(_lib.lib().b200vae_dp_unpack(ptr(recv), world, rec, n_delta, ptr(everyone), ptr(g_small), na, ptr(g_bd), nb,
-                                           ptr(loss_slot), 4, stream_ptr()))
+                                           ptr(loss_slot), 4, stream_ptr(self.device)))
         if tm is not None:
             tm.mark("main: packed all_gather (delta, hidden-layer / b_d gradients, loss) + local sums")
         eng.enc0_grad(rb.all_rows, everyone, kw["dropout_p"], kw["seed"], step, 0)

@@ -298,3 +298,30 @@ def test_train_batch_csr_host_batches():
     # rows 0..B-1 of the first batch coincide with the resident rows, later batches do not
     assert abs(a[0] - b[0]) / abs(b[0]) < 1e-6
     assert abs(a[-1] - b[-1]) / abs(b[-1]) < 0.05
+
+
+def test_deterministic_mode_is_bit_reproducible():
+    """b200vae_set_deterministic: the sparse encoder-0 product and its gradient (the only floating-point atomics of
+    the step) become ordered reductions, so repeating the same steps gives bit-identical weights and Adam moments;
+    the default (atomic) path agrees with it to summation-order rounding."""
+    from rectorch_b200 import synth
+    csr = synth.make_matrix(640, 4096, seed=4, mu=4.0, sigma=0.7, min_len=3, max_len=600)   # rows longer than one segment
+
+    def run(det):
+        torch.manual_seed(3)
+        model = MultiVAE(MultiVAE_net([48, 160, 4096]).cuda(), beta=0.2, anneal_steps=20)
+        model._engine.set_deterministic(det)
+        torch.manual_seed(5)
+        sampler = DataSampler(csr, None, batch_size=160, shuffle=False)
+        losses = [model.train_batch(rb) for rb in sampler.iter_rows()]
+        torch.cuda.synchronize()
+        eng = model._engine
+        return np.array(losses), eng.w.clone(), eng.m.clone(), eng.v.clone()
+    l1, w1, m1, v1 = run(True)
+    l2, w2, m2, v2 = run(True)
+    assert np.array_equal(l1, l2)
+    assert torch.equal(w1, w2) and torch.equal(m1, m2) and torch.equal(v1, v2)
+    l3, w3, _, _ = run(False)
+    assert np.allclose(l1, l3, rtol=1e-5)
+    assert (w1 - w3).abs().max().item() < 5e-3      # a handful of Adam sign flips on ~0 gradients at lr 1e-3, 4 steps
+    assert (w1 - w3).abs().mean().item() < 1e-5
