@@ -307,7 +307,9 @@ int64_t b200vae_launch_count(b200vae_ctx* ctx, int reset);
 /* Time (ms) of the most recent execution of an instrumented kernel group, measured
  * with CUDA events on the launching stream; which: 0 = decoder fwd (K4), 1 = Adam (K8),
  * 2 = decoder bwd recompute (K5), 3 = dW_d GEMM, 4 = dh GEMM.  Enable with
- * b200vae_set_timing(ctx, 1); values are valid after the stream is synchronised. */
+ * b200vae_set_timing(ctx, 1); values are valid after the stream is synchronised.
+ * enable = 2 keeps the production two-stream schedule and makes b200vae_timing_report give completion times since the
+ * start of the step (side-stream launches are suffixed with '+') instead of per-launch intervals. */
 int  b200vae_set_timing(b200vae_ctx* ctx, int enable);
 /* "launcher_name milliseconds\n" for every launch of the most recent step run with timing enabled
  * (CUDA events recorded after each launch on the launching stream; sync the stream first).

@@ -146,6 +146,7 @@ struct AdamW1 {                     // ADAM_ROWS_MOD (by value to the kernel)
     __half* w1g;
     int mod_n, mod_r;
     int64_t rows_per;
+    int stream;                     // 1: w / m / v go through L2 with evict-first hints (AdamOpt::stream)
 };
 struct AdamOpt {
     const int32_t* mark = nullptr;
@@ -157,6 +158,8 @@ struct AdamOpt {
     __half* w1g = nullptr;          // ADAM_ROWS_MOD: gathered fp16 image of the encoder-0 weight [mod_n][rows_per x row_len]
     int mod_n = 1, mod_r = 0;
     int64_t rows_per = 0;
+    bool stream = false;            // the gradient of this range is expected in L2 (written just before by its producer):
+                                    // load / store w, m, v with evict-first hints so they do not push it out
     __half* shadow2 = nullptr;      // fp16 image of the hidden-layer tensors: elements [s2_lo, s2_hi) of THIS launch
     int64_t s2_lo = 0, s2_hi = 0;   // (indices relative to the launch's base pointers) go to shadow2[e - s2_lo]
 };
@@ -164,6 +167,7 @@ int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float
                 float beta1, float beta2, float bc2_sqrt, float eps, float wd, float lam,
                 const float* norm_ptr, __half* shadow, int64_t sh_lo, int64_t sh_hi, int64_t z_lo, int64_t z_hi,
                 const AdamOpt& opt, cudaStream_t s);
+int launch_discard_l2(Ctx* c, const float* p, int64_t n, cudaStream_t s);
 int launch_to_f16(Ctx* c, const float* x, __half* y, int64_t rows, int cols, int64_t ldy, cudaStream_t s);
 
 // topk.cu

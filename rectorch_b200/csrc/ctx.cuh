@@ -123,7 +123,8 @@ struct Ctx {
     std::vector<cudaEvent_t> tev;     // one event after every launch of the current step (timing mode)
     std::vector<const char*> tnames;
     int tcount = 0;
-    bool timing = false;
+    int timing = 0;                   // 1: serial schedule, interval per launch; 2: production schedule, completion timeline
+    std::vector<cudaStream_t> tstream;
     cudaEvent_t ev[5][2];
     bool ev_valid[5] = {false, false, false, false, false};
 
@@ -140,14 +141,18 @@ struct Ctx {
     cudaEvent_t ev_side = nullptr;    // side-stream Adam of the current step is complete
     int overlap = 1;                  // bit 0: decoder-output Adam beside the encoder backward (default);
                                       // bit 1: untouched encoder-0 rows beside the forward pass -- measured slower
-                                      // (the tcgen05 kernels wait for the narrow launch), kept for experiments
-                                      // (B200VAE_OVERLAP)
+                                      // (the tcgen05 kernels wait for the narrow launch), kept for experiments;
+                                      // bit 2 (with bit 1): those rows after the decoder-output Adam instead -- no gain
+                                      // (B200VAE_OVERLAP; profiles/r2_schedule_experiments.txt)
     // scratch of b200vae_enc0_grad (a GLOBAL batch: rows of every data-parallel rank), grown on demand
     int64_t* gl_bp = nullptr;
     int32_t* gl_sp = nullptr;
     float*   gl_xt = nullptr;
     int64_t  gl_rows = 0, gl_nnz = 0;
-    int overlap_host = 3;             // schedule of the host-synchronous entry point (B200VAE_HOST_OVERLAP)
+    int wd_chunks = 0;                // > 1: dW_d GEMM + decoder-output Adam in item chunks on the side stream (B200VAE_WD_CHUNKS)
+    int wd_chunk_ctas = 8;            // CTAs per SM of the chunked Adam launches (B200VAE_WD_CHUNK_CTAS)
+    int wd_discard = 1;               // discard the consumed gradient lines from L2 (B200VAE_WD_DISCARD)
+    int overlap_host = 1;             // schedule of the host-synchronous entry point (B200VAE_HOST_OVERLAP)
     int side_ctas[2] = {2, 2};        // CTAs per SM of the two side launches (B200VAE_SIDE_CTAS="a,b")
     int side_threads = 256;
 };
@@ -161,8 +166,10 @@ inline void note(Ctx* c, const char* name, cudaStream_t s) {
             cudaEventCreate(&e);
             c->tev.push_back(e);
             c->tnames.push_back(name);
+            c->tstream.push_back(s);
         }
         c->tnames[c->tcount] = name;
+        c->tstream[c->tcount] = s;
         cudaEventRecord(c->tev[c->tcount], s);
         c->tcount++;
     }

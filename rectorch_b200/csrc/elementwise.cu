@@ -238,15 +238,16 @@ k_adam(float* __restrict__ w, float* __restrict__ g, float* __restrict__ m, floa
                 zero_g = true;          // no scatter reached this row: its gradient is +0 and stays in memory as such
             }
         }
-        float4 ww = w4[i], mm = m4[i], vv = v4[i];
+        float4 ww, mm, vv;
+        if (w1.stream) { ww = __ldcs(w4 + i); mm = __ldcs(m4 + i); vv = __ldcs(v4 + i); }
+        else           { ww = w4[i]; mm = m4[i]; vv = v4[i]; }
         float4 gg = zero_g ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldcs(g4 + i);
         adam_one(ww.x, gg.x, mm.x, vv.x, neg_step, b1c, b2, b2c, bc2_sqrt, eps, EXTRAS ? wd : 0.f, reg);
         adam_one(ww.y, gg.y, mm.y, vv.y, neg_step, b1c, b2, b2c, bc2_sqrt, eps, EXTRAS ? wd : 0.f, reg);
         adam_one(ww.z, gg.z, mm.z, vv.z, neg_step, b1c, b2, b2c, bc2_sqrt, eps, EXTRAS ? wd : 0.f, reg);
         adam_one(ww.w, gg.w, mm.w, vv.w, neg_step, b1c, b2, b2c, bc2_sqrt, eps, EXTRAS ? wd : 0.f, reg);
-        w4[i] = ww;
-        m4[i] = mm;
-        v4[i] = vv;
+        if (w1.stream) { __stcs(w4 + i, ww); __stcs(m4 + i, mm); __stcs(v4 + i, vv); }
+        else           { w4[i] = ww; m4[i] = mm; v4[i] = vv; }
         if (FILTER == ADAM_ROWS_MOD && w1_pos >= 0) {       // fp16 image of the updated row, into this rank's block
             const __half2 lo = __floats2half2_rn(f16_clamp(ww.x), f16_clamp(ww.y));
             const __half2 hi = __floats2half2_rn(f16_clamp(ww.z), f16_clamp(ww.w));
@@ -320,7 +321,7 @@ int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float
     if (filter == ADAM_ROWS_MOD)
         B200_REQUIRE(opt.w1g && opt.mod_n > 1 && opt.mod_r >= 0 && opt.mod_r < opt.mod_n && opt.rows_per > 0, B200VAE_EINVAL,
                      "adam: bad encoder-0 shard description");
-    const AdamW1 w1 = {opt.w1g, opt.mod_n, opt.mod_r, opt.rows_per};
+    const AdamW1 w1 = {opt.w1g, opt.mod_n, opt.mod_r, opt.rows_per, opt.stream ? 1 : 0};
     // persistent-style grid: a multiple of the SM count (default 8 CTAs of 256 threads per SM)
     const int threads = std::min(256, std::max(32, opt.threads & ~31));
     int64_t want = cdiv(std::max<int64_t>(n >> 2, 1), threads);
@@ -343,6 +344,27 @@ int launch_adam(Ctx* c, float* w, float* g, float* m, float* v, int64_t n, float
         else ADAM_LAUNCH(false, ADAM_ROWS_ALL);
     }
 #undef ADAM_LAUNCH
+    note(c, __func__, s);
+    B200_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// Drop the L2 lines of a consumed buffer without writing them back (discard.global.L2): the decoder-output gradient is
+// produced chunk by chunk, read once by Adam while still in L2, and overwritten next step -- it never needs to reach HBM.
+__global__ void k_discard_l2(const char* __restrict__ p, int64_t n_lines) {
+    pdl_sync();
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n_lines; i += stride) asm volatile("discard.global.L2 [%0], 128;" ::"l"(p + i * 128) : "memory");
+}
+int launch_discard_l2(Ctx* c, const float* p, int64_t n, cudaStream_t s) {
+    // whole 128-byte lines inside [p, p + n)
+    const uintptr_t a = (reinterpret_cast<uintptr_t>(p) + 127) & ~(uintptr_t)127;
+    const uintptr_t b = reinterpret_cast<uintptr_t>(p + n) & ~(uintptr_t)127;
+    if (b <= a) return 0;
+    const int64_t n_lines = (int64_t)((b - a) >> 7);
+    const int blocks = (int)std::min<int64_t>(cdiv(n_lines, 256), (int64_t)c->num_sms * 4);
+    B200_CUDA_OK(launch_pdl(k_discard_l2, dim3(blocks), dim3(256), 0, s, reinterpret_cast<const char*>(a), n_lines));
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;

@@ -225,7 +225,7 @@ struct AdamHyper {
     int ov = 0;           // effective overlap bits of the fused step this update belongs to (0 = serial)
 };
 static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo = 0, int64_t r_hi = -1,
-                     int w1_filter = ADAM_ROWS_ALL, int ctas_per_sm = 8);
+                     int w1_filter = ADAM_ROWS_ALL, int ctas_per_sm = 8, bool stream_hints = false);
 
 // `fused` (single-GPU fused step only): batch_prep stamps the encoder-0 rows this step touches, and the Adam
 // update of all the OTHER rows -- zero gradient, not read by this step's gather -- starts right away on the side
@@ -237,7 +237,7 @@ static int forward_hidden(Ctx* c, FwdState* st, int B, bool train, float p, uint
     B200_CHECK(launch_batch_prep(c, st->in, p, seed, step, row_offset, keep_tape, train, c->xt, row_sum_out,
                                  split_rows ? c->mark : nullptr, split_rows ? (int32_t)fused->step : 0, s));
     const Layer& e0 = c->enc[0];
-    if (split_rows) {
+    if (split_rows && !(fused->ov & 4)) {
         B200_CUDA_OK(cudaEventRecord(c->ev_mark, s));
         B200_CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_mark, 0));
         B200_CHECK(adam_step(c, *fused, c->side, e0.w_off, e0.w_off + (int64_t)e0.in * e0.out, ADAM_ROWS_UNMARKED,
@@ -446,6 +446,23 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
     float* dbd = c->g + DL.b_off;
     float* d0 = c->dbuf[0];
     float* d1 = c->dbuf[1];
+    // Fused single-GPU step, plain Adam: the dW_d GEMM moves to the side stream and runs in item chunks, each followed by
+    // the Adam update of the same rows of W_d while that piece of the gradient is still in L2, and by a discard of its
+    // lines -- the 2 x 120 MB round trip of dW_d through HBM disappears and the GEMM leaves the critical path (the main
+    // stream goes straight to dh and the hidden layers).
+    const bool wd_chunked = fused && (fused->ov & 1) && c->tc_dec && c->wd_chunks > 1 && fused->wd == 0.f && fused->lam == 0.f &&
+                            I >= 64 * c->wd_chunks && (DL.w_off % 32) == 0;
+    const int Bp_ = (int)round_up(B, 8);
+    auto dwd_gemm = [&](int n0, int n1, cudaStream_t st) -> int {
+        TcEpi e2;
+        e2.bias_grad = dbd + n0;
+        e2.bias_col = H;       // row H of the product (the rs row of hsT) is the bias gradient
+        e2.transpose_out = 1;
+        e2.out_scale = exp2f(-(HS_LOG2_SCALE + PROB_LOG2_SCALE));
+        e2.out_scale_ptr = c->dw_scale;
+        return launch_tc_gemm(c, TC_EPI_STORE, c->hsT, Bp_, 0, c->P16 + (int64_t)n0 * Bp_, Bp_, 0, dWd + (int64_t)n0 * H, H, H + 8,
+                              n1 - n0, B, e2, st);
+    };
     if (c->tc_dec) {
         // P~^T [I x Bp] (item-major, users contiguous, fp16) = softmax * 2^14 from the recompute kernel
         const int Bp = (int)round_up(B, 8);
@@ -462,15 +479,11 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         // shared memory), B = P~^T (K-major).  Computing the transpose puts the hidden index on the TMEM lanes, so each
         // epilogue store instruction writes 32 consecutive floats of a dW_d row (full 128 B lines).  The epilogue
         // un-scales by R * 2^-(8+14).
-        TcEpi e2;
-        e2.bias_grad = dbd;
-        e2.bias_col = H;       // row H of the product (the rs row of hsT) is the bias gradient
-        e2.transpose_out = 1;
-        e2.out_scale = exp2f(-(HS_LOG2_SCALE + PROB_LOG2_SCALE));
-        e2.out_scale_ptr = c->dw_scale;
-        tick(c, 3, 0, s);
-        B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->hsT, Bp, 0, c->P16, Bp, 0, dWd, H, H + 8, I, B, e2, s));
-        tick(c, 3, 1, s);
+        if (!wd_chunked) {
+            tick(c, 3, 0, s);
+            B200_CHECK(dwd_gemm(0, I, s));
+            tick(c, 3, 1, s);
+        }
         // dh = rs_u * 2^-14 * (P~ W_d) : A = P~^T given as [K=I x M=Bp] (MN-major), B = W_d [K=I x N=H] (MN-major);
         // the per-user factor and tanh' are applied by the split-K reduction
         TcEpi e3;
@@ -521,7 +534,28 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         // host-bound here, and a side launch issued after them would start too late to overlap anything
         // (measured: 869 us/step end to end vs 740 us when the host runs ahead)
         B200_CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_wd, 0));
-        B200_CHECK(adam_step(c, *fused, c->side, c->dec.back().w_off, c->n_elems, ADAM_ROWS_ALL, c->side_ctas[0]));
+        if (wd_chunked) {
+            const int per = (int)round_up(cdiv(I, c->wd_chunks), 32);   // 32 rows: chunk boundaries on 128-byte lines
+            for (int n0 = 0; n0 < I; n0 += per) {
+                const int n1 = std::min(I, n0 + per);
+                B200_CHECK(dwd_gemm(n0, n1, c->side));
+                const int64_t lo = DL.w_off + (int64_t)n0 * H;
+                const int64_t hi = (n1 == I) ? c->n_elems : DL.w_off + (int64_t)n1 * H;
+                B200_CHECK(adam_step(c, *fused, c->side, lo, hi, ADAM_ROWS_ALL, c->wd_chunk_ctas, true));
+                if (c->wd_discard) B200_CHECK(launch_discard_l2(c, c->g + lo, hi - lo, c->side));
+            }
+        } else {
+            B200_CHECK(adam_step(c, *fused, c->side, c->dec.back().w_off, c->n_elems, ADAM_ROWS_ALL, c->side_ctas[0]));
+        }
+    }
+    if (fused && (fused->ov & 6) == 6) {
+        // schedule bit 2 ("late"): the untouched encoder-0 rows follow the decoder-output Adam on the side stream, beside the
+        // hidden-layer backward and the sparse scatter -- the part of the step that leaves HBM idle -- instead of beside
+        // the forward pass, so the closing Adam on the main stream only has the rows this batch touched
+        const Layer& E0 = c->enc[0];
+        B200_CUDA_OK(cudaStreamWaitEvent(c->side, c->ev_wd, 0));
+        B200_CHECK(adam_step(c, *fused, c->side, E0.w_off, E0.w_off + (int64_t)E0.in * E0.out, ADAM_ROWS_UNMARKED,
+                             c->side_ctas[1]));
     }
 
     // ---------------- backward: hidden decoder layers ----------------
@@ -573,7 +607,7 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
 // of one step are issued tail first and the range that starts at 0 closes the step.  `w1_filter` selects rows
 // of the encoder-0 weight by their step mark (AdamOpt), `ctas_per_sm` the width of the launch.
 static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo, int64_t r_hi, int w1_filter,
-                     int ctas_per_sm) {
+                     int ctas_per_sm, bool stream_hints) {
     if (r_hi < 0) r_hi = c->n_elems;
     B200_REQUIRE(r_lo >= 0 && r_lo < r_hi && r_hi <= c->n_elems && r_lo % 4 == 0, B200VAE_EINVAL, "bad Adam range");
     B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
@@ -596,6 +630,7 @@ static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo, i
     opt.row_len = E0.out;
     opt.ctas_per_sm = ctas_per_sm;
     opt.threads = (ctas_per_sm < 8) ? c->side_threads : 256;
+    opt.stream = stream_hints;
     if (c->w1_mod_n > 1 && w1_filter == ADAM_ROWS_ALL) {      // this rank updates only its rows of the encoder-0 weight
         opt.filter = ADAM_ROWS_MOD;
         opt.w1g = c->w1g;
@@ -651,8 +686,9 @@ static int adam_step(Ctx* c, const AdamHyper& h, cudaStream_t s, int64_t r_lo, i
 // schedule bits that can actually be used out of the requested ones (B200VAE_OVERLAP semantics)
 static int effective_overlap(const Ctx* c, int requested) {
     const Layer& E0 = c->enc[0];
-    int ov = (c->timing || !c->side) ? 0 : (requested & 3);
-    if (E0.out % 4 != 0 || E0.w_off % 4 != 0) ov &= ~2;      // the row filter works on whole float4s
+    int ov = (c->timing == 1 || !c->side) ? 0 : (requested & 7);
+    if (!(ov & 2)) ov &= ~4;
+    if (E0.out % 4 != 0 || E0.w_off % 4 != 0) ov &= ~6;      // the row filter works on whole float4s
     return ov;
 }
 
@@ -679,10 +715,10 @@ static int train_step_fused(Ctx* c, const int32_t* row_ids, int B, int use_targe
                             const uint8_t* keep_tape, const float* eps_tape, AdamHyper h, float* loss_out,
                             cudaStream_t s, bool host_sync = false) {
     // host_sync: the caller synchronises with the host after every step (b200vae_train_step_host), so the GPU
-    // starts each step idle.  Measured [B200, cfg2]: schedule 1 (decoder-output Adam beside the encoder backward)
-    // is the fastest when the host runs ahead (735 us/step; 781 for schedule 3) but the slowest when it does not
-    // (866 us; 826 serial; 794 for schedule 3, whose side stream already has work early in the step; issuing the
-    // side launch earlier in host order or a warm-up no-op on the side stream change nothing: host issue is 124 us).
+    // starts each step idle.  Round 1 (tf32 kernels, no programmatic dependent launch) had schedule 3 ahead for such
+    // callers; with the round-2 kernels schedule 1 wins for both kinds of caller [B200, cfg2, 60 steps]:
+    // 652 us/step and 710 K users/s end to end, against 700 us / 669 K for schedule 3 and 715 us / 662 K for 7
+    // (profiles/r2_schedule_experiments.txt).
     h.ov = effective_overlap(c, host_sync ? c->overlap_host : c->overlap);
     if (!h.ov) {
         B200_CHECK(forward_backward(c, row_ids, B, B, use_target, beta, h.lam, p, seed, (uint64_t)h.step, 0, keep_tape,
@@ -770,8 +806,11 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     cudaEventCreateWithFlags(&c->ev_mark, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming);
     if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) c->side = nullptr;
-    if (const char* e = getenv("B200VAE_OVERLAP")) c->overlap = c->overlap_host = atoi(e) & 3;
-    if (const char* e = getenv("B200VAE_HOST_OVERLAP")) c->overlap_host = atoi(e) & 3;
+    if (const char* e = getenv("B200VAE_OVERLAP")) c->overlap = c->overlap_host = atoi(e) & 7;
+    if (const char* e = getenv("B200VAE_HOST_OVERLAP")) c->overlap_host = atoi(e) & 7;
+    if (const char* e = getenv("B200VAE_WD_CHUNKS")) c->wd_chunks = std::max(0, std::min(64, atoi(e)));
+    if (const char* e = getenv("B200VAE_WD_CHUNK_CTAS")) c->wd_chunk_ctas = std::max(1, std::min(8, atoi(e)));
+    if (const char* e = getenv("B200VAE_WD_DISCARD")) c->wd_discard = atoi(e) != 0;
     // width of the decoder-output Adam on the side stream: narrow when there are hidden-layer kernels to share
     // the SMs with (cfg2: 2 CTAs/SM = 743 us/step vs 778 at 8), full width when the backward tail is only the
     // sparse scatter (cfg3, one hidden layer: 386 us at 8 vs 392 at 2)            [B200, profiles/r1_overlap_sweep.txt]
@@ -1190,7 +1229,7 @@ int b200vae_adam_step_split(b200vae_ctx* ctx, float lr, float beta1, float beta2
     B200_REQUIRE(c && (touched_items || n_touched == 0) && n_touched >= 0, B200VAE_EINVAL, "bad argument");
     B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
     AdamHyper h = {lr, beta1, beta2, eps, weight_decay, lam, step};
-    h.ov = effective_overlap(c, overlap_bits);
+    h.ov = effective_overlap(c, overlap_bits & 3);     // bit 2 only moves a launch inside the fused step
     if (!h.ov) return adam_step(c, h, s);
     if (lam != 0.f) {
         B200_CHECK(launch_tensor_norms(c, c->w, c->d_toff, c->d_tlen, c->n_tensors, c->norm_partial, c->norms, s));
@@ -1455,7 +1494,7 @@ int b200vae_set_timing(b200vae_ctx* ctx, int enable) {
     Ctx* c = reinterpret_cast<Ctx*>(ctx);
     DeviceGuard dev_guard(c ? c->cfg.device : -1);
     if (!c) return B200VAE_EINVAL;
-    c->timing = enable != 0;
+    c->timing = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
     return 0;
 }
 
@@ -1477,8 +1516,11 @@ int b200vae_timing_report(b200vae_ctx* ctx, char* buf, int cap) {
     buf[0] = 0;
     for (int i = 1; i < c->tcount; ++i) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, c->tev[i - 1], c->tev[i]) != cudaSuccess) ms = -1.f;
-        int n = snprintf(buf + pos, cap - pos, "%s %.6f\n", c->tnames[i], ms);
+        // mode 1: interval since the previous launch (one stream); mode 2: completion time since the step started,
+        // with a '+' suffix on the launches that ran on the side stream
+        if (cudaEventElapsedTime(&ms, c->tev[c->timing == 2 ? 0 : i - 1], c->tev[i]) != cudaSuccess) ms = -1.f;
+        int n = snprintf(buf + pos, cap - pos, "%s%s %.6f\n", c->tnames[i],
+                         (c->timing == 2 && c->side && c->tstream[i] == c->side) ? "+" : "", ms);
         if (n <= 0 || n >= cap - pos) break;
         pos += n;
     }

@@ -428,7 +428,7 @@ class Engine:
         return int(_lib.lib().b200vae_launch_count(self._ctx, 1 if reset else 0)) if self._ctx else 0
 
     def set_timing(self, on):
-        check(_lib.lib().b200vae_set_timing(self._ctx, 1 if on else 0))
+        check(_lib.lib().b200vae_set_timing(self._ctx, int(on)))
 
     def timing_report(self):
         """[(launcher, ms)] for every launch of the most recent instrumented step."""
