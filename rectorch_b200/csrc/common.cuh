@@ -86,12 +86,21 @@ int launch_batch_scan(Ctx* c, const int64_t* indptr, const int32_t* row_ids, int
                       int64_t* bp, int32_t* sp, cudaStream_t s);
 int launch_batch_prep(Ctx* c, const BatchView& in, float p, uint64_t seed, uint64_t step,
                       int64_t row_offset, const uint8_t* keep_tape, bool train, float* xt, float* row_sum_out,
-                      int32_t* mark, int32_t mark_step, cudaStream_t s);
+                      int32_t* mark, int32_t mark_step, cudaStream_t s, bool with_scan = false);
 int launch_build_cond_batch(Ctx* c, const int32_t* ex_rows, const int32_t* ex_conds, int B,
                             const uint64_t* item_cond_mask, cudaStream_t s);
+// what k_loss_final computes, handed to the fix-up kernel so that its last CTA closes the loss (no extra launch)
+struct LossTail {
+    float* loss_out;        // nullptr: the fix-up kernel stops after the per-row terms
+    const float* kl_row;
+    const float* norms;
+    int* ticket;            // one zero-initialised int; the closing CTA resets it
+    int B, n_tensors;
+    float inv_Bg, beta, lam;
+};
 int launch_target_fixup(Ctx* c, const BatchView& tgt, __half* PT, int64_t ldp, const float* T, const float* lse,
                         const __half* h16, int64_t ldh, const __half* W16, int64_t ldw, const float* bias, int H,
-                        float* loss_row, cudaStream_t s);
+                        float* loss_row, cudaStream_t s, const LossTail* tail = nullptr);
 int launch_row_sums(Ctx* c, const BatchView& v, float* out, cudaStream_t s);
 // Wt16 != NULL (then mod_n > 1): the weight rows are read from the rank-interleaved gathered fp16 image
 // [mod_n][rows_per x H] (row j lives at block j % mod_n, index j / mod_n) instead of Wt

@@ -102,7 +102,7 @@ struct Ctx {
     int64_t* det_ent = nullptr;       // [max_batch_nnz] (row << 32 | position) per item, fill order
     int64_t* det_sorted = nullptr;    // [max_batch_nnz] the same, ascending per item
     float* spmm_acc = nullptr;        // [B x max(width)] zeroed accumulator for multi-segment gathers
-    int*   spmm_ticket = nullptr;     // [B] zeroed per-row completion tickets
+    int*   spmm_ticket = nullptr;     // [B + 1] zeroed per-row completion tickets; [B] = the loss-closing ticket of the fix-up
     float* dbuf[2] = {nullptr, nullptr};  // [B x max_width] ping-pong activation gradients
     float* part_max = nullptr;        // [n_tiles x B]
     float* part_sum = nullptr;
@@ -149,6 +149,7 @@ struct Ctx {
     int32_t* gl_sp = nullptr;
     float*   gl_xt = nullptr;
     int64_t  gl_rows = 0, gl_nnz = 0;
+    bool fuse_small = true;           // offset scans inside batch_prep, loss closed by the fix-up kernel (B200VAE_FUSE_SMALL=0: own launches)
     int wd_chunks = 0;                // > 1: dW_d GEMM + decoder-output Adam in item chunks on the side stream (B200VAE_WD_CHUNKS)
     int wd_chunk_ctas = 8;            // CTAs per SM of the chunked Adam launches (B200VAE_WD_CHUNK_CTAS)
     int wd_discard = 1;               // discard the consumed gradient lines from L2 (B200VAE_WD_DISCARD)

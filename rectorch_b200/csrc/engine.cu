@@ -123,7 +123,8 @@ static void free_ctx(Ctx* c) {
     delete c;
 }
 
-static int make_view(Ctx* c, int slot, const int32_t* row_ids, int B, BatchView* v, cudaStream_t s) {
+// defer_scan: the caller's next launch on this view is batch_prep(..., with_scan = true), which writes bp / sp itself
+static int make_view(Ctx* c, int slot, const int32_t* row_ids, int B, BatchView* v, cudaStream_t s, bool defer_scan = false) {
     CsrSlot& S = c->slot[slot];
     v->B = B;
     v->row_ids = row_ids;
@@ -139,7 +140,7 @@ static int make_view(Ctx* c, int slot, const int32_t* row_ids, int B, BatchView*
     }
     v->bp = S.bp;
     v->sp = S.sp;
-    B200_CHECK(launch_batch_scan(c, v->indptr, row_ids, B, c->cfg.max_batch_nnz, S.bp, S.sp, s));
+    if (!defer_scan) B200_CHECK(launch_batch_scan(c, v->indptr, row_ids, B, c->cfg.max_batch_nnz, S.bp, S.sp, s));
     return 0;
 }
 
@@ -216,6 +217,7 @@ struct FwdState {
     const float* h_last;      // input of the last decoder layer [B x H]
     const float* h_last_tanh; // same pointer if that activation came out of a tanh, else NULL
     int H;
+    bool scan_deferred = false;   // `in` was made with defer_scan: batch_prep computes bp / sp
 };
 
 // encoder + reparameterisation + hidden decoder layers.  Leaves z and h_last in the ctx.
@@ -235,7 +237,7 @@ static int forward_hidden(Ctx* c, FwdState* st, int B, bool train, float p, uint
                           float* row_sum_out, cudaStream_t s, const AdamHyper* fused = nullptr) {
     const bool split_rows = fused && (fused->ov & 2);
     B200_CHECK(launch_batch_prep(c, st->in, p, seed, step, row_offset, keep_tape, train, c->xt, row_sum_out,
-                                 split_rows ? c->mark : nullptr, split_rows ? (int32_t)fused->step : 0, s));
+                                 split_rows ? c->mark : nullptr, split_rows ? (int32_t)fused->step : 0, s, st->scan_deferred));
     const Layer& e0 = c->enc[0];
     if (split_rows && !(fused->ov & 4)) {
         B200_CUDA_OK(cudaEventRecord(c->ev_mark, s));
@@ -415,7 +417,9 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         c->norms_valid = true;      // the weights do not change before this step's Adam: it reuses them
     }
     FwdState st;
-    B200_CHECK(make_view(c, 0, row_ids, B, &st.in, s));
+    // batch_prep folds the offset scans in (every CTA re-sums the rows before its own: fine up to a few thousand rows)
+    st.scan_deferred = (B <= 4096) && c->fuse_small;
+    B200_CHECK(make_view(c, 0, row_ids, B, &st.in, s, st.scan_deferred));
     if (use_target) {
         B200_CHECK(make_view(c, 1, row_ids, B, &st.tgt, s));
     } else {
@@ -473,8 +477,21 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
         B200_CHECK(launch_tc_gemm(c, TC_EPI_PROB, c->h16, H, 0, c->wd16, H, 0, c->P16, Bp, B, I, H, e, s));
         tick(c, 2, 1, s);
         // sparse part of dlogits + the sparse loss term, straight on P~^T
+        // ... and, from its last CTA, the loss itself (k_loss_final without its launch)
+        LossTail lt = {};
+        if (c->fuse_small) {
+            lt.loss_out = loss_out;
+            lt.kl_row = c->cfg.is_vae ? c->kl_row : nullptr;
+            lt.norms = dae_reg ? c->norms : nullptr;
+            lt.ticket = c->spmm_ticket + c->cfg.max_batch;
+            lt.B = B;
+            lt.n_tensors = c->n_tensors;
+            lt.inv_Bg = inv_Bg;
+            lt.beta = c->cfg.is_vae ? beta : 0.f;
+            lt.lam = dae_reg ? lam : 0.f;
+        }
         B200_CHECK(launch_target_fixup(c, st.tgt, c->P16, Bp, c->T, c->lse, c->h16, H, c->wd16, H, c->w + DL.b_off, H,
-                                       c->loss_row, s));
+                                       c->loss_row, s, c->fuse_small ? &lt : nullptr));
         // (dW_d | db_d)^T = [hs | rs]^T [(H+8) x B] * P~ [B x I]: A = hsT (K-major, from dec_lse; stays resident in
         // shared memory), B = P~^T (K-major).  Computing the transpose puts the hidden index on the TMEM lanes, so each
         // epilogue store instruction writes 32 consecutive floats of a dW_d row (full 128 B lines).  The epilogue
@@ -522,9 +539,10 @@ static int forward_backward(Ctx* c, const int32_t* row_ids, int B, int Bg, int u
     }
     // sparse part of dlogits = -t/Bg (the tensor-core path already folded it into P^T)
     if (!c->tc_dec) B200_CHECK(launch_spmm_scatter_bias(c, st.tgt, nullptr, -inv_Bg, st.h_last, H, dWd, dbd, s));
-    B200_CHECK(launch_loss_final(c, c->loss_row, c->cfg.is_vae ? c->kl_row : nullptr, B, inv_Bg,
-                                 c->cfg.is_vae ? beta : 0.f, dae_reg ? lam : 0.f,
-                                 dae_reg ? c->norms : nullptr, c->n_tensors, loss_out, s));
+    if (!(c->tc_dec && c->fuse_small))
+        B200_CHECK(launch_loss_final(c, c->loss_row, c->cfg.is_vae ? c->kl_row : nullptr, B, inv_Bg,
+                                     c->cfg.is_vae ? beta : 0.f, dae_reg ? lam : 0.f,
+                                     dae_reg ? c->norms : nullptr, c->n_tensors, loss_out, s));
     // the decoder-output gradients (the tail of the gradient arena) are final from here on: a data-parallel
     // caller can start reducing them while the rest of the backward pass runs (b200vae_wait_wd_ready)
     B200_CUDA_OK(cudaEventRecord(c->ev_wd, s));
@@ -740,7 +758,8 @@ static int predict(Ctx* c, const int32_t* row_ids, int B, int remove_train, int 
     B200_REQUIRE(c->params_bound, B200VAE_ESTATE, "bind_params has not been called");
     B200_REQUIRE(B >= 1 && B <= c->cfg.max_batch, B200VAE_ECAPACITY, "batch %d exceeds capacity %d", B, c->cfg.max_batch);
     FwdState st;
-    B200_CHECK(make_view(c, 0, row_ids, B, &st.in, s));
+    st.scan_deferred = (B <= 4096) && c->fuse_small;
+    B200_CHECK(make_view(c, 0, row_ids, B, &st.in, s, st.scan_deferred));
     st.tgt = st.in;
     B200_CHECK(forward_hidden(c, &st, B, train_mode != 0, p, seed, step, 0, nullptr, nullptr, nullptr, s));
     const int L = c->latent, I = c->n_items;
@@ -808,6 +827,7 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) c->side = nullptr;
     if (const char* e = getenv("B200VAE_OVERLAP")) c->overlap = c->overlap_host = atoi(e) & 7;
     if (const char* e = getenv("B200VAE_HOST_OVERLAP")) c->overlap_host = atoi(e) & 7;
+    if (const char* e = getenv("B200VAE_FUSE_SMALL")) c->fuse_small = atoi(e) != 0;
     if (const char* e = getenv("B200VAE_WD_CHUNKS")) c->wd_chunks = std::max(0, std::min(64, atoi(e)));
     if (const char* e = getenv("B200VAE_WD_CHUNK_CTAS")) c->wd_chunk_ctas = std::max(1, std::min(8, atoi(e)));
     if (const char* e = getenv("B200VAE_WD_DISCARD")) c->wd_discard = atoi(e) != 0;
@@ -889,7 +909,7 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     A_(dmalloc(&c->dw_scale, 1));
     A_(dmalloc(&c->d_specs, 128));
     A_(dmalloc(&c->spmm_acc, Bm * std::max(c->max_width, H)));
-    A_(dmalloc(&c->spmm_ticket, Bm));
+    A_(dmalloc(&c->spmm_ticket, Bm + 1));
     A_(dmalloc(&c->mark, c->enc_in));
     A_(dmalloc(&c->dbuf[0], Bm * c->max_width)); A_(dmalloc(&c->dbuf[1], Bm * c->max_width));
     if (c->tc_hidden) {
@@ -913,7 +933,7 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
 #undef A_
     if (!rc && cudaMemset(c->d_err, 0, sizeof(int)) != cudaSuccess) rc = B200VAE_ECUDA;
     if (!rc && cudaMemset(c->spmm_acc, 0, (size_t)Bm * std::max(c->max_width, H) * sizeof(float)) != cudaSuccess) rc = B200VAE_ECUDA;
-    if (!rc && cudaMemset(c->spmm_ticket, 0, (size_t)Bm * sizeof(int)) != cudaSuccess) rc = B200VAE_ECUDA;
+    if (!rc && cudaMemset(c->spmm_ticket, 0, (size_t)(Bm + 1) * sizeof(int)) != cudaSuccess) rc = B200VAE_ECUDA;
     if (!rc && cudaMemset(c->mark, 0, (size_t)c->enc_in * sizeof(int32_t)) != cudaSuccess) rc = B200VAE_ECUDA;   // steps start at 1
     if (rc) { free_ctx(c); return rc; }
     *out = reinterpret_cast<b200vae_ctx*>(c);

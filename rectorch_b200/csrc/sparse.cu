@@ -107,17 +107,69 @@ int launch_scan_i64(Ctx* c, const int64_t* lens, int n, int64_t cap, int64_t* ou
 // batch_prep: per row  s = 1/max(||x||,1e-12);  xt = x*s*keep/(1-p)   (nets.py:395-397)
 // one warp per row
 // ------------------------------------------------------------------------------------------
-__global__ void k_batch_prep(BatchView v, float p, uint64_t seed, uint64_t step, int64_t row_offset,
-                             const uint8_t* __restrict__ keep_tape, int train, int64_t cap,
-                             float* __restrict__ xt, float* __restrict__ row_sum_out,
-                             int32_t* __restrict__ mark, int32_t mark_step, int n_items) {
+template <bool SCAN>
+__global__ void __launch_bounds__(256)
+k_batch_prep(BatchView v, float p, uint64_t seed, uint64_t step, int64_t row_offset,
+             const uint8_t* __restrict__ keep_tape, int train, int64_t cap,
+             float* __restrict__ xt, float* __restrict__ row_sum_out,
+             int32_t* __restrict__ mark, int32_t mark_step, int n_items,
+             int64_t* __restrict__ bp_out, int32_t* __restrict__ sp_out, int* __restrict__ err) {
+    __shared__ int64_t s_len[8];
+    __shared__ int64_t s_pl[8];
+    __shared__ int32_t s_ps[8];
     pdl_sync();
+    const int wid = threadIdx.x >> 5;
     int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
+    int64_t o_scan = 0;
+    if (SCAN) {
+        // The exclusive scans of the row lengths (bp) and of the per-row segment counts (sp) that k_batch_scan would
+        // produce, without the extra kernel on the critical path: every CTA sums the rows before its own (<= 2048 rows,
+        // L2-resident row pointers) and scans its 8 rows in shared memory.
+        const int row0 = blockIdx.x * 8;
+        int64_t pl = 0;
+        int32_t ps = 0;
+        for (int r = threadIdx.x; r < row0; r += 256) {
+            const int64_t g = v.row_ids ? (int64_t)v.row_ids[r] : (int64_t)r;
+            const int64_t len = v.indptr[g + 1] - v.indptr[g];
+            pl += len;
+            ps += (int32_t)max((int64_t)1, (len + SPMM_SEG - 1) / SPMM_SEG);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            pl += __shfl_xor_sync(0xffffffffu, pl, d);
+            ps += __shfl_xor_sync(0xffffffffu, ps, d);
+        }
+        int64_t my_len = 0;
+        if (warp < v.B) {
+            const int64_t g = v.row_ids ? (int64_t)v.row_ids[warp] : (int64_t)warp;
+            my_len = v.indptr[g + 1] - v.indptr[g];
+        }
+        if (lane == 0) { s_pl[wid] = pl; s_ps[wid] = ps; s_len[wid] = my_len; }
+        __syncthreads();
+        int64_t off = 0;
+        int32_t soff = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { off += s_pl[i]; soff += s_ps[i]; }
+        for (int i = 0; i < wid; ++i) {
+            off += s_len[i];
+            soff += (int32_t)max((int64_t)1, (s_len[i] + SPMM_SEG - 1) / SPMM_SEG);
+        }
+        if (warp < v.B && lane == 0) {
+            bp_out[warp] = off;
+            sp_out[warp] = soff;
+            if (warp == v.B - 1) {
+                bp_out[v.B] = off + my_len;
+                sp_out[v.B] = soff + (int32_t)max((int64_t)1, (my_len + SPMM_SEG - 1) / SPMM_SEG);
+                if (off + my_len > cap) *err = 1;
+            }
+        }
+        o_scan = off;
+    }
     if (warp >= v.B) return;
     int64_t gr = v.row_ids ? (int64_t)v.row_ids[warp] : (int64_t)warp;
     int64_t a = v.indptr[gr], b = v.indptr[gr + 1];
-    int64_t o = v.bp[warp];
+    int64_t o = SCAN ? o_scan : v.bp[warp];
     if (o + (b - a) > cap) return;   // capacity overflow flagged by the scan
     float ss = 0.f, sx = 0.f;
     // columns >= n_items are condition flags (CMultiVAE_net.encode, nets.py:466-470): concatenated AFTER
@@ -163,13 +215,20 @@ __global__ void k_batch_prep(BatchView v, float p, uint64_t seed, uint64_t step,
 
 int launch_batch_prep(Ctx* c, const BatchView& in, float p, uint64_t seed, uint64_t step,
                       int64_t row_offset, const uint8_t* keep_tape, bool train, float* xt, float* row_sum_out,
-                      int32_t* mark, int32_t mark_step, cudaStream_t s) {
+                      int32_t* mark, int32_t mark_step, cudaStream_t s, bool with_scan) {
     if (in.B == 0) return 0;
     int threads = 256;
     int blocks = (int)cdiv((int64_t)in.B * 32, threads);
-    B200_CUDA_OK(launch_pdl(k_batch_prep, dim3(blocks), dim3(threads), 0, s, in, p, seed, step, row_offset, keep_tape,
-                            train ? 1 : 0, c->cfg.max_batch_nnz, xt, row_sum_out, mark, mark_step,
-                            c->n_items > 0 ? c->n_items : INT32_MAX));
+    const int n_items = c->n_items > 0 ? c->n_items : INT32_MAX;
+    // with_scan: the view's bp / sp have NOT been computed (make_view(..., defer_scan)); this launch writes them
+    if (with_scan)
+        B200_CUDA_OK(launch_pdl(k_batch_prep<true>, dim3(blocks), dim3(threads), 0, s, in, p, seed, step, row_offset, keep_tape,
+                                train ? 1 : 0, c->cfg.max_batch_nnz, xt, row_sum_out, mark, mark_step, n_items,
+                                const_cast<int64_t*>(in.bp), const_cast<int32_t*>(in.sp), c->d_err));
+    else
+        B200_CUDA_OK(launch_pdl(k_batch_prep<false>, dim3(blocks), dim3(threads), 0, s, in, p, seed, step, row_offset, keep_tape,
+                                train ? 1 : 0, c->cfg.max_batch_nnz, xt, row_sum_out, mark, mark_step, n_items,
+                                (int64_t*)nullptr, (int32_t*)nullptr, c->d_err));
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
@@ -814,8 +873,10 @@ __global__ void __launch_bounds__(128)
 k_target_fixup(BatchView tgt, __half* __restrict__ PT, int64_t ldp, const float* __restrict__ T,
                const float* __restrict__ lse, const __half* __restrict__ h16, int64_t ldh,
                const __half* __restrict__ W16, int64_t ldw, const float* __restrict__ bias, int H,
-               float log2_scale, float* __restrict__ loss_row, int* __restrict__ err) {
+               float log2_scale, float* __restrict__ loss_row, int* __restrict__ err, LossTail lt) {
     __shared__ float sh[4];
+    __shared__ float s1[128], s2[128];
+    __shared__ int s_last;
     pdl_sync();
     const int u = blockIdx.x;
     const float Tu = T[u];
@@ -850,14 +911,52 @@ k_target_fixup(BatchView tgt, __half* __restrict__ PT, int64_t ldp, const float*
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) loss_row[u] = -((sh[0] + sh[1]) + (sh[2] + sh[3]));
+    if (!lt.loss_out) return;
+    // the CTA that finishes last closes the loss (what k_loss_final does in its own launch): fixed-order tree over the
+    // per-row terms, so the value does not depend on which CTA that is
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(lt.ticket, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float a1 = 0.f, a2 = 0.f;
+    for (int i = threadIdx.x; i < lt.B; i += 128) {
+        a1 += __ldcg(loss_row + i);
+        if (lt.kl_row) a2 += __ldcg(lt.kl_row + i);
+    }
+    s1[threadIdx.x] = a1;
+    s2[threadIdx.x] = a2;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            s1[threadIdx.x] += s1[threadIdx.x + o];
+            s2[threadIdx.x] += s2[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float nll = s1[0] * lt.inv_Bg, kld = s2[0] * lt.inv_Bg;
+        float reg = 0.f;
+        if (lt.norms)
+            for (int t = 0; t < lt.n_tensors; ++t) reg += lt.norms[t];
+        lt.loss_out[0] = nll + lt.beta * kld + lt.lam * reg;
+        lt.loss_out[1] = nll;
+        lt.loss_out[2] = kld;
+        lt.loss_out[3] = reg;
+        *lt.ticket = 0;
+    }
 }
 
 int launch_target_fixup(Ctx* c, const BatchView& tgt, __half* PT, int64_t ldp, const float* T, const float* lse,
                         const __half* h16, int64_t ldh, const __half* W16, int64_t ldw, const float* bias, int H,
-                        float* loss_row, cudaStream_t s) {
+                        float* loss_row, cudaStream_t s, const LossTail* tail) {
     if (tgt.B == 0) return 0;
+    LossTail lt = {};
+    if (tail) lt = *tail;
     B200_CUDA_OK(launch_pdl(k_target_fixup, dim3(tgt.B), dim3(128), 0, s, tgt, PT, ldp, T, lse, h16, ldh, W16, ldw, bias, H,
-                            PROB_LOG2_SCALE, loss_row, c->d_err));
+                            PROB_LOG2_SCALE, loss_row, c->d_err, lt));
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;
