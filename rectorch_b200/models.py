@@ -648,7 +648,7 @@ class AETrainer(TorchNNTrainer):
         eng = self._engine
         rank, world = _dist_world()
         B = int(indptr.numel()) - 1
-        nnz = int(indptr[-1])
+        nnz = int(indices.numel())           # == indptr[-1]; read from the shape: indexing a tensor costs microseconds
         beta, lam = self._step_coeffs()
         lr, betas, eps, wd = self._hyper()
         p = float(self.network.dropout.p)
@@ -659,14 +659,15 @@ class AETrainer(TorchNNTrainer):
             eng._sync_weights_if_dirty()
             if getattr(self, "_loss_host", None) is None:
                 self._loss_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+                self._loss_np = self._loss_host.numpy()
             eng.adam_steps += 1
-            with torch.cuda.device(self.device):
-                check(_lib.lib().b200vae_train_step_host(
-                    eng._ctx, ptr(indptr), ptr(indices), ptr(values), B, float(beta), float(lam), p, draw_seed(),
-                    eng.adam_steps, float(lr), float(wd), ptr(self._loss_host), stream_ptr()))
+            # the library makes the context's device current for the call (DeviceGuard), so no torch.cuda.device here
+            check(_lib.lib().b200vae_train_step_host(
+                eng._ctx, ptr(indptr), ptr(indices), ptr(values), B, float(beta), float(lam), p, draw_seed(),
+                eng.adam_steps, float(lr), float(wd), ptr(self._loss_host), stream_ptr(self.device)))
             self._step_tensor += 1.0
             self._after_step()
-            return float(self._loss_host[0])
+            return float(self._loss_np[0])
         if B % world != 0:
             raise ValueError("the global batch (%d rows) must be divisible by the world size (%d)" % (B, world))
         st = getattr(self, "_stage", None)
