@@ -4,12 +4,18 @@
 // (metrics.py:140-147, 190-196, 233-238, 276-285; evaluation.py:102-104): only
 // n_metrics x B floats leave the device.
 //
-// One CTA (256 threads) per user row:
+// One CTA (256 threads) per user row.
+//   Long rows (n_items >= 16384) -- ONE read of the scores instead of seven:
+//   0. 4096 keys are sampled from the row (512 evenly spaced 32-byte sectors); a radix select IN SHARED MEMORY finds
+//      the sample's r-th largest key tau, r chosen so that ~k + 4 sigma + margin row elements lie above it;
+//      one coalesced pass over the row appends every key > tau to a shared-memory candidate list (<= 4096);
+//      if the list holds at least k entries it contains the exact top-k (all ties of the k-th key included) and goes
+//      straight to step 3.  Otherwise (heavy ties, adversarial rows; P ~ 3e-4 on continuous scores) fall through:
 //   1. 4 passes of an 8-bit histogram over the order-preserving uint32 image of the scores
 //      narrow down the k-th largest key T and the number of ties at T to keep;
 //   2. all keys > T plus the lowest-index ties are compacted into shared memory
 //      (deterministic tie rule: smaller item id first -- argpartition's is unspecified);
-//   3. a bitonic sort of the <=1024 candidates gives the ranked list (needed by ndcg/mrr);
+//   3. a bitonic sort of the candidates (key descending, item id ascending) gives the ranked list (needed by ndcg/mrr);
 //   4. membership of each ranked item in the held-out CSR row is a binary search;
 //   5. each requested (metric, k) is reduced from the ranked hit list.
 #include "ctx.cuh"
@@ -18,18 +24,54 @@ namespace b200 {
 
 constexpr int TOPK_MAX = 1024;
 constexpr int TOPK_THREADS = 256;
+constexpr int TOPK_CAND = 4096;        // candidate capacity of the single-read path
+constexpr int TOPK_SAMPLE = 4096;      // sampled keys (alias the candidate storage)
+constexpr int TOPK_SAMPLE_MIN_I = 16384;
 
 __device__ __forceinline__ uint32_t f2key(float x) {
     uint32_t u = __float_as_uint(x);
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// k-th largest of n keys served by key_at(j): MSB-first radix select, 4 passes of an 8-bit shared-memory histogram.
+// Leaves the key in *s_prefix and the number of ties at that key still to take in *s_remaining.  Block-uniform.
+template <typename F>
+__device__ __forceinline__ void radix_select(F key_at, int n, uint32_t k, unsigned int* hist, uint32_t* s_prefix,
+                                             uint32_t* s_remaining) {
+    const int tid = threadIdx.x;
+    if (tid == 0) { *s_prefix = 0; *s_remaining = k; }
+    uint32_t mask = 0;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        hist[tid] = 0;
+        __syncthreads();
+        const uint32_t prefix = *s_prefix;
+        for (int j = tid; j < n; j += TOPK_THREADS) {
+            uint32_t u = key_at(j);
+            if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t rem = *s_remaining, above = 0;
+            int b = 255;
+            for (; b > 0; --b) {
+                if (above + hist[b] >= rem) break;
+                above += hist[b];
+            }
+            *s_remaining = rem - above;
+            *s_prefix = prefix | ((uint32_t)b << shift);
+        }
+        mask |= 0xFFu << shift;
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(TOPK_THREADS)
 k_topk_metrics(const float* __restrict__ scores, int I, BatchView gt, const int32_t* __restrict__ kinds,
                const int32_t* __restrict__ ks, int n_metrics, int kmax, float* __restrict__ out,
-               int32_t* __restrict__ topk_idx) {
+               int32_t* __restrict__ topk_idx, int sampling) {
     __shared__ unsigned int hist[256];
-    __shared__ unsigned long long cand[TOPK_MAX];
+    __shared__ unsigned long long cand[TOPK_CAND];
     __shared__ float hitval[TOPK_MAX];
     __shared__ uint32_t s_prefix, s_remaining;
     __shared__ unsigned int s_count;
@@ -39,32 +81,53 @@ k_topk_metrics(const float* __restrict__ scores, int I, BatchView gt, const int3
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const float* row = scores + (int64_t)r * I;
 
-    // ---- 1. radix select ------------------------------------------------------------------
-    if (tid == 0) { s_prefix = 0; s_remaining = (uint32_t)kmax; }
-    uint32_t mask = 0;
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        hist[tid] = 0;
-        __syncthreads();
-        const uint32_t prefix = s_prefix;
-        for (int j = tid; j < I; j += TOPK_THREADS) {
-            uint32_t u = f2key(row[j]);
-            if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+    // ---- 0. single-read path ----------------------------------------------------------------
+    int n_sort = 0;                   // > 0: cand[0 .. n_sort) is ready for the sort
+    if (sampling && I >= TOPK_SAMPLE_MIN_I) {
+        uint32_t* samp = reinterpret_cast<uint32_t*>(cand);
+        for (int i = tid; i < TOPK_SAMPLE; i += TOPK_THREADS) {
+            const int cl = i >> 3;                                            // 512 clusters of 8 consecutive scores
+            const int j = (int)(((int64_t)cl * I) / (TOPK_SAMPLE / 8)) + (i & 7);
+            samp[i] = (j < I) ? f2key(row[j]) : 0u;
         }
         __syncthreads();
-        if (tid == 0) {
-            uint32_t rem = s_remaining, above = 0;
-            int b = 255;
-            for (; b > 0; --b) {
-                if (above + hist[b] >= rem) break;
-                above += hist[b];
+        const float f = (float)TOPK_SAMPLE / (float)I;
+        const float mean = f * (float)kmax;
+        const int rs = min(TOPK_SAMPLE, (int)ceilf(mean + 4.f * sqrtf(mean) + 6.f));
+        radix_select([&](int j) { return samp[j]; }, TOPK_SAMPLE, (uint32_t)rs, hist, &s_prefix, &s_remaining);
+        const uint32_t tau = s_prefix;
+        if (tid == 0) s_count = 0;
+        __syncthreads();              // the sample is dead from here: cand is reused for the candidates
+        auto take = [&](float x, int j) {
+            const uint32_t u = f2key(x);
+            if (u > tau) {
+                const unsigned int p = atomicAdd(&s_count, 1u);
+                if (p < (unsigned)TOPK_CAND)
+                    cand[p] = ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)j);
             }
-            s_remaining = rem - above;
-            s_prefix = prefix | ((uint32_t)b << shift);
+        };
+        int j = tid;
+        for (; j + 7 * TOPK_THREADS < I; j += 8 * TOPK_THREADS) {     // 8 independent loads in flight per thread
+            float x[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) x[q] = __ldcs(row + j + q * TOPK_THREADS);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) take(x[q], j + q * TOPK_THREADS);
         }
-        mask |= 0xFFu << shift;
+        for (; j < I; j += TOPK_THREADS) take(row[j], j);
+        __syncthreads();
+        const unsigned int c = s_count;
+        if (c >= (unsigned)kmax && c <= (unsigned)TOPK_CAND) {
+            n_sort = 1;
+            while (n_sort < (int)c) n_sort <<= 1;
+            for (int i = (int)c + tid; i < n_sort; i += TOPK_THREADS) cand[i] = 0ull;   // padding sorts last
+        }
         __syncthreads();
     }
+
+    if (n_sort == 0) {
+    // ---- 1. radix select ------------------------------------------------------------------
+    radix_select([&](int j) { return f2key(row[j]); }, I, (uint32_t)kmax, hist, &s_prefix, &s_remaining);
     const uint32_t T = s_prefix;
     const uint32_t n_ties = s_remaining;         // ties at T to keep (>= 1)
     const uint32_t n_gt = (uint32_t)kmax - n_ties;
@@ -114,10 +177,11 @@ k_topk_metrics(const float* __restrict__ scores, int I, BatchView gt, const int3
         }
     }
     __syncthreads();
-
-    // ---- 3. bitonic sort, descending, over the next power of two >= kmax ---------------------
-    int n_sort = 1;
+    n_sort = 1;
     while (n_sort < kmax) n_sort <<= 1;
+    }   // multi-pass path
+
+    // ---- 3. bitonic sort, descending, over a power of two >= the number of candidates ----------
     for (int size = 2; size <= n_sort; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int i = tid; i < n_sort; i += TOPK_THREADS) {
@@ -197,7 +261,9 @@ int launch_topk_metrics(Ctx* c, const float* scores, int I, const BatchView& gt,
     B200_REQUIRE(kmax >= 1 && kmax <= TOPK_MAX && kmax <= I, B200VAE_EINVAL,
                  "topk: k must be in [1, min(%d, n_items)] (got %d)", TOPK_MAX, kmax);
     B200_REQUIRE(n_metrics <= TOPK_THREADS, B200VAE_EINVAL, "topk: too many metrics");
-    k_topk_metrics<<<gt.B, TOPK_THREADS, 0, s>>>(scores, I, gt, kinds, ks, n_metrics, kmax, out, topk_idx);
+    const char* e = getenv("B200VAE_TOPK_SAMPLE");          // 0: always the multi-pass radix select (tests, comparisons)
+    const int sampling = (e && atoi(e) == 0) ? 0 : 1;
+    k_topk_metrics<<<gt.B, TOPK_THREADS, 0, s>>>(scores, I, gt, kinds, ks, n_metrics, kmax, out, topk_idx, sampling);
     note(c, __func__, s);
     B200_CUDA_OK(cudaGetLastError());
     return 0;

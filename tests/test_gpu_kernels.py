@@ -213,6 +213,29 @@ def test_topk_metrics_vs_oracle(B, I):
         assert np.nanmax(np.abs(a - b)) < 1e-5 if np.isfinite(b).any() else True, m
 
 
+@pytest.mark.parametrize("ties", [False, True])
+def test_topk_single_read_path_equals_multipass(ties, monkeypatch):
+    """Rows of >= 16384 items take the single-read path (sampled threshold + one pass); it must rank exactly like the
+    multi-pass radix select (B200VAE_TOPK_SAMPLE=0) -- including on rows full of ties, where the sampled threshold
+    leaves fewer than k candidates and the kernel falls back, and with -inf masked items."""
+    from rectorch_b200.metrics import Metrics
+    rng = np.random.default_rng(11)
+    B, I = 96, 30000
+    x = rng.standard_normal((B, I)).astype(np.float32)
+    if ties:
+        x = np.round(x * 2) / 2          # ~13 distinct values
+        x[5] = 0.25                      # one constant row
+    x[rng.random((B, I)) < 0.02] = -np.inf
+    scores = torch.from_numpy(x).cuda()
+    gt = torch.from_numpy((rng.random((B, I)) < 40.0 / I).astype(np.float32)).cuda()
+    mets = ["recall@1", "recall@20", "ndcg@100", "mrr@50", "hit@5", "recall@1000", "ndcg@1000"]
+    new = Metrics.compute(scores, gt, mets)
+    monkeypatch.setenv("B200VAE_TOPK_SAMPLE", "0")
+    old = Metrics.compute(scores, gt, mets)
+    for m in mets:
+        assert np.array_equal(np.asarray(new[m]), np.asarray(old[m]), equal_nan=True), m
+
+
 def test_topk_full_size_properties():
     """BASELINE-size row (I = 50000): size-independent properties -- recall@k is monotone in k,
     hit@k = (recall@k > 0), ndcg in [0,1], and recall@I == 1 is not required (k <= 1024)."""
