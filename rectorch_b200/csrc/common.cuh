@@ -195,6 +195,7 @@ struct TcEpi {
     int part_rows = 0;                 // capacity of the partial buffers (rows of M floats)
     const float* lse = nullptr;        // TC_EPI_PROB
     float prob_log2_scale = PROB_LOG2_SCALE;
+    const float* row_bias = nullptr;   // TC_EPI_STORE with transpose_out: added per ROW m of the product (C[n*ldc + m] += row_bias[m])
     float* bias_grad = nullptr;        // TC_EPI_STORE: column `bias_col` of the product goes here
     int bias_col = -1;
     int split_k = 1;                   // TC_EPI_STORE: partial products C[s] at C + s*split_stride

@@ -149,6 +149,7 @@ struct Ctx {
     int32_t* gl_sp = nullptr;
     float*   gl_xt = nullptr;
     int64_t  gl_rows = 0, gl_nnz = 0;
+    bool predict_transposed = true;   // score GEMM computed as W_d h^T with coalesced stores (B200VAE_PREDICT_T=0: h W_d^T)
     bool fuse_small = true;           // offset scans inside batch_prep, loss closed by the fix-up kernel (B200VAE_FUSE_SMALL=0: own launches)
     int wd_chunks = 0;                // > 1: dW_d GEMM + decoder-output Adam in item chunks on the side stream (B200VAE_WD_CHUNKS)
     int wd_chunk_ctas = 8;            // CTAs per SM of the chunked Adam launches (B200VAE_WD_CHUNK_CTAS)

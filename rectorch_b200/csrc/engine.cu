@@ -774,10 +774,18 @@ static int predict(Ctx* c, const int32_t* row_ids, int B, int remove_train, int 
     const Layer& DL = c->dec.back();
     if (c->tc_dec) {
         TcEpi e;
-        e.bias = c->w + DL.b_off;
         B200_CHECK(launch_to_f16(c, st.h_last, c->h16, B, st.H, st.H, s));
         B200_CHECK(wait_wd16(c, s));
-        B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->h16, st.H, 0, c->wd16, st.H, 0, scores, I, B, I, st.H, e, s));
+        if (c->predict_transposed) {
+            // scores^T = W_d h^T: the item index sits on the TMEM lanes, so every epilogue store instruction writes 32
+            // consecutive scores of one user (a full 128-byte line) instead of 16 bytes in each of 32 users' rows
+            e.transpose_out = 1;
+            e.row_bias = c->w + DL.b_off;
+            B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->wd16, st.H, 0, c->h16, st.H, 0, scores, I, I, B, st.H, e, s));
+        } else {
+            e.bias = c->w + DL.b_off;
+            B200_CHECK(launch_tc_gemm(c, TC_EPI_STORE, c->h16, st.H, 0, c->wd16, st.H, 0, scores, I, B, I, st.H, e, s));
+        }
     } else {
         B200_CHECK(linear_fwd(c, st.h_last, B, DL, scores, s));
     }
@@ -828,6 +836,7 @@ int b200vae_ctx_create(b200vae_ctx** out, const b200vae_config* cfg) {
     if (const char* e = getenv("B200VAE_OVERLAP")) c->overlap = c->overlap_host = atoi(e) & 7;
     if (const char* e = getenv("B200VAE_HOST_OVERLAP")) c->overlap_host = atoi(e) & 7;
     if (const char* e = getenv("B200VAE_FUSE_SMALL")) c->fuse_small = atoi(e) != 0;
+    if (const char* e = getenv("B200VAE_PREDICT_T")) c->predict_transposed = atoi(e) != 0;
     if (const char* e = getenv("B200VAE_WD_CHUNKS")) c->wd_chunks = std::max(0, std::min(64, atoi(e)));
     if (const char* e = getenv("B200VAE_WD_CHUNK_CTAS")) c->wd_chunk_ctas = std::max(1, std::min(8, atoi(e)));
     if (const char* e = getenv("B200VAE_WD_DISCARD")) c->wd_discard = atoi(e) != 0;

@@ -203,6 +203,7 @@ struct TcArgs {
     float* part_sum;
     const float* lse;
     float* bias_grad;
+    const float* row_bias;  // STORE + transpose_out: per-row (m) addend, or nullptr
     float out_scale;        // STORE: D * out_scale (* *out_scale_ptr): exact power-of-two un-scaling of fp16 operands
     const float* out_scale_ptr;
     int act;                // STORE: tanh after the bias
@@ -341,9 +342,10 @@ __device__ __forceinline__ void epi_chunk(const TcArgs& a, const float* v, const
         if (m < a.M) {
             if (m < a.n_store) {
                 float* dst = reinterpret_cast<float*>(a.C) + (int64_t)(n0 + c0) * a.ldc + m;
+                const float rb = a.row_bias ? a.row_bias[m] : 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                    if (i < nc) dst[(int64_t)i * a.ldc] = v[i] * oscale;
+                    if (i < nc) dst[(int64_t)i * a.ldc] = fmaf(v[i], oscale, rb);
             } else if (m == a.bias_col) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
@@ -809,6 +811,7 @@ int launch_tc_gemm(Ctx* c, int mode, const void* A, int64_t lda, int a_mn, const
     a.split_stride = e.split_stride;
     a.bias = e.bias; a.part_max = e.part_max; a.part_sum = e.part_sum; a.lse = e.lse;
     a.bias_grad = e.bias_grad;
+    a.row_bias = e.row_bias;
     a.bias_col = e.bias_col;
     a.transpose_out = e.transpose_out;
     a.n_store = (e.bias_col >= 0) ? e.bias_col : (e.transpose_out ? M : N);
