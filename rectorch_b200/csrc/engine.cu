@@ -1402,9 +1402,14 @@ int b200vae_decode(b200vae_ctx* ctx, const float* z, int32_t B, float* scores, v
     const Layer& DL = c->dec.back();
     if (c->tc_dec) {
         TcEpi e;
-        e.bias = c->w + DL.b_off;
         B200_CHECK(launch_to_f16(c, h, c->h16, B, DL.in, DL.in, s));
         B200_CHECK(wait_wd16(c, s));
+        if (c->predict_transposed) {      // as in predict(): scores^T = W_d h^T, coalesced score stores
+            e.transpose_out = 1;
+            e.row_bias = c->w + DL.b_off;
+            return launch_tc_gemm(c, TC_EPI_STORE, c->wd16, DL.in, 0, c->h16, DL.in, 0, scores, c->n_items, c->n_items, B, DL.in, e, s);
+        }
+        e.bias = c->w + DL.b_off;
         return launch_tc_gemm(c, TC_EPI_STORE, c->h16, DL.in, 0, c->wd16, DL.in, 0, scores, c->n_items, B, c->n_items, DL.in, e, s);
     }
     return linear_fwd(c, h, B, DL, scores, s);
