@@ -323,5 +323,6 @@ def test_deterministic_mode_is_bit_reproducible():
     assert torch.equal(w1, w2) and torch.equal(m1, m2) and torch.equal(v1, v2)
     l3, w3, _, _ = run(False)
     assert np.allclose(l1, l3, rtol=1e-5)
-    assert (w1 - w3).abs().max().item() < 5e-3      # a handful of Adam sign flips on ~0 gradients at lr 1e-3, 4 steps
-    assert (w1 - w3).abs().mean().item() < 1e-5
+    # Adam turns a sign flip of a ~0 gradient into a 2 * lr difference: at most 4 steps * 2e-3 on an element, on very few
+    assert (w1 - w3).abs().max().item() < 1e-2
+    assert (w1 - w3).abs().mean().item() < 1e-4
