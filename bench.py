@@ -78,11 +78,14 @@ def load_ncu_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).  nvidia-smi needs 0.1-0.3 s
+    to print its first sample, so it is started before a pre-roll of untimed steps (the GPU stays under load) and its
+    time-stamped samples are filtered to the wall-clock window of the timed region afterwards."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 10
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
@@ -91,36 +94,53 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.PERIOD_MS)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    @staticmethod
+    def now():
+        import datetime
+        return datetime.datetime.now()
+
+    def stop(self, t0=None, t1=None):
+        """t0 / t1: ClockSampler.now() taken (after a device sync) at both ends of the timed region."""
+        import datetime
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             out = self.proc.communicate(timeout=5)[0]
         except Exception:
             self.proc.kill()
             out = ""
-        sm, smax, reasons = [], None, set()
+        rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1]))
-                smax = float(f[2])
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+            except ValueError:
+                ts = None
+            try:
+                rows.append((ts, float(f[1]), float(f[2]), [v.lower().startswith("active") for v in f[4:8]]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        inside = rows
+        window = "whole sampling period (pre-roll + timed region)"
+        if t0 is not None and t1 is not None:
+            slack = datetime.timedelta(milliseconds=self.PERIOD_MS)
+            sel = [r for r in rows if r[0] is not None and t0 - slack <= r[0] <= t1 + slack]
+            if sel:
+                inside, window = sel, "timed region"
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({n for r in inside for n, on in zip(names, r[3]) if on})
+        sm = [r[1] for r in inside]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": inside[-1][2] if inside else None,
+                "reasons": reasons, "samples": len(sm), "samples_total": len(rows), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -432,15 +452,26 @@ def run_b200(args, cfg):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    t_w = time.perf_counter()
     for i in range(W):
         step(i)
     barrier()
-    eng.launch_count(reset=True)
+    # pre-roll: ~0.3 s of untimed steps with nvidia-smi already running, so that its samples cover the timed region
+    # (the same count on every rank: it is derived from the slowest rank's warm-up)
+    est = torch.tensor([(time.perf_counter() - t_w) / max(W, 1)], device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MAX)
+    n_pre = int(min(2000, max(0, 0.3 / max(float(est.item()), 1e-5))))
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for i in range(n_pre):
+        step(W + K + i)
+    barrier()
+    eng.launch_count(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_region0 = ClockSampler.now()
     ev0.record()
     for i in range(W, W + K):
         step(i)
@@ -448,8 +479,9 @@ def run_b200(args, cfg):
         torch.cuda.current_stream(dev).wait_stream(model._comm_stream)
     ev1.record()
     barrier()
+    t_region1 = ClockSampler.now()
     ms_total = ev0.elapsed_time(ev1)
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(t_region0, t_region1) if rank == 0 else None
     launches = eng.launch_count()
     if world > 1:
         t = torch.tensor([ms_total], device=dev)
@@ -601,7 +633,8 @@ def run_b200(args, cfg):
                     args.config, cfg["arch"], n_users, I, gen_s, B), "global_batch": B * world, "parallelism": par,
                     "schedule": "decoder-output Adam on a second stream beside the encoder backward" if world == 1 else
                                 "W_d exchange + sharded Adam on a side stream, overlapped with the encoder backward and the next step's encoder",
-                    "l2": "no flush: per-step working set (4 x %d MB arenas) exceeds the 126 MB L2" % (4 * P // 1000000)},
+                    "l2": "no flush: per-step working set (4 x %d MB arenas) exceeds the 126 MB L2" % (4 * P // 1000000),
+                    "pre_roll_steps": int(n_pre)},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "host_issue_us_per_step": host_us,
                 "roofline": roof_dom, "roofline_k4": roof_k4,
                 "kernel_ms": {n: float(v) for n, v in zip(names, kms)},
@@ -688,17 +721,26 @@ def run_eval(args, cfg):
     torch.cuda.synchronize(dev)
     clocks = ClockSampler(dev.index or 0)
     clocks.start()
+    t_w = time.perf_counter()
+    evaluate(model, sampler, mets)
+    torch.cuda.synchronize(dev)
+    per_eval = max(time.perf_counter() - t_w, 1e-4)
+    for _ in range(int(min(200, 0.3 / per_eval))):          # pre-roll under load while nvidia-smi starts up
+        evaluate(model, sampler, mets)
+    reps = int(max(3, min(100, 0.1 / per_eval)))            # a timed region of >= ~0.1 s
+    torch.cuda.synchronize(dev)
     model._engine.launch_count(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 3
+    t_region0 = ClockSampler.now()
     ev0.record()
     for _ in range(reps):
         res = evaluate(model, sampler, mets)
     ev1.record()
     torch.cuda.synchronize(dev)
+    t_region1 = ClockSampler.now()
     ms = ev0.elapsed_time(ev1) / (reps * n_b)
     launches = model._engine.launch_count()
-    clk = clocks.stop()
+    clk = clocks.stop(t_region0, t_region1)
     t0 = time.perf_counter()
     for _ in range(reps):
         evaluate(model, sampler, mets)
