@@ -106,7 +106,6 @@ class ClockSampler:
 
     def stop(self, t0=None, t1=None):
         """t0 / t1: ClockSampler.now() taken (after a device sync) at both ends of the timed region."""
-        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         time.sleep(0.05)
@@ -116,6 +115,13 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
             out = ""
+        return self.parse(out, t0, t1)
+
+    @classmethod
+    def parse(cls, out, t0=None, t1=None):
+        """nvidia-smi csv lines -> the `clocks` object of the bench line; samples outside [t0, t1] (+- one period) are
+        dropped when at least one falls inside."""
+        import datetime
         rows = []
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
@@ -132,7 +138,7 @@ class ClockSampler:
         inside = rows
         window = "whole sampling period (pre-roll + timed region)"
         if t0 is not None and t1 is not None:
-            slack = datetime.timedelta(milliseconds=self.PERIOD_MS)
+            slack = datetime.timedelta(milliseconds=cls.PERIOD_MS)
             sel = [r for r in rows if r[0] is not None and t0 - slack <= r[0] <= t1 + slack]
             if sel:
                 inside, window = sel, "timed region"
