@@ -269,3 +269,24 @@ def test_DataProcessing_pipeline_invariants(tmp_path):
     assert tr.data.min() > 1.0                                              # threshold applied (values kept: no topn)
     full = reader.load_data("full")
     assert full.shape == (len(uids), len(iids)) and full.nnz == tr.nnz + vtr.nnz + vte.nnz + ttr.nnz + tte.nnz
+
+
+def test_DataProcessing_pandas_and_plain_paths_write_the_same_files(tmp_path, monkeypatch):
+    """Reading / writing go through pandas' C parser and writer when pandas is importable and through plain Python
+    otherwise: both must produce byte-identical output (integer ids, float ratings, a string column, a header)."""
+    import sys
+    rng = np.random.default_rng(5)
+    lines = ["user,item,rating,tag"]
+    for u in range(80):
+        for i in rng.choice(50, size=int(rng.integers(2, 12)), replace=False):
+            lines.append("%d,%d,%s, t%d" % (1000 + u, i, repr(float(rng.integers(1, 11)) / 2), u % 3))
+    raw = "\n".join(lines) + "\n"
+    extra = {"header": 0, "threshold": 1.0, "u_min": 2, "i_min": 2, "heldout": 10, "test_prop": 0.25, "seed": 3}
+    os.makedirs(os.path.join(tmp_path, "a"))
+    os.makedirs(os.path.join(tmp_path, "b"))
+    _, _, with_pandas = _process(os.path.join(tmp_path, "a"), raw, extra, sep=",")
+    monkeypatch.setitem(sys.modules, "pandas", None)            # `import pandas` now raises ImportError
+    _, _, plain = _process(os.path.join(tmp_path, "b"), raw, extra, sep=",")
+    assert set(with_pandas) == set(plain)
+    for name in plain:
+        assert with_pandas[name] == plain[name], name
