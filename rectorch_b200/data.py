@@ -6,11 +6,13 @@ CSV files are parsed and turned into CSR by the multi-threaded host ingest of li
 (``b200vae_csv_*``, csrc/ingest.cu) instead of ``pd.read_csv`` + ``csr_matrix((values, (rows, cols)))``.
 The matrices go straight into :class:`rectorch_b200.samplers.DataSampler`, which uploads them to HBM once.
 
-``DataProcessing(data_config).process()`` (data.py:46-325) is restated with numpy only: the reference's version
+``DataProcessing(data_config).process()`` (data.py:46-325) is restated on numpy arrays: the reference's version
 depends on pandas group-by semantics that current pandas releases no longer have (``groupby(..., as_index=False)
 .size()`` returning a Series), so it cannot run in this environment; the restatement follows its steps and its
 ``numpy.random`` call sequence one by one and is pinned by the exact file contents the reference's own tests expect
-(tests/test_data.py:14-101, 280-350).
+(tests/test_data.py:14-101, 280-350).  Only the two ends use pandas, when it is importable: ``pd.read_csv`` for the raw
+file and ``DataFrame.to_csv`` for the output (what the reference itself calls); a plain-Python path writes
+byte-identical files without it.
 
 Not mirrored: ``DataReader.load_data_as_dict`` (sequence view used by SVAE only).
 """
