@@ -458,16 +458,21 @@ def run_b200(args, cfg):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    t_w = time.perf_counter()
     for i in range(W):
         step(i)
     barrier()
-    # pre-roll: ~0.3 s of untimed steps with nvidia-smi already running, so that its samples cover the timed region
-    # (the same count on every rank: it is derived from the slowest rank's warm-up)
-    est = torch.tensor([(time.perf_counter() - t_w) / max(W, 1)], device=dev)
+    # pre-roll: ~0.3 s of untimed steps with nvidia-smi already running (it needs 50-300 ms to print its first sample),
+    # so that its samples cover the timed region.  The step time is estimated on 5 steady-state steps AFTER the
+    # warm-up (the first warm-up step pays for context creation), and the count is the same on every rank: it is
+    # derived from the slowest rank's estimate.
+    t_w = time.perf_counter()
+    for i in range(5):
+        step(W + K + i)
+    barrier()
+    est = torch.tensor([(time.perf_counter() - t_w) / 5.0], device=dev)
     if world > 1:
         dist.all_reduce(est, op=dist.ReduceOp.MAX)
-    n_pre = int(min(2000, max(0, 0.3 / max(float(est.item()), 1e-5))))
+    n_pre = int(min(2000, max(50, 0.3 / max(float(est.item()), 1e-5))))
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
