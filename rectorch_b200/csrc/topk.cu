@@ -7,7 +7,7 @@
 // One CTA (256 threads) per user row.
 //   Long rows (n_items >= 16384) -- ONE read of the scores instead of seven:
 //   0. 4096 keys are sampled from the row (512 evenly spaced 32-byte sectors); a radix select IN SHARED MEMORY finds
-//      the sample's r-th largest key tau, r chosen so that ~k + 4 sigma + margin row elements lie above it;
+//      the sample's r-th largest key tau, r chosen so that ~k + 6 sigma + margin row elements lie above it;
 //      one coalesced pass over the row appends every key > tau to a shared-memory candidate list (<= 4096);
 //      if the list holds at least k entries it contains the exact top-k (all ties of the k-th key included) and goes
 //      straight to step 3.  Otherwise (heavy ties, adversarial rows; P ~ 3e-4 on continuous scores) fall through:
@@ -93,7 +93,9 @@ k_topk_metrics(const float* __restrict__ scores, int I, BatchView gt, const int3
         __syncthreads();
         const float f = (float)TOPK_SAMPLE / (float)I;
         const float mean = f * (float)kmax;
-        const int rs = min(TOPK_SAMPLE, (int)ceilf(mean + 4.f * sqrtf(mean) + 6.f));
+        // 6 sigma + 8: the sample is 512 clusters of 8 neighbouring items, whose scores are correlated (similar
+        // popularity), so its effective size is below 4096; a larger margin only lengthens the candidate list a little
+        const int rs = min(TOPK_SAMPLE, (int)ceilf(mean + 6.f * sqrtf(mean) + 8.f));
         radix_select([&](int j) { return samp[j]; }, TOPK_SAMPLE, (uint32_t)rs, hist, &s_prefix, &s_remaining);
         const uint32_t tau = s_prefix;
         if (tid == 0) s_count = 0;
