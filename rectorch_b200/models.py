@@ -529,12 +529,13 @@ class AETrainer(TorchNNTrainer):
         """Mean and standard error of the per-user validation metric.  Under data parallelism every rank evaluates
         its own shard of the validation users: the sums are all-reduced so that every rank logs / compares the same
         numbers (and takes the same best-checkpoint decision)."""
+        if _dist_world()[1] == 1:           # exactly the reference's expressions (models.py:392-394, 884-886)
+            return np.mean(valid_res), np.std(valid_res) / np.sqrt(len(valid_res))
         res = np.asarray(valid_res, dtype=np.float64)
-        n, s1, s2 = float(res.size), float(np.nansum(res)), float(np.nansum(res * res))
-        if _dist_world()[1] > 1:
-            t = torch.tensor([n, s1, s2], dtype=torch.float64, device=self.device)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            n, s1, s2 = t.tolist()
+        t = torch.tensor([float(res.size), float(np.sum(res)), float(np.sum(res * res))], dtype=torch.float64,
+                         device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        n, s1, s2 = t.tolist()
         mu = s1 / max(n, 1.0)
         var = max(s2 / max(n, 1.0) - mu * mu, 0.0)
         return mu, np.sqrt(var) / np.sqrt(max(n, 1.0))
